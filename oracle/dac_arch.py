@@ -1,0 +1,252 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+CPU restatement, in plain PyTorch fp32, of the third-party backbone the reference
+pulls in with ``import dac`` (PyPI ``descript-audio-codec``, version UNPINNED by
+the reference: the only mention is a ``pip install`` docstring at
+Training/compare_dacvsproposal_3.py:12; call sites
+Training/compare_dacvsproposal_3.py:344-350 and
+Evaluation/dac_vcpwq_proposed6_latency.py:527-535).
+
+PARITY UNPINNED for this file: the ``dac`` package is not installed in the build
+container, there is no network, and the reference holds no test, fixture or
+golden vector at that boundary.  The restatement follows the published 24 kHz
+configuration of descript-audio-codec 1.0.0 and is
+anchored only on what the reference's committed result JSON pins:
+``tps = 75`` and ``bins = 1024``
+(Evaluation/eval_vs_dac24_with_vcpwq_rawPSNR_latency/
+eval_all_vs_dac24_vcpwq_rawPSNR_latency.json:11-12) and ``n_q <= 32``
+(Evaluation/compare_dacvsproposal_3.5_eval.py:75) -- see tests/test_oracle_cpu.py.
+
+State-dict keys mirror the package's (old-style weight-norm ``weight_g`` /
+``weight_v``; ``block.N`` / ``model.N`` Sequential indices) so that checkpoints
+written by the reference's trainers (keys ``A_ENC.* A_QUANT.* T_ENC.* T_DEC.*``,
+Training/compare_dacvsproposal_3.py:442-447) load unchanged.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# 24 kHz configuration (Appendix A)
+ENCODER_DIM = 64
+ENCODER_RATES = (2, 4, 5, 8)
+DECODER_DIM = 1536
+DECODER_RATES = (8, 5, 4, 2)
+N_CODEBOOKS = 32
+CODEBOOK_SIZE = 1024
+CODEBOOK_DIM = 8
+SAMPLE_RATE = 24000
+LATENT_DIM = ENCODER_DIM * 2 ** len(ENCODER_RATES)  # 1024
+HOP = 320
+
+
+def _wn(module: nn.Module) -> nn.Module:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.nn.utils.weight_norm(module)
+
+
+def wn_conv(cin, cout, k, stride=1, dilation=1, padding=0):
+    return _wn(nn.Conv1d(cin, cout, k, stride=stride, dilation=dilation, padding=padding))
+
+
+def wn_convT(cin, cout, k, stride=1, padding=0):
+    return _wn(nn.ConvTranspose1d(cin, cout, k, stride=stride, padding=padding))
+
+
+def snake(x: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    """x + 1/(alpha + 1e-9) * sin(alpha x)^2, alpha broadcast over [1, C, 1]."""
+    shape = x.shape
+    x = x.reshape(shape[0], shape[1], -1)
+    x = x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+    return x.reshape(shape)
+
+
+class Snake1d(nn.Module):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, channels, 1))
+
+    def forward(self, x):
+        return snake(x, self.alpha)
+
+
+class ResidualUnit(nn.Module):
+    def __init__(self, dim: int, dilation: int):
+        super().__init__()
+        pad = ((7 - 1) * dilation) // 2
+        self.block = nn.Sequential(
+            Snake1d(dim),
+            wn_conv(dim, dim, 7, dilation=dilation, padding=pad),
+            Snake1d(dim),
+            wn_conv(dim, dim, 1),
+        )
+
+    def forward(self, x):
+        y = self.block(x)
+        trim = (x.shape[-1] - y.shape[-1]) // 2
+        if trim > 0:
+            x = x[..., trim:-trim]
+        return x + y
+
+
+class EncoderBlock(nn.Module):
+    def __init__(self, dim: int, stride: int):
+        super().__init__()
+        self.block = nn.Sequential(
+            ResidualUnit(dim // 2, 1),
+            ResidualUnit(dim // 2, 3),
+            ResidualUnit(dim // 2, 9),
+            Snake1d(dim // 2),
+            wn_conv(dim // 2, dim, 2 * stride, stride=stride, padding=math.ceil(stride / 2)),
+        )
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class Encoder(nn.Module):
+    def __init__(self, d_model=ENCODER_DIM, strides=ENCODER_RATES, d_latent=LATENT_DIM):
+        super().__init__()
+        layers = [wn_conv(1, d_model, 7, padding=3)]
+        for s in strides:
+            d_model *= 2
+            layers.append(EncoderBlock(d_model, s))
+        layers += [Snake1d(d_model), wn_conv(d_model, d_latent, 3, padding=1)]
+        self.block = nn.Sequential(*layers)
+        self.enc_dim = d_model
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class DecoderBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.block = nn.Sequential(
+            Snake1d(cin),
+            wn_convT(cin, cout, 2 * stride, stride=stride, padding=math.ceil(stride / 2)),
+            ResidualUnit(cout, 1),
+            ResidualUnit(cout, 3),
+            ResidualUnit(cout, 9),
+        )
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class Decoder(nn.Module):
+    def __init__(self, input_channel=LATENT_DIM, channels=DECODER_DIM, rates=DECODER_RATES, d_out=1):
+        super().__init__()
+        layers = [wn_conv(input_channel, channels, 7, padding=3)]
+        out_dim = channels
+        for i, s in enumerate(rates):
+            in_dim = channels // 2 ** i
+            out_dim = channels // 2 ** (i + 1)
+            layers.append(DecoderBlock(in_dim, out_dim, s))
+        layers += [Snake1d(out_dim), wn_conv(out_dim, d_out, 7, padding=3), nn.Tanh()]
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class VectorQuantize(nn.Module):
+    """Factorised, L2-normalised codebook lookup (one DAC quantizer stage)."""
+
+    def __init__(self, input_dim=LATENT_DIM, codebook_size=CODEBOOK_SIZE, codebook_dim=CODEBOOK_DIM):
+        super().__init__()
+        self.codebook_size = codebook_size
+        self.codebook_dim = codebook_dim
+        self.in_proj = wn_conv(input_dim, codebook_dim, 1)
+        self.out_proj = wn_conv(codebook_dim, input_dim, 1)
+        self.codebook = nn.Embedding(codebook_size, codebook_dim)
+
+    def decode_latents(self, latents):
+        b, d, t = latents.shape
+        enc = latents.permute(0, 2, 1).reshape(b * t, d)
+        cb = self.codebook.weight
+        enc_n = F.normalize(enc)
+        cb_n = F.normalize(cb)
+        dist = (
+            enc_n.pow(2).sum(1, keepdim=True)
+            - 2 * enc_n @ cb_n.t()
+            + cb_n.pow(2).sum(1, keepdim=True).t()
+        )
+        idx = (-dist).max(1)[1].reshape(b, t)
+        z_q = F.embedding(idx, cb).transpose(1, 2)
+        return z_q, idx, dist
+
+    def forward(self, z):
+        z_e = self.in_proj(z)
+        z_q, idx, _ = self.decode_latents(z_e)
+        commit = F.mse_loss(z_e, z_q.detach(), reduction="none").mean([1, 2])
+        cbl = F.mse_loss(z_q, z_e.detach(), reduction="none").mean([1, 2])
+        z_q = z_e + (z_q - z_e).detach()
+        z_q = self.out_proj(z_q)
+        return z_q, commit, cbl, idx, z_e
+
+
+class ResidualVectorQuantize(nn.Module):
+    def __init__(self, input_dim=LATENT_DIM, n_codebooks=N_CODEBOOKS, codebook_size=CODEBOOK_SIZE,
+                 codebook_dim=CODEBOOK_DIM, quantizer_dropout=0.0):
+        super().__init__()
+        self.n_codebooks = n_codebooks
+        self.codebook_dim = codebook_dim
+        self.codebook_size = codebook_size
+        self.quantizers = nn.ModuleList(
+            [VectorQuantize(input_dim, codebook_size, codebook_dim) for _ in range(n_codebooks)]
+        )
+        self.quantizer_dropout = quantizer_dropout
+
+    def forward(self, z, n_quantizers=None):
+        z_q = 0
+        residual = z
+        commit = 0
+        cbl = 0
+        codes, latents = [], []
+        if n_quantizers is None:
+            n_quantizers = self.n_codebooks
+        for i, q in enumerate(self.quantizers):
+            if not self.training and i >= n_quantizers:
+                break
+            z_q_i, c_i, l_i, idx_i, z_e_i = q(residual)
+            mask = torch.full((z.shape[0],), fill_value=i, device=z.device) < n_quantizers
+            z_q = z_q + z_q_i * mask[:, None, None]
+            residual = residual - z_q_i
+            commit = commit + (c_i * mask).mean()
+            cbl = cbl + (l_i * mask).mean()
+            codes.append(idx_i)
+            latents.append(z_e_i)
+        return z_q, torch.stack(codes, dim=1), torch.cat(latents, dim=1), commit, cbl
+
+
+class DAC(nn.Module):
+    """24 kHz model container: ``.encoder``, ``.quantizer``, ``.decoder``,
+    ``.encode(x, n_quantizers)``, ``.decode(z)`` as the reference scripts use them
+    (Evaluation/dac_vcpwq_proposed6_latency.py:528-535, :569-570)."""
+
+    def __init__(self):
+        super().__init__()
+        self.sample_rate = SAMPLE_RATE
+        self.hop_length = HOP
+        self.encoder = Encoder()
+        self.quantizer = ResidualVectorQuantize()
+        self.decoder = Decoder()
+
+    def encode(self, x, n_quantizers=None):
+        z = self.encoder(x)
+        return self.quantizer(z, n_quantizers)
+
+    def decode(self, z):
+        return self.decoder(z)
+
+
+def fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Effective weight of an old-style weight-normed conv: g * v / ||v|| over all
+    dims but 0 (torch._weight_norm with dim=0)."""
+    return torch._weight_norm(v, g, 0)

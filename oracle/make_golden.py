@@ -1,0 +1,102 @@
+"""ORACLE golden-vector generator (test infrastructure).
+
+Run HERE (the build container, where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+It executes the REFERENCE's own classes (ast-extracted from
+Evaluation/dac_vcpwq_proposed6_latency.py by oracle/ref_loader.py) on top of the
+DAC-architecture restatement (oracle/dac_arch.py; the third-party package is
+absent) and writes small fixtures to tests/golden/.  The fixtures travel to the
+GPU box; /root/reference does not.
+
+Recipe: module construction under torch.manual_seed(7)
+(reference SEED, Training/compare_dacvsproposal_3.py:50), inputs U(-1,1) from
+torch.Generator().manual_seed(123).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import dac_arch, ref_loader  # noqa: E402
+from oracle.cases import (  # noqa: E402
+    CODEC_CASES, SEARCH_CASES, build_reference_style_model, codec_inputs, search_inputs,
+    chunk_lengths, predictor_inputs,
+)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def weights_fingerprint(model) -> np.ndarray:
+    """A few float64 sums over the state dict, to detect RNG drift between the box
+    that made the goldens and the box that rebuilds the model from the seed."""
+    sd = model.state_dict()
+    keys = sorted(sd.keys())
+    tot = np.array([float(sd[k].double().sum()) for k in keys if sd[k].dtype.is_floating_point])
+    return np.array([tot.sum(), np.abs(tot).sum(), float(len(keys))])
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference not mounted; goldens can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load_reference_classes()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---- full-path cases: reference ProposedEval.forward_eval ----
+    for name, case in CODEC_CASES.items():
+        model = build_reference_style_model(ns["ProposedEval"], case)
+        a, t = codec_inputs(case)
+        tl = a.shape[-1] // dac_arch.HOP
+        with ref_loader.IndexSpy(ns) as spy, torch.no_grad():
+            z_run = model.encode_latents(a, t, books_use=case.get("books_use"))
+            y = model.T_DEC(z_run)
+            za = model.A_ENC(a)
+            qa, a_codes, *_ = model.A_QUANT(za)
+            zt = model.T_ENC(t)
+        books_used = min(case.get("books_use") or case["books"], case["books"])
+        idx = spy.indices(a.shape[0], books_used, chunk_lengths(tl))
+        np.savez_compressed(
+            os.path.join(OUT, f"codec_{name}.npz"),
+            fingerprint=weights_fingerprint(model),
+            idx=idx.numpy().astype(np.int16),
+            a_codes=a_codes.numpy().astype(np.int16),
+            y=y.numpy(), z_run=z_run.numpy().astype(np.float32),
+            za_sample=za[:, ::64, :].numpy(), zt_sample=zt[:, ::64, :].numpy(),
+            qa_sample=qa[:, ::64, :].numpy(),
+        )
+        print("wrote", name, "y", tuple(y.shape), "idx", tuple(idx.shape))
+
+    # ---- module-level: reference CrossPredictor + ResidualVQEMA on seeded tensors ----
+    torch.manual_seed(7)
+    pred = ns["CrossPredictor"](c=1024).eval()
+    zp, za = predictor_inputs()
+    with torch.no_grad():
+        out = pred(zp, za)
+    np.savez_compressed(os.path.join(OUT, "predictor.npz"), out=out.numpy())
+    print("wrote predictor", tuple(out.shape))
+
+    # ---- _nearest_l2 on the stress shapes ----
+    blobs = {}
+    for name, (n, d, k) in SEARCH_CASES.items():
+        x, emb = search_inputs(n, d, k)
+        with torch.no_grad():
+            idx = ns["ResidualVQEMA"]._nearest_l2(x, emb)
+            sc = x @ emb.t() - 0.5 * (emb * emb).sum(dim=1).unsqueeze(0)
+            top2 = sc.topk(2, dim=1).values
+        blobs[f"{name}_idx"] = idx.numpy().astype(np.int16 if k <= 32767 else np.int32)
+        blobs[f"{name}_margin"] = (top2[:, 0] - top2[:, 1]).numpy()
+    np.savez_compressed(os.path.join(OUT, "nearest.npz"), **blobs)
+    print("wrote nearest", list(SEARCH_CASES))
+
+
+if __name__ == "__main__":
+    main()
