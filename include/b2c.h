@@ -1,0 +1,165 @@
+/*
+ * b2c.h -- C ABI of libb2c.so: the B200 (sm_100a) encode -> quantize -> decode path of
+ * the proposed audio/vibrotactile VQ-VAE codec.
+ *
+ * The reference (aymenboudhina/Multimodal_VQVAE_compression_audio_tactile) has no FFI:
+ * its "plugin interface" is a set of PyTorch nn.Module slots
+ * (ProposedEval(A_ENC, A_QUANT, T_ENC, T_DEC, ...),
+ * Evaluation/dac_vcpwq_proposed6_latency.py:437-449).  The host-side mirror of those
+ * modules lives in multimodal_vqvae_compression_audio_tactile_b200/modules.py and binds
+ * this header with ctypes; INTEGRATION.md shows the binding.  Each entry point below
+ * names the reference computation it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types; nothing throws; every function
+ *    returns B2C_OK (0) or a negative error code, b2c_last_error() gives the text.
+ *  - device tensors are fp32 unless stated.  Activations inside a program are
+ *    CHANNEL-LAST: [batch][position][channel]; the module boundary tensors of the
+ *    reference ([B, C, L]) are converted by b2c_prog_transpose.
+ *  - a *program* is a straight-line list of kernel launches over one workspace;
+ *    it is built once per (batch, length) and run many times (b2c_prog_run enqueues
+ *    on the caller's stream and never synchronises).
+ *  - a buffer reference (b2c_ref) is (slot << 56) | byte_offset.  slot 0 is the
+ *    workspace passed to b2c_prog_run, slots 1.. are the caller's external tensors
+ *    (ext[slot-1]).  B2C_NULL_REF means "absent".
+ *  - packed weights are owned by the context and freed by b2c_ctx_destroy.
+ */
+#ifndef B2C_H
+#define B2C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2c_ctx b2c_ctx;
+typedef struct b2c_prog b2c_prog;
+typedef uint64_t b2c_ref;
+
+#define B2C_ABI_VERSION 1
+#define B2C_NULL_REF ((b2c_ref)0xFFFFFFFFFFFFFFFFull)
+#define B2C_REF(slot, off) ((((b2c_ref)(slot)) << 56) | (b2c_ref)(off))
+
+#define B2C_OK 0
+#define B2C_ERR_ARG (-1)
+#define B2C_ERR_CUDA (-2)
+#define B2C_ERR_WORKSPACE (-3)
+#define B2C_ERR_STATE (-4)
+#define B2C_ERR_UNSUPPORTED (-5)
+
+/* epilogue activation written to out_act (out_raw always gets the pre-activation) */
+#define B2C_ACT_NONE 0
+#define B2C_ACT_SNAKE 1 /* x + sin(alpha x)^2 / (alpha + 1e-9)   (dac Snake1d) */
+#define B2C_ACT_GELU 2  /* exact erf GELU (nn.GELU default, :379) */
+#define B2C_ACT_TANH 3
+
+/* arithmetic of the contraction */
+#define B2C_PREC_F32 0    /* FP32 FFMA on CUDA cores (bit-faithful to fp32 up to summation order) */
+#define B2C_PREC_BF16X3 1 /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate (>= 16 mantissa bits) */
+#define B2C_PREC_BF16 2   /* tcgen05 single-pass bf16, fp32 accumulate */
+
+/* row addressing modes of the token-wise ops (predictor two-pass schedule) */
+#define B2C_ROWS_DENSE 0     /* row n                                               */
+#define B2C_ROWS_HEAD 1      /* n = (b, j): row b*Tl + chunk*(j+1)      (chunk heads) */
+#define B2C_ROWS_HEAD_PREV 2 /* n = (b, j): row b*Tl + chunk*(j+1) - 1              */
+#define B2C_ROWS_ZERO 3      /* no input: zeros                                     */
+
+/* positional-encoding row selection */
+#define B2C_PE_NONE 0
+#define B2C_PE_CHUNK_POS 1 /* pe[(n % Tl) % chunk]  (PosEnc1D on a chunk slice, :349-351) */
+#define B2C_PE_ROW0 2      /* pe[0] */
+#define B2C_PE_ROW_N 3     /* pe[n] */
+
+const char* b2c_last_error(void);
+int b2c_abi_version(void);
+
+/* ---------------- context + packed weights ---------------- */
+int b2c_ctx_create(int device, b2c_ctx** out);
+int b2c_ctx_destroy(b2c_ctx* ctx);
+/* bytes of device memory held by packed weights */
+size_t b2c_ctx_weight_bytes(const b2c_ctx* ctx);
+
+/* Conv1d / ConvTranspose1d / Linear weights, HOST fp32 pointers in PyTorch layout.
+ *   v    : Conv1d [cout, cin, k]; ConvTranspose1d [cin, cout, k]; Linear [cout, cin] (k = 1)
+ *   g    : old-style weight-norm gain (weight_g, one per dim-0 slice) or NULL for a plain weight;
+ *          the fold w = g * v / ||v|| replaces torch._weight_norm (dac WNConv1d)
+ *   bias : [cout] or NULL
+ *   transposed : 0 Conv1d, 1 ConvTranspose1d (k = 2*stride, phase-decomposed at pack time)
+ * Returns a weight id >= 0. */
+int b2c_pack_conv(b2c_ctx* ctx, const float* v, const float* g, const float* bias, int cout, int cin, int k,
+                  int transposed, int stride, int padding);
+/* a plain fp32 vector / matrix (snake alpha, LayerNorm gamma/beta, positional table ...) */
+int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n);
+/* ResidualVQEMA.books (:412-415): n_books host pointers to [K, D]; also stores 0.5*|e|^2 */
+int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n_books, int K, int D);
+/* dac ResidualVectorQuantize: per stage in_proj (v,g,bias) [d,c,1], out_proj (v,g,bias) [c,d,1],
+ * codebook [K,d]; arrays of n_q host pointers each. */
+int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, const float* const* in_v, const float* const* in_g,
+                     const float* const* in_b, const float* const* out_v, const float* const* out_g,
+                     const float* const* out_b, const float* const* codebook);
+
+/* ---------------- programs ---------------- */
+int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out);
+int b2c_prog_destroy(b2c_prog* prog);
+int b2c_prog_num_launches(const b2c_prog* prog);
+
+/* dac Encoder stem: Conv1d(1, cout, k=7, p=3) on x [B, L] -> [B, L, cout]. */
+int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act, int alpha_wid, int B,
+                  int L);
+/* Conv1d (any k, stride, dilation, zero padding) or Linear (k = 1) as an implicit GEMM:
+ *   x [B, Lin, cin] -> [B, Lout, cout];  v = conv + bias (+ res);  out_raw = v;  out_act = act(v).
+ *   res_mode 0: res has the output's shape; 1: res is a [chunk, cout] table indexed by (lo % Tl) % chunk. */
+int b2c_prog_conv(b2c_prog* p, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act, int act,
+                  int alpha_wid, int B, int Lin, int stride, int dilation, int padding, int res_mode, int Tl,
+                  int chunk, int precision);
+/* ConvTranspose1d (k = 2*stride, padding = ceil(stride/2)), x [B, Lin, cin] -> [B, Lout, cout]. */
+int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act, int alpha_wid, int B,
+                   int Lin, int precision);
+/* dac Decoder head: Conv1d(cin, 1, k=7, p=3) + tanh on x [B, L, cin] -> y [B, L]. */
+int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L);
+/* LayerNorm over C of rows gathered by a_mode from a (minus sub, plus pe row), optional scale*tanh.
+ * nn.LayerNorm eps = 1e-5.  (CrossPredictor.ln_q/ln_kv/ffn[0] :394-395,:377; TokenNorm :357-360 with
+ * tanh and the clamped scalar, :472-474) */
+int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub, int pe_wid,
+                       int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk);
+/* softmax(Q K^T / sqrt(dh)) V inside each chunk (:401-402).
+ *   kv [B*Tl, 2*heads*dh] (K | V).  q_mode 0: q is a [chunk, heads*dh] table (row = position in chunk),
+ *   out rows dense [B*Tl].  q_mode 1: q is [B*nfix, heads*dh], one query per chunk head, out [B*nfix]. */
+int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv, b2c_ref out, int B, int Tl, int chunk,
+                       int heads, int dh);
+/* ResidualVQEMA.forward (:421-435) on rows x [N, D]; qsum [N, D]; idx int32 laid out [B, books_use, Tl]
+ * (row_mode DENSE: n = b*Tl + t; HEAD: n = (b, j) -> t = chunk*(j+1)). */
+int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N, int row_mode,
+                 int B, int Tl, int chunk);
+/* ResidualVQEMA._nearest_l2 (:417-419) with caller tensors: x [N, D], emb [K, D] -> idx int32 [N].
+ * scratch: K floats (receives 0.5*|e_k|^2). */
+int b2c_prog_nearest(b2c_prog* p, b2c_ref x, b2c_ref emb, b2c_ref scratch, b2c_ref idx, int N, int D, int K,
+                     int precision);
+/* dac ResidualVectorQuantize.forward (eval), z [B*Tl, c] -> zq [B*Tl, c], codes int32 [B, n_q, Tl]. */
+int b2c_prog_dac_rvq(b2c_prog* p, int wid, int n_q, b2c_ref z, b2c_ref zq, b2c_ref codes, int B, int Tl);
+/* out[b*Tl + chunk*(j+1)] = src[b*nfix + j] for rows of width C (second pass write-back). */
+int b2c_prog_scatter_heads(b2c_prog* p, b2c_ref src, b2c_ref dst, int B, int Tl, int chunk, int C);
+/* [B, R, C] -> [B, C, R] */
+int b2c_prog_transpose(b2c_prog* p, b2c_ref in, b2c_ref out, int B, int R, int C);
+/* widen int32 -> int64 (PyTorch index dtype at the module boundary) */
+int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n);
+
+/* Enqueue the program on `stream` (a cudaStream_t).  ext[i] is the device pointer of slot i+1. */
+int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext);
+
+typedef struct {
+  void* host;   /* pinned or pageable host buffer */
+  int slot;     /* external slot (>= 1) whose device buffer is the other end */
+  size_t bytes;
+} b2c_hostcopy;
+/* Host-buffer entry: H2D copies, the program, D2H copies, then a stream synchronise.
+ * This is the call bench.py's e2e leg and a non-PyTorch host would make. */
+int b2c_prog_run_host(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext,
+                      const b2c_hostcopy* h2d, int n_h2d, const b2c_hostcopy* d2h, int n_d2h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H */

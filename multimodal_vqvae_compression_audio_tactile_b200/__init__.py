@@ -1,0 +1,7 @@
+"""B200-native (sm_100a) encode -> quantize -> decode path of the audio/vibrotactile VQ-VAE codec
+of aymenboudhina/Multimodal_VQVAE_compression_audio_tactile, behind the reference's own
+nn.Module interface.  See DESIGN.md / INTEGRATION.md."""
+from ._lib import B2CError, LIB_PATH, load  # noqa: F401
+from .modules import (AR_CHUNK_TOK, CODE_DIM, DAC, CrossPredictor, Decoder, Encoder, PosEnc1D, ProposedEval,  # noqa: F401
+                      ResidualVectorQuantize, ResidualVQEMA, TokenNorm, build_proposed)
+from .ops import nearest_code  # noqa: F401

@@ -1,0 +1,761 @@
+// libb2c.so -- C ABI (include/b2c.h): packed weights, straight-line programs, launchers.
+#include "../../include/b2c.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels_f32.cuh"
+#include "kernels_tc.cuh"
+
+using namespace b2c;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) return fail(B2C_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" const char* b2c_last_error(void) { return g_err; }
+extern "C" int b2c_abi_version(void) { return B2C_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// context + weights
+// ------------------------------------------------------------------------------------------
+enum WKind { W_CONV = 1, W_VEC = 2, W_BOOKS = 3, W_DACRVQ = 4 };
+
+struct Weight {
+  int kind = 0;
+  float* dev = nullptr;       // main blob
+  float* bias = nullptr;      // conv bias or null
+  float* aux = nullptr;       // codebooks: half norms
+  TcWeight tc;                // bf16 hi/lo operand planes for the tcgen05 path (lazily absent)
+  size_t n = 0;
+  int cout = 0, cin = 0, k = 0, transposed = 0, stride = 1, padding = 0;
+  int n_phase = 1, kt = 0;
+  int in_off[8] = {0}, out_off[8] = {0};
+  int n_books = 0, K = 0, D = 0;     // codebooks / dac rvq
+  int n_q = 0, c = 0;
+  long stage_stride = 0;
+};
+
+struct b2c_ctx {
+  int device = 0;
+  std::vector<Weight> w;
+  size_t bytes = 0;
+  int sm_count = 148;
+};
+
+static int upload(b2c_ctx* ctx, const float* host, size_t n, float** dev) {
+  CUDA_TRY(cudaMalloc((void**)dev, n * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(*dev, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->bytes += n * sizeof(float);
+  return B2C_OK;
+}
+
+extern "C" int b2c_ctx_create(int device, b2c_ctx** out) {
+  if (!out) return fail(B2C_ERR_ARG, "b2c_ctx_create: out is NULL");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(B2C_ERR_ARG, "b2c_ctx_create: device %d of %d", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B2C_ERR_UNSUPPORTED, "b2c: built for sm_100a only, device %d is sm_%d%d (no fallback path)", device,
+                prop.major, prop.minor);
+  b2c_ctx* c = new b2c_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return B2C_OK;
+}
+
+extern "C" int b2c_ctx_destroy(b2c_ctx* ctx) {
+  if (!ctx) return B2C_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& w : ctx->w) {
+    if (w.dev) cudaFree(w.dev);
+    if (w.bias) cudaFree(w.bias);
+    if (w.aux) cudaFree(w.aux);
+    tc_weight_free(w.tc);
+  }
+  delete ctx;
+  return B2C_OK;
+}
+
+extern "C" size_t b2c_ctx_weight_bytes(const b2c_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+// w = g * v / ||v||_2 over all dims but 0 (torch._weight_norm, dim = 0); norm in double.
+static void fold_weight_norm(const float* v, const float* g, size_t n0, size_t inner, std::vector<float>& out) {
+  out.resize(n0 * inner);
+  for (size_t i = 0; i < n0; ++i) {
+    const float* row = v + i * inner;
+    if (!g) {
+      memcpy(&out[i * inner], row, inner * sizeof(float));
+      continue;
+    }
+    double s = 0.0;
+    for (size_t j = 0; j < inner; ++j) s += (double)row[j] * (double)row[j];
+    float scale = (float)((double)g[i] / sqrt(s));
+    for (size_t j = 0; j < inner; ++j) out[i * inner + j] = row[j] * scale;
+  }
+}
+
+extern "C" int b2c_pack_conv(b2c_ctx* ctx, const float* v, const float* g, const float* bias, int cout, int cin,
+                             int k, int transposed, int stride, int padding) {
+  if (!ctx || !v || cout <= 0 || cin <= 0 || k <= 0) return fail(B2C_ERR_ARG, "b2c_pack_conv: bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Weight w;
+  w.kind = W_CONV;
+  w.cout = cout; w.cin = cin; w.k = k; w.transposed = transposed; w.stride = stride; w.padding = padding;
+  std::vector<float> folded, packed;
+  if (!transposed) {
+    fold_weight_norm(v, g, cout, (size_t)cin * k, folded);  // [co][ci][t]
+    w.n_phase = 1; w.kt = k;
+    packed.resize((size_t)k * cin * cout);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < k; ++t)
+          packed[((size_t)t * cin + ci) * cout + co] = folded[((size_t)co * cin + ci) * k + t];
+  } else {
+    if (k != 2 * stride || stride > 8 || stride < 1)
+      return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_conv: ConvTranspose1d needs k == 2*stride <= 16 (got k=%d s=%d)", k, stride);
+    fold_weight_norm(v, g, cin, (size_t)cout * k, folded);  // [ci][co][kk]
+    w.n_phase = stride; w.kt = 2;
+    packed.resize((size_t)stride * 2 * cin * cout);
+    for (int r = 0; r < stride; ++r) {
+      int q = (r + padding) / stride, rem = (r + padding) % stride;
+      w.in_off[r] = q - 1;
+      w.out_off[r] = r;
+      for (int t = 0; t < 2; ++t) {
+        int kk = t == 0 ? rem + stride : rem;  // tap 0 reads x[j+q-1], tap 1 reads x[j+q]
+        for (int ci = 0; ci < cin; ++ci)
+          for (int co = 0; co < cout; ++co)
+            packed[(((size_t)r * 2 + t) * cin + ci) * cout + co] = folded[((size_t)ci * cout + co) * k + kk];
+      }
+    }
+  }
+  w.n = packed.size();
+  int rc = upload(ctx, packed.data(), packed.size(), &w.dev);
+  if (rc) return rc;
+  if (bias) {
+    rc = upload(ctx, bias, cout, &w.bias);
+    if (rc) return rc;
+  }
+  // tensor-core operand planes (bf16 hi / lo, K-major) for layers the tcgen05 kernel can take
+  rc = tc_weight_pack(packed.data(), w.n_phase, w.kt, cin, cout, &w.tc, &ctx->bytes);
+  if (rc) return fail(B2C_ERR_CUDA, "b2c_pack_conv: tensor-core operand upload failed (%d)", rc);
+  ctx->w.push_back(w);
+  return (int)ctx->w.size() - 1;
+}
+
+extern "C" int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n) {
+  if (!ctx || !data || n == 0) return fail(B2C_ERR_ARG, "b2c_pack_vector: bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Weight w;
+  w.kind = W_VEC;
+  w.n = n;
+  int rc = upload(ctx, data, n, &w.dev);
+  if (rc) return rc;
+  ctx->w.push_back(w);
+  return (int)ctx->w.size() - 1;
+}
+
+extern "C" int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n_books, int K, int D) {
+  if (!ctx || !books || n_books <= 0 || K <= 0 || D <= 0) return fail(B2C_ERR_ARG, "b2c_pack_codebooks: bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<float> all((size_t)n_books * K * D), hn((size_t)n_books * K);
+  for (int b = 0; b < n_books; ++b) {
+    if (!books[b]) return fail(B2C_ERR_ARG, "b2c_pack_codebooks: book %d is NULL", b);
+    memcpy(&all[(size_t)b * K * D], books[b], (size_t)K * D * sizeof(float));
+    for (int k = 0; k < K; ++k) {
+      // 0.5 * (emb*emb).sum(1): fp32 accumulation like the reference's tensor op
+      float s = 0.f;
+      for (int d = 0; d < D; ++d) { float e = books[b][(size_t)k * D + d]; s += e * e; }
+      hn[(size_t)b * K + k] = 0.5f * s;
+    }
+  }
+  Weight w;
+  w.kind = W_BOOKS; w.n_books = n_books; w.K = K; w.D = D; w.n = all.size();
+  int rc = upload(ctx, all.data(), all.size(), &w.dev);
+  if (rc) return rc;
+  rc = upload(ctx, hn.data(), hn.size(), &w.aux);
+  if (rc) return rc;
+  ctx->w.push_back(w);
+  return (int)ctx->w.size() - 1;
+}
+
+extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, const float* const* in_v,
+                                const float* const* in_g, const float* const* in_b, const float* const* out_v,
+                                const float* const* out_g, const float* const* out_b,
+                                const float* const* codebook) {
+  if (!ctx || n_q <= 0 || !in_v || !out_v || !codebook) return fail(B2C_ERR_ARG, "b2c_pack_dac_rvq: bad argument");
+  if (d != 8) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: codebook_dim must be 8 (got %d)", d);
+  if (c % 32 != 0 || c > 1024) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: latent dim %d (need multiple of 32, <= 1024)", c);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long stride = 8L * c + 8 + 8L * K + K + 8L * K + 8L * c + c;
+  std::vector<float> blob((size_t)stride * n_q, 0.f), tmp;
+  for (int s = 0; s < n_q; ++s) {
+    float* Win = &blob[(size_t)s * stride];
+    float* bin = Win + 8L * c;
+    float* cbn = bin + 8;
+    float* c2 = cbn + 8L * K;
+    float* cb = c2 + K;
+    float* Wout = cb + 8L * K;
+    float* bout = Wout + 8L * c;
+    fold_weight_norm(in_v[s], in_g ? in_g[s] : nullptr, 8, c, tmp);  // [d][c]
+    memcpy(Win, tmp.data(), 8L * c * sizeof(float));
+    if (in_b && in_b[s]) memcpy(bin, in_b[s], 8 * sizeof(float));
+    for (int k = 0; k < K; ++k) {
+      const float* e = codebook[s] + 8L * k;
+      float nn = 0.f;
+      for (int j = 0; j < 8; ++j) nn += e[j] * e[j];
+      float den = fmaxf(sqrtf(nn), 1e-12f);  // F.normalize
+      float cc = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        float v = e[j] / den;
+        cbn[8L * k + j] = v;
+        cb[8L * k + j] = e[j];
+        cc += v * v;
+      }
+      c2[k] = cc;
+    }
+    fold_weight_norm(out_v[s], out_g ? out_g[s] : nullptr, c, 8, tmp);  // [c][d]
+    memcpy(Wout, tmp.data(), 8L * c * sizeof(float));
+    if (out_b && out_b[s]) memcpy(bout, out_b[s], c * sizeof(float));
+  }
+  Weight w;
+  w.kind = W_DACRVQ; w.n_q = n_q; w.c = c; w.D = d; w.K = K; w.stage_stride = stride; w.n = blob.size();
+  int rc = upload(ctx, blob.data(), blob.size(), &w.dev);
+  if (rc) return rc;
+  ctx->w.push_back(w);
+  return (int)ctx->w.size() - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// programs
+// ------------------------------------------------------------------------------------------
+enum OpType { OP_STEM, OP_CONV, OP_HEAD, OP_LN, OP_ATTN, OP_RVQ, OP_NEAREST, OP_DACRVQ, OP_SCATTER, OP_TRANSPOSE,
+              OP_WIDEN, OP_CONV_TC };
+
+struct Op {
+  OpType type;
+  b2c_ref r[6];
+  int wid = -1, wid2 = -1, wid3 = -1;
+  ConvArgs conv;
+  LnArgs ln;
+  AttnArgs attn;
+  RvqArgs rvq;
+  DacRvqArgs dac;
+  TcConvPlan tc;
+  int i[8] = {0};
+  size_t n = 0;
+  int precision = 0;
+};
+
+struct b2c_prog {
+  b2c_ctx* ctx;
+  std::vector<Op> ops;
+};
+
+static const Weight* get_w(const b2c_prog* p, int wid, int kind, const char* who) {
+  if (wid < 0 || wid >= (int)p->ctx->w.size() || p->ctx->w[wid].kind != kind) {
+    fail(B2C_ERR_ARG, "%s: weight id %d is not of the expected kind", who, wid);
+    return nullptr;
+  }
+  return &p->ctx->w[wid];
+}
+
+extern "C" int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out) {
+  if (!ctx || !out) return fail(B2C_ERR_ARG, "b2c_prog_create: NULL argument");
+  *out = new b2c_prog{ctx, {}};
+  return B2C_OK;
+}
+extern "C" int b2c_prog_destroy(b2c_prog* p) {
+  delete p;
+  return B2C_OK;
+}
+extern "C" int b2c_prog_num_launches(const b2c_prog* p) { return p ? (int)p->ops.size() : 0; }
+
+static void blank_refs(Op& op) {
+  for (auto& r : op.r) r = B2C_NULL_REF;
+}
+
+extern "C" int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act,
+                             int alpha_wid, int B, int L) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_stem: NULL program");
+  const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_stem");
+  if (!w) return B2C_ERR_ARG;
+  if (w->cin != 1 || w->k != 7 || w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_stem: expects Conv1d(1, C, 7)");
+  if (act == B2C_ACT_SNAKE && !get_w(p, alpha_wid, W_VEC, "b2c_prog_stem(alpha)")) return B2C_ERR_ARG;
+  if (B <= 0 || L <= 0) return fail(B2C_ERR_ARG, "b2c_prog_stem: empty batch or length");
+  Op op;
+  op.type = OP_STEM;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = out_raw; op.r[2] = out_act;
+  op.wid = wid; op.wid2 = alpha_wid;
+  op.i[0] = B; op.i[1] = L; op.i[2] = act;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act,
+                    int act, int alpha_wid, int B, int Lin, int stride, int dilation, int padding, int res_mode,
+                    int Tl, int chunk, int precision) {
+  if (!p) return fail(B2C_ERR_ARG, "%s: NULL program", who);
+  const Weight* w = get_w(p, wid, W_CONV, who);
+  if (!w) return B2C_ERR_ARG;
+  if (act == B2C_ACT_SNAKE && !get_w(p, alpha_wid, W_VEC, who)) return B2C_ERR_ARG;
+  if (B <= 0 || Lin <= 0) return fail(B2C_ERR_ARG, "%s: empty batch or length", who);
+  if (w->cin % 16 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cin=%d must be a multiple of 16", who, w->cin);
+  if (w->cout % 2 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cout=%d must be even", who, w->cout);
+  if (res_mode == 1 && (Tl <= 0 || chunk <= 0)) return fail(B2C_ERR_ARG, "%s: table residual needs Tl and chunk", who);
+  Op op;
+  op.type = OP_CONV;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = res; op.r[2] = out_raw; op.r[3] = out_act;
+  op.wid = wid; op.wid2 = alpha_wid;
+  op.precision = precision;
+  ConvArgs& a = op.conv;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.Lin = Lin; a.Cin = w->cin; a.Cout = w->cout; a.KT = w->kt;
+  a.n_phase = w->n_phase;
+  a.act = act; a.res_mode = res_mode; a.Tl = Tl > 0 ? Tl : 1; a.chunk = chunk > 0 ? chunk : 1;
+  if (!w->transposed) {
+    if (stride < 1 || dilation < 1 || padding < 0) return fail(B2C_ERR_ARG, "%s: bad stride/dilation/padding", who);
+    int Lout = (Lin + 2 * padding - dilation * (w->k - 1) - 1) / stride + 1;
+    if (Lout <= 0) return fail(B2C_ERR_ARG, "%s: input of length %d is too short", who, Lin);
+    a.in_step = stride; a.dil = dilation; a.Lj = Lout; a.out_step = 1; a.Lout = Lout;
+    a.in_off[0] = -padding; a.out_off[0] = 0;
+  } else {
+    int s = w->stride;
+    int Lout = (Lin - 1) * s - 2 * w->padding + w->k;
+    a.in_step = 1; a.dil = 1; a.out_step = s; a.Lout = Lout; a.Lj = (Lout + s - 1) / s;
+    for (int r = 0; r < s; ++r) { a.in_off[r] = w->in_off[r]; a.out_off[r] = w->out_off[r]; }
+  }
+  if ((long)B * a.n_phase > 65535) return fail(B2C_ERR_UNSUPPORTED, "%s: batch*phases %ld exceeds grid.z", who, (long)B * a.n_phase);
+  if (precision != B2C_PREC_F32) {
+    int rc = tc_conv_plan(a, w->tc, precision, p->ctx->sm_count, &op.tc);
+    if (rc == 0) op.type = OP_CONV_TC;
+    else if (rc < 0) return fail(B2C_ERR_UNSUPPORTED, "%s: tensor-core plan failed (%d)", who, rc);
+    // rc > 0: shape not eligible for the tcgen05 kernel -> FP32 CUDA-core kernel (still sm_100a CUDA)
+  }
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_conv(b2c_prog* p, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act,
+                             int act, int alpha_wid, int B, int Lin, int stride, int dilation, int padding,
+                             int res_mode, int Tl, int chunk, int precision) {
+  if (p) {
+    const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_conv");
+    if (!w) return B2C_ERR_ARG;
+    if (w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_conv: weight %d is a ConvTranspose1d", wid);
+  }
+  return add_conv(p, "b2c_prog_conv", wid, x, res, out_raw, out_act, act, alpha_wid, B, Lin, stride, dilation,
+                  padding, res_mode, Tl, chunk, precision);
+}
+
+extern "C" int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act,
+                              int alpha_wid, int B, int Lin, int precision) {
+  if (p) {
+    const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_convT");
+    if (!w) return B2C_ERR_ARG;
+    if (!w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_convT: weight %d is not a ConvTranspose1d", wid);
+  }
+  return add_conv(p, "b2c_prog_convT", wid, x, B2C_NULL_REF, out_raw, out_act, act, alpha_wid, B, Lin, 1, 1, 0, 0, 0,
+                  0, precision);
+}
+
+extern "C" int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_head: NULL program");
+  const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_head");
+  if (!w) return B2C_ERR_ARG;
+  if (w->cout != 1 || w->k != 7 || w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_head: expects Conv1d(C, 1, 7)");
+  if (B <= 0 || L <= 0) return fail(B2C_ERR_ARG, "b2c_prog_head: empty batch or length");
+  Op op;
+  op.type = OP_HEAD;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = y;
+  op.wid = wid;
+  op.i[0] = B; op.i[1] = L;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+static int nfix_of(int Tl, int chunk) { return (Tl + chunk - 1) / chunk - 1; }
+
+extern "C" int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub,
+                                  int pe_wid, int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C,
+                                  int Tl, int chunk) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: NULL program");
+  if (!get_w(p, gamma_wid, W_VEC, "b2c_prog_layernorm(gamma)") || !get_w(p, beta_wid, W_VEC, "b2c_prog_layernorm(beta)"))
+    return B2C_ERR_ARG;
+  if (pe_mode != B2C_PE_NONE && !get_w(p, pe_wid, W_VEC, "b2c_prog_layernorm(pe)")) return B2C_ERR_ARG;
+  if (N <= 0 || C <= 0 || Tl <= 0 || chunk <= 0) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: bad sizes");
+  Op op;
+  op.type = OP_LN;
+  blank_refs(op);
+  op.r[0] = a; op.r[1] = sub; op.r[2] = out;
+  op.wid = gamma_wid; op.wid2 = beta_wid; op.wid3 = pe_wid;
+  LnArgs& l = op.ln;
+  memset(&l, 0, sizeof(l));
+  l.N = N; l.C = C; l.Tl = Tl; l.chunk = chunk; l.nfix = nfix_of(Tl, chunk) > 0 ? nfix_of(Tl, chunk) : 1;
+  l.a_mode = a_mode; l.pe_mode = pe_mode; l.tanh_post = tanh_post; l.post_scale = post_scale;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv, b2c_ref out, int B, int Tl,
+                                  int chunk, int heads, int dh) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_attention: NULL program");
+  if (dh != 128 || heads < 1 || heads > 8) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_attention: heads<=8, head dim 128 only (got %d x %d)", heads, dh);
+  if (chunk < 1 || chunk > 16) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_attention: chunk %d > 16", chunk);
+  if (B <= 0 || Tl <= 0) return fail(B2C_ERR_ARG, "b2c_prog_attention: empty");
+  Op op;
+  op.type = OP_ATTN;
+  blank_refs(op);
+  op.r[0] = q; op.r[1] = kv; op.r[2] = out;
+  AttnArgs& a = op.attn;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.Tl = Tl; a.chunk = chunk; a.heads = heads; a.q_mode = q_mode;
+  a.nchunks = (Tl + chunk - 1) / chunk;
+  a.nfix = a.nchunks - 1;
+  if (q_mode == 1 && a.nfix <= 0) return B2C_OK;  // single chunk: nothing to re-do
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N,
+                            int row_mode, int B, int Tl, int chunk) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_rvq: NULL program");
+  const Weight* w = get_w(p, books_wid, W_BOOKS, "b2c_prog_rvq");
+  if (!w) return B2C_ERR_ARG;
+  if (books_use < 0 || books_use > w->n_books) return fail(B2C_ERR_ARG, "b2c_prog_rvq: books_use %d of %d", books_use, w->n_books);
+  if (N <= 0) return fail(B2C_ERR_ARG, "b2c_prog_rvq: empty");
+  if (w->D > 256) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_rvq: code dim %d > 256", w->D);
+  Op op;
+  op.type = OP_RVQ;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = qsum; op.r[2] = idx;
+  op.wid = books_wid;
+  RvqArgs& r = op.rvq;
+  memset(&r, 0, sizeof(r));
+  r.N = N; r.D = w->D; r.K = w->K; r.books_use = books_use; r.row_mode = row_mode; r.B = B; r.Tl = Tl > 0 ? Tl : 1;
+  r.chunk = chunk > 0 ? chunk : 1;
+  r.nfix = nfix_of(r.Tl, r.chunk) > 0 ? nfix_of(r.Tl, r.chunk) : 1;
+  r.idx_flat = 0;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_nearest(b2c_prog* p, b2c_ref x, b2c_ref emb, b2c_ref scratch, b2c_ref idx, int N, int D,
+                                int K, int precision) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_nearest: NULL program");
+  if (N <= 0 || D <= 0 || K <= 0) return fail(B2C_ERR_ARG, "b2c_prog_nearest: empty input (N=%d D=%d K=%d)", N, D, K);
+  if (D > 256) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_nearest: D=%d > 256", D);
+  Op op;
+  op.type = OP_NEAREST;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = emb; op.r[2] = scratch; op.r[3] = idx;
+  op.precision = precision;
+  RvqArgs& r = op.rvq;
+  memset(&r, 0, sizeof(r));
+  r.N = N; r.D = D; r.K = K; r.books_use = 1; r.idx_flat = 1; r.Tl = 1; r.chunk = 1; r.nfix = 1;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_dac_rvq(b2c_prog* p, int wid, int n_q, b2c_ref z, b2c_ref zq, b2c_ref codes, int B, int Tl) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_dac_rvq: NULL program");
+  const Weight* w = get_w(p, wid, W_DACRVQ, "b2c_prog_dac_rvq");
+  if (!w) return B2C_ERR_ARG;
+  if (n_q < 1 || n_q > w->n_q) return fail(B2C_ERR_ARG, "b2c_prog_dac_rvq: n_q %d of %d", n_q, w->n_q);
+  if (B <= 0 || Tl <= 0) return fail(B2C_ERR_ARG, "b2c_prog_dac_rvq: empty");
+  Op op;
+  op.type = OP_DACRVQ;
+  blank_refs(op);
+  op.r[0] = z; op.r[1] = zq; op.r[2] = codes;
+  op.wid = wid;
+  DacRvqArgs& d = op.dac;
+  memset(&d, 0, sizeof(d));
+  d.N = B * Tl; d.C = w->c; d.K = w->K; d.n_q = n_q; d.Tl = Tl; d.stage_stride = w->stage_stride;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_scatter_heads(b2c_prog* p, b2c_ref src, b2c_ref dst, int B, int Tl, int chunk, int C) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_scatter_heads: NULL program");
+  int nfix = nfix_of(Tl, chunk);
+  if (nfix <= 0) return B2C_OK;
+  Op op;
+  op.type = OP_SCATTER;
+  blank_refs(op);
+  op.r[0] = src; op.r[1] = dst;
+  op.i[0] = B; op.i[1] = Tl; op.i[2] = chunk; op.i[3] = C; op.i[4] = nfix;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_transpose(b2c_prog* p, b2c_ref in, b2c_ref out, int B, int R, int C) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_transpose: NULL program");
+  if (B <= 0 || R <= 0 || C <= 0 || B > 65535) return fail(B2C_ERR_ARG, "b2c_prog_transpose: bad sizes");
+  Op op;
+  op.type = OP_TRANSPOSE;
+  blank_refs(op);
+  op.r[0] = in; op.r[1] = out;
+  op.i[0] = B; op.i[1] = R; op.i[2] = C;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_i32_to_i64: NULL program");
+  Op op;
+  op.type = OP_WIDEN;
+  blank_refs(op);
+  op.r[0] = in; op.r[1] = out;
+  op.n = n;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------
+struct Resolver {
+  char* ws;
+  size_t ws_bytes;
+  void* const* ext;
+  int n_ext;
+  bool bad = false;
+  template <class T>
+  T* get(b2c_ref r) {
+    if (r == B2C_NULL_REF) return nullptr;
+    int slot = (int)(r >> 56);
+    size_t off = (size_t)(r & 0x00FFFFFFFFFFFFFFull);
+    if (slot == 0) {
+      if (!ws || off >= ws_bytes) { bad = true; return nullptr; }
+      return reinterpret_cast<T*>(ws + off);
+    }
+    if (slot > n_ext || !ext || !ext[slot - 1]) { bad = true; return nullptr; }
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(ext[slot - 1]) + off);
+  }
+};
+
+static int launch_conv_f32(const ConvArgs& a, cudaStream_t st, int sm_count) {
+  long tiles_m = (a.Lj + 127) / 128;
+  long z = (long)a.B * a.n_phase;
+  int tn;
+  if (a.Cout % 128 == 0 && tiles_m * z * (a.Cout / 128) >= 2L * sm_count) tn = 8;
+  else if (a.Cout % 64 == 0) tn = 4;
+  else if (a.Cout % 96 == 0) tn = 6;
+  else tn = 4;
+  if (tn != 6 && a.Cout % 4 != 0) return fail(B2C_ERR_UNSUPPORTED, "conv: Cout=%d needs a multiple of 4", a.Cout);
+  dim3 grid((unsigned)tiles_m, (unsigned)((a.Cout + 16 * tn - 1) / (16 * tn)), (unsigned)z);
+  if (tn == 8) conv_gemm_f32<8><<<grid, 256, 0, st>>>(a);
+  else if (tn == 6) conv_gemm_f32<6><<<grid, 256, 0, st>>>(a);
+  else conv_gemm_f32<4><<<grid, 256, 0, st>>>(a);
+  return B2C_OK;
+}
+
+static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R) {
+  b2c_ctx* ctx = p->ctx;
+  for (size_t oi = 0; oi < p->ops.size(); ++oi) {
+    Op& op = p->ops[oi];
+    switch (op.type) {
+      case OP_STEM: {
+        const Weight& w = ctx->w[op.wid];
+        const float* x = R.get<const float>(op.r[0]);
+        float* o_raw = R.get<float>(op.r[1]);
+        float* o_act = R.get<float>(op.r[2]);
+        const float* alpha = op.i[2] == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
+        if (R.bad || !x) return fail(B2C_ERR_WORKSPACE, "op %zu (stem): unresolved buffer", oi);
+        int B = op.i[0], L = op.i[1];
+        dim3 grid((L + 63) / 64, B);
+        size_t sm = (64 + 8 + 7 * w.cout) * sizeof(float);
+        stem_k7_f32<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, o_act, alpha, L, w.cout, op.i[2]);
+        break;
+      }
+      case OP_CONV:
+      case OP_CONV_TC: {
+        const Weight& w = ctx->w[op.wid];
+        ConvArgs a = op.conv;
+        a.x = R.get<const float>(op.r[0]);
+        a.res = R.get<const float>(op.r[1]);
+        a.out_raw = R.get<float>(op.r[2]);
+        a.out_act = R.get<float>(op.r[3]);
+        a.w = w.dev;
+        a.bias = w.bias;
+        a.alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
+        if (R.bad || !a.x || (!a.out_raw && !a.out_act)) return fail(B2C_ERR_WORKSPACE, "op %zu (conv): unresolved buffer", oi);
+        if (op.type == OP_CONV_TC) {
+          int rc = tc_conv_launch(op.tc, a, w.tc, st);
+          if (rc) return fail(B2C_ERR_CUDA, "op %zu (conv, tcgen05): launch failed (%d)", oi, rc);
+        } else {
+          int rc = launch_conv_f32(a, st, ctx->sm_count);
+          if (rc) return rc;
+        }
+        break;
+      }
+      case OP_HEAD: {
+        const Weight& w = ctx->w[op.wid];
+        const float* x = R.get<const float>(op.r[0]);
+        float* y = R.get<float>(op.r[1]);
+        if (R.bad || !x || !y) return fail(B2C_ERR_WORKSPACE, "op %zu (head): unresolved buffer", oi);
+        int B = op.i[0], L = op.i[1];
+        dim3 grid((L + 63) / 64, B);
+        head_k7_tanh_f32<<<grid, 256, 7 * w.cin * sizeof(float), st>>>(x, w.dev, w.bias, y, L, w.cin);
+        break;
+      }
+      case OP_LN: {
+        LnArgs l = op.ln;
+        l.a = R.get<const float>(op.r[0]);
+        l.sub = R.get<const float>(op.r[1]);
+        l.out = R.get<float>(op.r[2]);
+        l.gamma = ctx->w[op.wid].dev;
+        l.beta = ctx->w[op.wid2].dev;
+        l.pe = l.pe_mode != PE_NONE ? ctx->w[op.wid3].dev : nullptr;
+        if (R.bad || !l.out || (l.a_mode != ROWS_ZERO && !l.a)) return fail(B2C_ERR_WORKSPACE, "op %zu (layernorm): unresolved buffer", oi);
+        layernorm_rows_f32<<<(l.N + 7) / 8, 256, 0, st>>>(l);
+        break;
+      }
+      case OP_ATTN: {
+        AttnArgs a = op.attn;
+        a.q = R.get<const float>(op.r[0]);
+        a.kv = R.get<const float>(op.r[1]);
+        a.out = R.get<float>(op.r[2]);
+        if (R.bad || !a.q || !a.kv || !a.out) return fail(B2C_ERR_WORKSPACE, "op %zu (attention): unresolved buffer", oi);
+        int blocks = a.q_mode != 1 ? a.B * a.nchunks : a.B * a.nfix;
+        attention_chunk_f32<<<blocks, 32 * a.heads, 0, st>>>(a);
+        break;
+      }
+      case OP_RVQ:
+      case OP_NEAREST: {
+        RvqArgs r = op.rvq;
+        if (op.type == OP_RVQ) {
+          const Weight& w = ctx->w[op.wid];
+          r.x = R.get<const float>(op.r[0]);
+          r.qsum = R.get<float>(op.r[1]);
+          r.idx = r.books_use > 0 ? R.get<int>(op.r[2]) : nullptr;
+          r.books = w.dev;
+          r.half_n = w.aux;
+        } else {
+          r.x = R.get<const float>(op.r[0]);
+          r.books = R.get<const float>(op.r[1]);
+          float* scratch = R.get<float>(op.r[2]);
+          r.idx = R.get<int>(op.r[3]);
+          r.qsum = nullptr;
+          if (R.bad || !scratch || !r.books) return fail(B2C_ERR_WORKSPACE, "op %zu (nearest): unresolved buffer", oi);
+          half_sqnorm_f32<<<(r.K + 127) / 128, 128, 0, st>>>(r.books, scratch, r.K, r.D);
+          r.half_n = scratch;
+          if (op.precision != B2C_PREC_F32) {
+            int rc = tc_nearest_launch(r, op.precision, ctx->sm_count, st);
+            if (rc == 0) break;
+            if (rc < 0) return fail(B2C_ERR_CUDA, "op %zu (nearest, tcgen05): launch failed (%d)", oi, rc);
+          }
+        }
+        if (R.bad || !r.x || (!r.idx && r.books_use > 0)) return fail(B2C_ERR_WORKSPACE, "op %zu (rvq): unresolved buffer", oi);
+        if (r.books_use > 0) {
+          size_t sm = ((size_t)64 * r.D + 64 * (r.D + 1)) * sizeof(float);
+          if (sm > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(rvq_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
+          }
+          rvq_f32<<<(r.N + 31) / 32, 256, sm, st>>>(r);
+        } else if (r.qsum) {
+          cudaError_t e = cudaMemsetAsync(r.qsum, 0, (size_t)r.N * r.D * sizeof(float), st);
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq memset: %s", cudaGetErrorString(e));
+        }
+        break;
+      }
+      case OP_DACRVQ: {
+        DacRvqArgs d = op.dac;
+        d.z = R.get<const float>(op.r[0]);
+        d.zq = R.get<float>(op.r[1]);
+        d.codes = R.get<int>(op.r[2]);
+        d.w = ctx->w[op.wid].dev;
+        if (R.bad || !d.z || !d.zq || !d.codes) return fail(B2C_ERR_WORKSPACE, "op %zu (dac rvq): unresolved buffer", oi);
+        int blocks = (d.N + 7) / 8;
+        switch (d.C / 32) {
+          case 32: dac_rvq_f32<32><<<blocks, 256, 0, st>>>(d); break;
+          case 16: dac_rvq_f32<16><<<blocks, 256, 0, st>>>(d); break;
+          case 8: dac_rvq_f32<8><<<blocks, 256, 0, st>>>(d); break;
+          case 4: dac_rvq_f32<4><<<blocks, 256, 0, st>>>(d); break;
+          case 2: dac_rvq_f32<2><<<blocks, 256, 0, st>>>(d); break;
+          default: return fail(B2C_ERR_UNSUPPORTED, "dac rvq: latent dim %d not in {64,128,256,512,1024}", d.C);
+        }
+        break;
+      }
+      case OP_SCATTER: {
+        const float* src = R.get<const float>(op.r[0]);
+        float* dst = R.get<float>(op.r[1]);
+        if (R.bad || !src || !dst) return fail(B2C_ERR_WORKSPACE, "op %zu (scatter): unresolved buffer", oi);
+        long total = (long)op.i[0] * op.i[4] * op.i[3];
+        scatter_heads_f32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, op.i[4], op.i[1], op.i[2], op.i[3], total);
+        break;
+      }
+      case OP_TRANSPOSE: {
+        const float* in = R.get<const float>(op.r[0]);
+        float* out = R.get<float>(op.r[1]);
+        if (R.bad || !in || !out) return fail(B2C_ERR_WORKSPACE, "op %zu (transpose): unresolved buffer", oi);
+        dim3 grid((op.i[2] + 31) / 32, (op.i[1] + 31) / 32, op.i[0]);
+        transpose_brc_f32<<<grid, dim3(32, 8), 0, st>>>(in, out, op.i[1], op.i[2]);
+        break;
+      }
+      case OP_WIDEN: {
+        const int* in = R.get<const int>(op.r[0]);
+        long long* out = R.get<long long>(op.r[1]);
+        if (R.bad || !in || !out) return fail(B2C_ERR_WORKSPACE, "op %zu (widen): unresolved buffer", oi);
+        widen_i32_i64<<<(unsigned)((op.n + 255) / 256), 256, 0, st>>>(in, out, op.n);
+        break;
+      }
+    }
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "op %zu (type %d): %s", oi, (int)op.type, cudaGetErrorString(e));
+  }
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext,
+                            int n_ext) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_run: NULL program");
+  Resolver R{reinterpret_cast<char*>(workspace), workspace_bytes, ext, n_ext};
+  return run_ops(p, reinterpret_cast<cudaStream_t>(stream), R);
+}
+
+extern "C" int b2c_prog_run_host(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes,
+                                 void* const* ext, int n_ext, const b2c_hostcopy* h2d, int n_h2d,
+                                 const b2c_hostcopy* d2h, int n_d2h) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_run_host: NULL program");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_h2d; ++i) {
+    if (h2d[i].slot < 1 || h2d[i].slot > n_ext || !h2d[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host: bad h2d[%d]", i);
+    CUDA_TRY(cudaMemcpyAsync(ext[h2d[i].slot - 1], h2d[i].host, h2d[i].bytes, cudaMemcpyHostToDevice, st));
+  }
+  int rc = b2c_prog_run(p, stream, workspace, workspace_bytes, ext, n_ext);
+  if (rc) return rc;
+  for (int i = 0; i < n_d2h; ++i) {
+    if (d2h[i].slot < 1 || d2h[i].slot > n_ext || !d2h[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host: bad d2h[%d]", i);
+    CUDA_TRY(cudaMemcpyAsync(d2h[i].host, ext[d2h[i].slot - 1], d2h[i].bytes, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return B2C_OK;
+}

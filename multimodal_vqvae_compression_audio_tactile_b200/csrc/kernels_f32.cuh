@@ -1,0 +1,683 @@
+// FP32 CUDA-core kernels of the encode -> quantize -> decode path (sm_100a).
+// These are the bit-faithful arm (fp32 everywhere, only the summation order differs from
+// the reference's CPU fp32) and the on-GPU cross-check for the tcgen05 kernels.
+// Activations are channel-last: [batch][position][channel].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2c {
+
+enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_GELU = 2, ACT_TANH = 3 };
+enum { ROWS_DENSE = 0, ROWS_HEAD = 1, ROWS_HEAD_PREV = 2, ROWS_ZERO = 3 };
+enum { PE_NONE = 0, PE_CHUNK_POS = 1, PE_ROW0 = 2, PE_ROW_N = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// epilogue activations.  __f*_rn keep the reference's op order (no FMA contraction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float snake_f(float v, float alpha) {
+  // dac Snake1d: x + (alpha + 1e-9)^-1 * sin(alpha x)^2
+  float inv = __frcp_rn(__fadd_rn(alpha, 1e-9f));
+  float s = sinf(__fmul_rn(alpha, v));
+  return __fadd_rn(v, __fmul_rn(inv, __fmul_rn(s, s)));
+}
+__device__ __forceinline__ float gelu_f(float v) {
+  // nn.GELU() (erf form): 0.5 x (1 + erf(x / sqrt 2))
+  return __fmul_rn(__fmul_rn(v, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(v, 0.70710678118654752440f))));
+}
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  if (act == ACT_SNAKE) return snake_f(v, alpha);
+  if (act == ACT_GELU) return gelu_f(v);
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic Conv1d / Linear / ConvTranspose1d-phase implicit GEMM, FP32 FFMA.
+//   out[b, j*out_step + out_off[ph], co] = bias[co] + sum_{t<KT} sum_ci
+//        x[b, j*in_step + t*dil + in_off[ph], ci] * w[ph][t][ci][co]      (+ res)
+// M = positions (128 per CTA), N = output channels (16*TN per CTA), K = KT*Cin in slices of 16.
+// ---------------------------------------------------------------------------------------------
+struct ConvArgs {
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* res;
+  float* out_raw;
+  float* out_act;
+  const float* alpha;
+  int B, Lin, Cin, Cout, KT;
+  int in_step, dil;
+  int n_phase, Lj;
+  int out_step, Lout;
+  int in_off[8];
+  int out_off[8];
+  int act, res_mode, Tl, chunk;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256, 2) conv_gemm_f32(const ConvArgs a) {
+  constexpr int BM = 128, BK = 16, BN = 16 * TN;
+  constexpr int VW = (TN == 6) ? 2 : 4;   // vector width of the per-thread channel groups
+  constexpr int NG = TN / VW;             // channel groups per thread
+  constexpr int NB4 = (4 * BN + 255) / 256;  // float4 loads of the weight tile per thread
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z / a.n_phase, ph = blockIdx.z % a.n_phase;
+  const int j0 = blockIdx.x * BM, co0 = blockIdx.y * BN;
+  const float* __restrict__ wp = a.w + (size_t)ph * a.KT * a.Cin * a.Cout;
+  const float* __restrict__ xb = a.x + (size_t)b * a.Lin * a.Cin;
+  const int in_off = a.in_off[ph];
+
+  // A-tile load mapping: two float4 per thread
+  int a_m[2], a_kq[2], a_l0[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    int f = tid + u * 256;
+    a_m[u] = f >> 2;
+    a_kq[u] = f & 3;
+    int j = j0 + a_m[u];
+    a_ok[u] = j < a.Lj;
+    a_l0[u] = j * a.in_step + in_off;
+  }
+  const int nK = a.Cin / BK;
+  const int nIt = a.KT * nK;
+
+  float4 ra[2];
+  float4 rb[NB4];
+
+  auto load_g = [&](int it) {
+    int tap = it / nK;
+    int ci0 = (it - tap * nK) * BK;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      int l = a_l0[u] + tap * a.dil;
+      if (a_ok[u] && l >= 0 && l < a.Lin)
+        ra[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)l * a.Cin + ci0 + a_kq[u] * 4));
+      else
+        ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < NB4; ++u) {
+      int f = tid + u * 256;
+      int kk = f / (BN / 4), nq = f % (BN / 4);
+      int co = co0 + nq * 4;
+      if (f < 4 * BN && co < a.Cout)
+        rb[u] = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)tap * a.Cin + ci0 + kk) * a.Cout + co));
+      else
+        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_s = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      As[buf][a_kq[u] * 4 + 0][a_m[u]] = ra[u].x;
+      As[buf][a_kq[u] * 4 + 1][a_m[u]] = ra[u].y;
+      As[buf][a_kq[u] * 4 + 2][a_m[u]] = ra[u].z;
+      As[buf][a_kq[u] * 4 + 3][a_m[u]] = ra[u].w;
+    }
+#pragma unroll
+    for (int u = 0; u < NB4; ++u) {
+      int f = tid + u * 256;
+      if (f < 4 * BN) {
+        int kk = f / (BN / 4), nq = f % (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = rb[u];
+      }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[i][n] = 0.f;
+
+  load_g(0);
+  store_s(0);
+  __syncthreads();
+  for (int it = 0; it < nIt; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nIt) load_g(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[8], bv[TN];
+      *reinterpret_cast<float4*>(&av[0]) = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      *reinterpret_cast<float4*>(&av[4]) = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if constexpr (VW == 4)
+          *reinterpret_cast<float4*>(&bv[g * 4]) =
+              *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tx * 4]);
+        else
+          *reinterpret_cast<float2*>(&bv[g * 2]) =
+              *reinterpret_cast<const float2*>(&Bs[buf][k][g * 32 + tx * 2]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) acc[i][n] = fmaf(av[i], bv[n], acc[i][n]);
+    }
+    if (it + 1 < nIt) store_s(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue
+  const int out_off = a.out_off[ph];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int j = j0 + ty * 8 + i;
+    if (j >= a.Lj) continue;
+    int lo = j * a.out_step + out_off;
+    if (lo < 0 || lo >= a.Lout) continue;
+    size_t orow = ((size_t)b * a.Lout + lo) * a.Cout;
+    size_t rrow = orow;
+    if (a.res_mode == 1) rrow = (size_t)((lo % a.Tl) % a.chunk) * a.Cout;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      int co = co0 + g * (16 * VW) + tx * VW;
+      if (co >= a.Cout) continue;
+      float v[VW], w[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        float t = acc[i][g * VW + e];
+        if (a.bias) t = __fadd_rn(t, __ldg(a.bias + co + e));
+        if (a.res) t = __fadd_rn(t, __ldg(a.res + rrow + co + e));
+        v[e] = t;
+      }
+      if (a.out_raw) {
+        if constexpr (VW == 4)
+          *reinterpret_cast<float4*>(a.out_raw + orow + co) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+          *reinterpret_cast<float2*>(a.out_raw + orow + co) = make_float2(v[0], v[1]);
+      }
+      if (a.out_act) {
+#pragma unroll
+        for (int e = 0; e < VW; ++e)
+          w[e] = apply_act(v[e], a.act, a.act == ACT_SNAKE ? __ldg(a.alpha + co + e) : 0.f);
+        if constexpr (VW == 4)
+          *reinterpret_cast<float4*>(a.out_act + orow + co) = make_float4(w[0], w[1], w[2], w[3]);
+        else
+          *reinterpret_cast<float2*>(a.out_act + orow + co) = make_float2(w[0], w[1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Encoder stem: Conv1d(1, Cout, k=7, p=3).  HBM-bound on the store (Cout floats per sample).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_k7_f32(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ out_raw,
+                                                    float* __restrict__ out_act, const float* __restrict__ alpha,
+                                                    int L, int Cout, int act) {
+  constexpr int TP = 64;
+  extern __shared__ float sm[];
+  float* xs = sm;             // TP + 6
+  float* ws = sm + TP + 8;    // 7 * Cout, then bias, then alpha
+  const int b = blockIdx.y, l0 = blockIdx.x * TP;
+  for (int i = threadIdx.x; i < TP + 6; i += blockDim.x) {
+    int l = l0 + i - 3;
+    xs[i] = (l >= 0 && l < L) ? __ldg(x + (size_t)b * L + l) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 7 * Cout; i += blockDim.x) ws[i] = __ldg(w + i);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TP * Cout; idx += blockDim.x) {
+    int p = idx / Cout, co = idx - p * Cout;
+    int l = l0 + p;
+    if (l >= L) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) acc = fmaf(xs[p + t], ws[t * Cout + co], acc);
+    if (bias) acc = __fadd_rn(acc, __ldg(bias + co));
+    size_t o = ((size_t)b * L + l) * Cout + co;
+    if (out_raw) out_raw[o] = acc;
+    if (out_act) out_act[o] = apply_act(acc, act, act == ACT_SNAKE ? __ldg(alpha + co) : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder head: Conv1d(Cin, 1, k=7, p=3) + tanh.  In channel-last layout the 7*Cin window of one
+// output is CONTIGUOUS, so y[l] = tanh(b + <w_flat, x_flat[(l-3)*Cin ...]>): one warp per output,
+// coalesced reads, HBM/L1-bound.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_k7_tanh_f32(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int L,
+                                                         int Cin) {
+  extern __shared__ float wsm[];
+  const int n = 7 * Cin;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) wsm[i] = __ldg(w + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * L * Cin;
+  const long total = (long)L * Cin;
+  constexpr int PPW = 8;
+  const int l_base = (blockIdx.x * 8 + warp) * PPW;
+  for (int p = 0; p < PPW; ++p) {
+    int l = l_base + p;
+    if (l >= L) break;
+    long base = (long)(l - 3) * Cin;
+    float acc = 0.f;
+    for (int f = lane; f < n; f += 32) {
+      long g = base + f;
+      float xv = (g >= 0 && g < total) ? __ldg(xb + g) : 0.f;
+      acc = fmaf(xv, wsm[f], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[(size_t)b * L + l] = tanhf(__fadd_rn(acc, bias ? __ldg(bias) : 0.f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row LayerNorm with fused input composition: v = a[row(n)] - sub[n] + pe[pos(n)];
+// out[n] = LN(v) * gamma + beta; optional out = post_scale * tanh(out).   One warp per row.
+// ---------------------------------------------------------------------------------------------
+struct LnArgs {
+  const float* a;
+  const float* sub;
+  const float* pe;
+  const float* gamma;
+  const float* beta;
+  float* out;
+  int N, C, Tl, chunk, nfix;
+  int a_mode, pe_mode, tanh_post;
+  float post_scale;
+};
+
+__device__ __forceinline__ long gather_row(int n, int mode, int Tl, int chunk, int nfix) {
+  if (mode == ROWS_DENSE) return n;
+  int b = n / nfix, j = n - b * nfix;
+  long r = (long)b * Tl + (long)chunk * (j + 1);
+  return mode == ROWS_HEAD ? r : r - 1;
+}
+
+__global__ void __launch_bounds__(256) layernorm_rows_f32(const LnArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  const int C = p.C;
+  const float* ar = nullptr;
+  if (p.a_mode != ROWS_ZERO) ar = p.a + gather_row(n, p.a_mode, p.Tl, p.chunk, p.nfix) * (long)C;
+  const float* sr = p.sub ? p.sub + (long)n * C : nullptr;
+  const float* pr = nullptr;
+  if (p.pe_mode == PE_CHUNK_POS) pr = p.pe + (long)((n % p.Tl) % p.chunk) * C;
+  else if (p.pe_mode == PE_ROW0) pr = p.pe;
+  else if (p.pe_mode == PE_ROW_N) pr = p.pe + (long)n * C;
+
+  auto val = [&](int c) -> float {
+    float v = ar ? __ldg(ar + c) : 0.f;
+    if (sr) v = __fsub_rn(v, __ldg(sr + c));
+    if (pr) v = __fadd_rn(v, __ldg(pr + c));
+    return v;
+  };
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += val(c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float d = val(c) - mean;
+    q = fmaf(d, d, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)C + 1e-5f);
+  const float nb = -rstd * mean;
+  for (int c = lane; c < C; c += 32) {
+    float v = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(val(c), rstd), nb), __ldg(p.gamma + c)), __ldg(p.beta + c));
+    if (p.tanh_post) v = __fmul_rn(p.post_scale, tanhf(v));
+    p.out[(long)n * C + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk-local multi-head attention (head dim 128, <= 16 keys per chunk).  One warp per head.
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const float* q;   // q_mode 0: [chunk, C] table; 1: [B*nfix, C]; 2: dense [B*Tl, C]
+  const float* kv;  // [B*Tl, 2C]
+  float* out;       // q_mode 0: [B*Tl, C]; 1: [B*nfix, C]
+  int B, Tl, chunk, heads, nchunks, nfix, q_mode;
+};
+
+__global__ void __launch_bounds__(256) attention_chunk_f32(const AttnArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.heads) return;
+  const int C = p.heads * 128;
+  int b, ck;
+  if (p.q_mode != 1) { b = blockIdx.x / p.nchunks; ck = blockIdx.x % p.nchunks; }
+  else { b = blockIdx.x / p.nfix; ck = blockIdx.x % p.nfix + 1; }
+  const int s = ck * p.chunk;
+  const int tk = min(p.Tl, s + p.chunk) - s;
+  const int hoff = warp * 128 + lane * 4;
+  float4 kr[16], vr[16];
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    if (l < tk) {
+      const float* row = p.kv + ((long)b * p.Tl + s + l) * (2 * C);
+      kr[l] = __ldg(reinterpret_cast<const float4*>(row + hoff));
+      vr[l] = __ldg(reinterpret_cast<const float4*>(row + C + hoff));
+    } else {
+      kr[l] = make_float4(0, 0, 0, 0);
+      vr[l] = make_float4(0, 0, 0, 0);
+    }
+  }
+  const int nq = p.q_mode != 1 ? tk : 1;
+  const float inv_sqrt_dh = 11.313708498984761f;  // sqrt(128): the reference divides by it (:401)
+  for (int i = 0; i < nq; ++i) {
+    const float* qrow = p.q_mode == 0 ? p.q + (long)i * C
+                        : p.q_mode == 1 ? p.q + (long)blockIdx.x * C
+                                        : p.q + ((long)b * p.Tl + s + i) * C;
+    float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + hoff));
+    float sc[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      float d = q4.x * kr[l].x;
+      d = fmaf(q4.y, kr[l].y, d);
+      d = fmaf(q4.z, kr[l].z, d);
+      d = fmaf(q4.w, kr[l].w, d);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      sc[l] = __fdiv_rn(d, inv_sqrt_dh);
+      if (l < tk) mx = fmaxf(mx, sc[l]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      sc[l] = (l < tk) ? expf(sc[l] - mx) : 0.f;
+      sum += sc[l];
+    }
+    float4 o4 = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      float pl = __fdiv_rn(sc[l], sum);
+      o4.x = fmaf(pl, vr[l].x, o4.x);
+      o4.y = fmaf(pl, vr[l].y, o4.y);
+      o4.z = fmaf(pl, vr[l].z, o4.z);
+      o4.w = fmaf(pl, vr[l].w, o4.w);
+    }
+    long orow = p.q_mode != 1 ? ((long)b * p.Tl + s + i) : (long)blockIdx.x;
+    *reinterpret_cast<float4*>(p.out + orow * C + hoff) = o4;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Residual VQ (ResidualVQEMA.forward) -- FP32 CUDA-core version.  32 tokens per CTA, codebooks
+// streamed through shared memory 64 codes at a time; score = x.e - 0.5|e|^2, first maximum wins.
+// ---------------------------------------------------------------------------------------------
+struct RvqArgs {
+  const float* x;       // [N, D]
+  const float* books;   // [n_books][K][D]
+  const float* half_n;  // [n_books][K]   0.5*|e|^2
+  float* qsum;          // [N, D] or null
+  int* idx;             // [B, books_use, Tl] or (single-book nearest) [N]
+  int N, D, K, books_use;
+  int row_mode, B, Tl, chunk, nfix;
+  int idx_flat;         // 1: idx[n] (nearest op)
+};
+
+__global__ void __launch_bounds__(256) rvq_f32(const RvqArgs p) {
+  constexpr int TPW = 4, CH = 64;
+  extern __shared__ float sm[];
+  const int D = p.D, DP = D + 1;
+  float* xs = sm;                   // [32][D]  residual
+  float* qs = xs + 32 * D;          // [32][D]  q_sum
+  float* es = qs + 32 * D;          // [CH][D+1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * D; i += 256) {
+    int t = i / D;
+    int n = n0 + t;
+    xs[i] = n < p.N ? __ldg(p.x + (long)n0 * D + i) : 0.f;
+    qs[i] = 0.f;
+  }
+  __syncthreads();
+  for (int bk = 0; bk < p.books_use; ++bk) {
+    const float* book = p.books + (long)bk * p.K * D;
+    const float* hn = p.half_n + (long)bk * p.K;
+    float best[TPW];
+    int bidx[TPW];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) { best[t] = -INFINITY; bidx[t] = 0x7fffffff; }
+    for (int c0 = 0; c0 < p.K; c0 += CH) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < CH * D; i += 256) {
+        int r = i / D, d = i - r * D;
+        es[r * DP + d] = (c0 + r < p.K) ? __ldg(book + (long)c0 * D + i) : 0.f;
+      }
+      __syncthreads();
+      float acc[TPW][2];
+#pragma unroll
+      for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = 0.f;
+      const float* e0 = es + lane * DP;
+      const float* e1 = es + (lane + 32) * DP;
+      const float* xw = xs + warp * TPW * D;
+      for (int d = 0; d < D; ++d) {
+        float ev0 = e0[d], ev1 = e1[d];
+#pragma unroll
+        for (int t = 0; t < TPW; ++t) {
+          float xv = xw[t * D + d];
+          acc[t][0] = fmaf(xv, ev0, acc[t][0]);
+          acc[t][1] = fmaf(xv, ev1, acc[t][1]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int code = c0 + lane + 32 * h;
+        if (code < p.K) {
+          float hv = __ldg(hn + code);
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) {
+            float s = __fsub_rn(acc[t][h], hv);
+            if (s > best[t]) { best[t] = s; bidx[t] = code; }
+          }
+        }
+      }
+    }
+    // warp arg-max, lowest index wins ties (torch.argmax)
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float bs = best[t];
+      int bi = bidx[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+      }
+      const int tl = warp * TPW + t;
+      const int n = n0 + tl;
+      if (n < p.N) {
+        if (bi >= p.K) bi = 0;
+        const float* e = book + (long)bi * D;
+        for (int d = lane; d < D; d += 32) {
+          float q = __ldg(e + d);
+          float r = xs[tl * D + d];
+          // q_sum = q_sum + (q - residual) + residual ; residual = residual - q   (:433-434)
+          qs[tl * D + d] = __fadd_rn(__fadd_rn(qs[tl * D + d], __fsub_rn(q, r)), r);
+          xs[tl * D + d] = __fsub_rn(r, q);
+        }
+        if (lane == 0) {
+          if (p.idx_flat) p.idx[n] = bi;
+          else {
+            int b, tt;
+            if (p.row_mode == ROWS_DENSE) { b = n / p.Tl; tt = n - b * p.Tl; }
+            else { b = n / p.nfix; tt = p.chunk * (n - b * p.nfix + 1); }
+            p.idx[((long)b * p.books_use + bk) * p.Tl + tt] = bi;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (p.qsum)
+    for (int i = threadIdx.x; i < 32 * D; i += 256)
+      if (n0 + i / D < p.N) p.qsum[(long)n0 * D + i] = qs[i];
+}
+
+// 0.5 * |e_k|^2 for caller-provided codebooks (nearest op)
+__global__ void half_sqnorm_f32(const float* __restrict__ emb, float* __restrict__ out, int K, int D) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) { float v = __ldg(emb + (long)k * D + d); s = fmaf(v, v, s); }
+  out[k] = 0.5f * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dac ResidualVectorQuantize (eval): all stages fused, one warp per token, residual and the
+// running z_q in registers (C = 32 * CPL channels, codebook dim 8).
+// Packed stage layout (floats): Win[8][C] | bin[8] | cbn[K][8] | c2[K] | cb[K][8] | Wout[C][8] | bout[C]
+// ---------------------------------------------------------------------------------------------
+struct DacRvqArgs {
+  const float* z;   // [N, C]
+  const float* w;   // packed stages
+  float* zq;        // [N, C]
+  int* codes;       // [B, n_q, Tl]
+  int N, C, K, n_q, Tl;
+  long stage_stride;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(256) dac_rvq_f32(const DacRvqArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  const int C = p.C, K = p.K;
+  float r[CPL], zq[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    r[i] = __ldg(p.z + (long)n * C + lane + 32 * i);
+    zq[i] = 0.f;
+  }
+  const int b = n / p.Tl, t = n - b * p.Tl;
+  for (int st = 0; st < p.n_q; ++st) {
+    const float* Win = p.w + st * p.stage_stride;
+    const float* bin = Win + 8 * C;
+    const float* cbn = bin + 8;
+    const float* c2 = cbn + (long)K * 8;
+    const float* cb = c2 + K;
+    const float* Wout = cb + (long)K * 8;
+    const float* bout = Wout + (long)C * 8;
+    // in_proj (1x1 conv C -> 8)
+    float ze[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) s = fmaf(__ldg(Win + (long)d * C + lane + 32 * i), r[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      ze[d] = __fadd_rn(s, __ldg(bin + d));
+    }
+    // F.normalize(encodings): x / max(|x|, 1e-12)
+    float nn = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) nn = fmaf(ze[d], ze[d], nn);
+    const float den = fmaxf(sqrtf(nn), 1e-12f);
+    float en[8];
+    float e2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { en[d] = __fdiv_rn(ze[d], den); }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) e2 = __fadd_rn(e2, __fmul_rn(en[d], en[d]));
+    // dist = |enc|^2 - 2 enc.cb + |cb|^2 ; first minimum of dist (== first maximum of -dist)
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      float4 c0 = __ldg(reinterpret_cast<const float4*>(cbn + (long)k * 8));
+      float4 c1 = __ldg(reinterpret_cast<const float4*>(cbn + (long)k * 8 + 4));
+      float dot = (2.f * en[0]) * c0.x;
+      dot = fmaf(2.f * en[1], c0.y, dot);
+      dot = fmaf(2.f * en[2], c0.z, dot);
+      dot = fmaf(2.f * en[3], c0.w, dot);
+      dot = fmaf(2.f * en[4], c1.x, dot);
+      dot = fmaf(2.f * en[5], c1.y, dot);
+      dot = fmaf(2.f * en[6], c1.z, dot);
+      dot = fmaf(2.f * en[7], c1.w, dot);
+      float dist = __fadd_rn(__fsub_rn(e2, dot), __ldg(c2 + k));
+      if (dist < best) { best = dist; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float os = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
+    }
+    if (bi >= K) bi = 0;
+    if (lane == 0) p.codes[((long)b * p.n_q + st) * p.Tl + t] = bi;
+    // straight-through value z_e + (z_q - z_e), then out_proj (1x1 conv 8 -> C)
+    float stv[8];
+    {
+      float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8));
+      float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8 + 4));
+      float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int d = 0; d < 8; ++d) stv[d] = __fadd_rn(ze[d], __fsub_rn(qv[d], ze[d]));
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      int c = lane + 32 * i;
+      float4 w0 = __ldg(reinterpret_cast<const float4*>(Wout + (long)c * 8));
+      float4 w1 = __ldg(reinterpret_cast<const float4*>(Wout + (long)c * 8 + 4));
+      float o = w0.x * stv[0];
+      o = fmaf(w0.y, stv[1], o);
+      o = fmaf(w0.z, stv[2], o);
+      o = fmaf(w0.w, stv[3], o);
+      o = fmaf(w1.x, stv[4], o);
+      o = fmaf(w1.y, stv[5], o);
+      o = fmaf(w1.z, stv[6], o);
+      o = fmaf(w1.w, stv[7], o);
+      o = __fadd_rn(o, __ldg(bout + c));
+      zq[i] = __fadd_rn(zq[i], o);
+      r[i] = __fsub_rn(r[i], o);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) p.zq[(long)n * C + lane + 32 * i] = zq[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// small data-movement kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_brc_f32(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* ib = in + (size_t)b * R * C;
+  float* ob = out + (size_t)b * R * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? ib[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) ob[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void scatter_heads_f32(const float* __restrict__ src, float* __restrict__ dst, int nfix, int Tl, int chunk,
+                                  int C, long total) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long n = i / C;
+  int c = (int)(i - n * C);
+  int b = (int)(n / nfix), j = (int)(n - (long)b * nfix);
+  dst[((long)b * Tl + (long)chunk * (j + 1)) * C + c] = src[i];
+}
+
+__global__ void widen_i32_i64(const int* __restrict__ in, long long* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+}  // namespace b2c

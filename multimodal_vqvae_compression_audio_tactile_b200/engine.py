@@ -1,0 +1,549 @@
+"""Host-side engine: packs module weights into a libb2c context and emits the
+straight-line programs (lists of CUDA kernel launches) for the encoder, the DAC
+quantizer, the predictor/residual-VQ two-pass schedule and the decoder.
+
+PyTorch is used here for device memory and streams only; all arithmetic runs in
+libb2c.so (hand-written sm_100a CUDA).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+ALIGN = 256
+
+
+def _np32(t: torch.Tensor) -> np.ndarray:
+    return np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Arena:
+    """First-fit allocator over the program workspace (offsets only; lifetimes are known
+    while the program is being emitted)."""
+
+    def __init__(self):
+        self.free_list = []   # (off, size)
+        self.top = 0
+        self.peak = 0
+        self.live = {}
+
+    def alloc(self, nbytes: int) -> int:
+        n = (max(int(nbytes), 1) + ALIGN - 1) // ALIGN * ALIGN
+        for i, (off, size) in enumerate(self.free_list):
+            if size >= n:
+                if size == n:
+                    self.free_list.pop(i)
+                else:
+                    self.free_list[i] = (off + n, size - n)
+                self.live[off] = n
+                return off
+        off = self.top
+        self.top += n
+        self.peak = max(self.peak, self.top)
+        self.live[off] = n
+        return off
+
+    def free(self, off):
+        if off is None:
+            return
+        n = self.live.pop(off)
+        self.free_list.append((off, n))
+        self.free_list.sort()
+        merged = []
+        for o, s in self.free_list:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        if merged and merged[-1][0] + merged[-1][1] == self.top:
+            self.top = merged[-1][0]
+            merged.pop()
+        self.free_list = merged
+
+
+@dataclass
+class ConvW:
+    wid: int
+    cin: int
+    cout: int
+    k: int
+    stride: int = 1
+    dilation: int = 1
+    padding: int = 0
+    transposed: bool = False
+
+
+@dataclass
+class Program:
+    handle: C.c_void_p
+    ws_bytes: int
+    n_ext: int
+    info: dict = field(default_factory=dict)
+
+
+class Engine:
+    """One libb2c context (= one set of packed weights on one device)."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise L.B2CError("b200 codec modules only run on CUDA tensors (sm_100a); there is no CPU path")
+        self.lib = L.load()
+        self.device = device
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        L.check(self.lib.b2c_ctx_create(idx, C.byref(h)), "b2c_ctx_create")
+        self.ctx = h
+        self.programs = {}
+        self._ws = None
+        self._keep = []  # host arrays kept alive during packing
+
+    def __del__(self):
+        try:
+            for p in self.programs.values():
+                self.lib.b2c_prog_destroy(p.handle)
+            self.lib.b2c_ctx_destroy(self.ctx)
+        except Exception:
+            pass
+
+    # ------------------------------ packing ------------------------------
+    def pack_wnconv(self, m) -> ConvW:
+        """m: modules.WNConv1d / WNConvTranspose1d (weight_g, weight_v, bias)."""
+        v, g = _np32(m.weight_v), _np32(m.weight_g).reshape(-1)
+        b = _np32(m.bias) if m.bias is not None else None
+        tr = bool(getattr(m, "transposed", False))
+        if tr:
+            cin, cout, k = v.shape
+        else:
+            cout, cin, k = v.shape
+        wid = L.check(self.lib.b2c_pack_conv(self.ctx, _fp(v), _fp(g), _fp(b) if b is not None else None,
+                                             cout, cin, k, int(tr), m.stride, m.padding), "b2c_pack_conv")
+        return ConvW(wid, cin, cout, k, m.stride, m.dilation, m.padding, tr)
+
+    def pack_plain(self, weight: torch.Tensor, bias=None) -> ConvW:
+        """nn.Linear [cout, cin] or nn.Conv1d(k=1) [cout, cin, 1] weights."""
+        v = _np32(weight)
+        if v.ndim == 2:
+            v = v[:, :, None]
+        cout, cin, k = v.shape
+        v = np.ascontiguousarray(v)
+        b = _np32(bias) if bias is not None else None
+        wid = L.check(self.lib.b2c_pack_conv(self.ctx, _fp(v), None, _fp(b) if b is not None else None,
+                                             cout, cin, k, 0, 1, 0), "b2c_pack_conv")
+        return ConvW(wid, cin, cout, k)
+
+    def pack_vec(self, t: torch.Tensor) -> int:
+        a = _np32(t).reshape(-1)
+        return L.check(self.lib.b2c_pack_vector(self.ctx, _fp(a), a.size), "b2c_pack_vector")
+
+    def pack_books(self, books) -> int:
+        arrs = [_np32(b) for b in books]
+        k, d = arrs[0].shape
+        ptrs = (C.POINTER(C.c_float) * len(arrs))(*[_fp(a) for a in arrs])
+        return L.check(self.lib.b2c_pack_codebooks(self.ctx, ptrs, len(arrs), k, d), "b2c_pack_codebooks")
+
+    def pack_dac_rvq(self, quantizers) -> int:
+        keep = []
+
+        def col(fn):
+            arrs = [fn(q) for q in quantizers]
+            keep.append(arrs)
+            return (C.POINTER(C.c_float) * len(arrs))(*[_fp(a) for a in arrs])
+
+        n_q = len(quantizers)
+        q0 = quantizers[0]
+        d, c, _ = q0.in_proj.weight_v.shape
+        k = q0.codebook.weight.shape[0]
+        return L.check(self.lib.b2c_pack_dac_rvq(
+            self.ctx, n_q, c, d, k,
+            col(lambda q: _np32(q.in_proj.weight_v)), col(lambda q: _np32(q.in_proj.weight_g).reshape(-1)),
+            col(lambda q: _np32(q.in_proj.bias)),
+            col(lambda q: _np32(q.out_proj.weight_v)), col(lambda q: _np32(q.out_proj.weight_g).reshape(-1)),
+            col(lambda q: _np32(q.out_proj.bias)),
+            col(lambda q: _np32(q.codebook.weight))), "b2c_pack_dac_rvq")
+
+    def weight_bytes(self) -> int:
+        return int(self.lib.b2c_ctx_weight_bytes(self.ctx))
+
+    # ------------------------------ running ------------------------------
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(nbytes, ALIGN), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def run(self, prog: Program, ext_ptrs):
+        ws = self.workspace(prog.ws_bytes)
+        arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.b2c_prog_run(prog.handle, C.c_void_p(stream), C.c_void_p(ws.data_ptr()), ws.numel(), arr,
+                                      len(ext_ptrs)), "b2c_prog_run")
+
+    def run_host(self, prog: Program, ext_ptrs, h2d, d2h):
+        """h2d / d2h: lists of (host_ptr, slot, nbytes).  Synchronises the stream."""
+        ws = self.workspace(prog.ws_bytes)
+        arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
+        hin = (L.HostCopy * max(len(h2d), 1))(*[L.HostCopy(p, s, n) for p, s, n in h2d])
+        hout = (L.HostCopy * max(len(d2h), 1))(*[L.HostCopy(p, s, n) for p, s, n in d2h])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.b2c_prog_run_host(prog.handle, C.c_void_p(stream), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                           arr, len(ext_ptrs), hin, len(h2d), hout, len(d2h)), "b2c_prog_run_host")
+
+
+class Emitter:
+    """Builds one program.  Buffers are workspace offsets (ints) or ('ext', slot, off)."""
+
+    def __init__(self, eng: Engine):
+        self.eng = eng
+        self.lib = eng.lib
+        h = C.c_void_p()
+        L.check(self.lib.b2c_prog_create(eng.ctx, C.byref(h)), "b2c_prog_create")
+        self.h = h
+        self.arena = Arena()
+
+    # buffers
+    def new(self, nfloats: int) -> int:
+        return self.arena.alloc(4 * nfloats)
+
+    def drop(self, *offs):
+        for o in offs:
+            if isinstance(o, int):
+                self.arena.free(o)
+
+    @staticmethod
+    def ext(slot: int, off_bytes: int = 0):
+        return ("ext", slot, off_bytes)
+
+    @staticmethod
+    def _r(buf):
+        if buf is None:
+            return L.NULL_REF
+        if isinstance(buf, tuple):
+            return L.ref(buf[1], buf[2])
+        return L.ref(0, buf)
+
+    def finish(self, n_ext: int, **info) -> Program:
+        return Program(self.h, self.arena.peak + ALIGN, n_ext, dict(info, launches=self.lib.b2c_prog_num_launches(self.h)))
+
+    # ops
+    def stem(self, w: ConvW, x, out_raw, out_act, alpha, B, Lx):
+        L.check(self.lib.b2c_prog_stem(self.h, w.wid, self._r(x), self._r(out_raw), self._r(out_act),
+                                       L.ACT_SNAKE if alpha is not None else L.ACT_NONE,
+                                       alpha if alpha is not None else -1, B, Lx), "b2c_prog_stem")
+
+    def conv(self, w: ConvW, x, B, Lin, *, res=None, out_raw=None, out_act=None, act=L.ACT_NONE, alpha=None,
+             res_mode=0, Tl=0, chunk=0, prec=L.PREC_F32, stride=None, dilation=None, padding=None):
+        if alpha is not None:
+            act = L.ACT_SNAKE
+        L.check(self.lib.b2c_prog_conv(self.h, w.wid, self._r(x), self._r(res), self._r(out_raw), self._r(out_act),
+                                       act, alpha if alpha is not None else -1, B, Lin,
+                                       w.stride if stride is None else stride,
+                                       w.dilation if dilation is None else dilation,
+                                       w.padding if padding is None else padding, res_mode, Tl, chunk, prec),
+                "b2c_prog_conv")
+
+    def convT(self, w: ConvW, x, B, Lin, *, out_raw=None, out_act=None, alpha=None, prec=L.PREC_F32):
+        L.check(self.lib.b2c_prog_convT(self.h, w.wid, self._r(x), self._r(out_raw), self._r(out_act),
+                                        L.ACT_SNAKE if alpha is not None else L.ACT_NONE,
+                                        alpha if alpha is not None else -1, B, Lin, prec), "b2c_prog_convT")
+
+    def head(self, w: ConvW, x, y, B, Lx):
+        L.check(self.lib.b2c_prog_head(self.h, w.wid, self._r(x), self._r(y), B, Lx), "b2c_prog_head")
+
+    def layernorm(self, gamma, beta, a, a_mode, out, N, Cc, Tl, chunk, *, sub=None, pe=-1, pe_mode=L.PE_NONE,
+                  tanh_post=0, post_scale=1.0):
+        L.check(self.lib.b2c_prog_layernorm(self.h, gamma, beta, self._r(a), a_mode, self._r(sub), pe, pe_mode,
+                                            tanh_post, post_scale, self._r(out), N, Cc, Tl, chunk),
+                "b2c_prog_layernorm")
+
+    def attention(self, q, q_mode, kv, out, B, Tl, chunk, heads, dh):
+        L.check(self.lib.b2c_prog_attention(self.h, self._r(q), q_mode, self._r(kv), self._r(out), B, Tl, chunk,
+                                            heads, dh), "b2c_prog_attention")
+
+    def rvq(self, books_wid, books_use, x, qsum, idx, N, row_mode, B, Tl, chunk):
+        L.check(self.lib.b2c_prog_rvq(self.h, books_wid, books_use, self._r(x), self._r(qsum), self._r(idx), N,
+                                      row_mode, B, Tl, chunk), "b2c_prog_rvq")
+
+    def nearest(self, x, emb, scratch, idx, N, D, K, prec=L.PREC_F32):
+        L.check(self.lib.b2c_prog_nearest(self.h, self._r(x), self._r(emb), self._r(scratch), self._r(idx), N, D, K,
+                                          prec), "b2c_prog_nearest")
+
+    def dac_rvq(self, wid, n_q, z, zq, codes, B, Tl):
+        L.check(self.lib.b2c_prog_dac_rvq(self.h, wid, n_q, self._r(z), self._r(zq), self._r(codes), B, Tl),
+                "b2c_prog_dac_rvq")
+
+    def scatter_heads(self, src, dst, B, Tl, chunk, Cc):
+        L.check(self.lib.b2c_prog_scatter_heads(self.h, self._r(src), self._r(dst), B, Tl, chunk, Cc),
+                "b2c_prog_scatter_heads")
+
+    def transpose(self, src, dst, B, R, Cc):
+        L.check(self.lib.b2c_prog_transpose(self.h, self._r(src), self._r(dst), B, R, Cc), "b2c_prog_transpose")
+
+    def widen(self, src, dst, n):
+        L.check(self.lib.b2c_prog_i32_to_i64(self.h, self._r(src), self._r(dst), n), "b2c_prog_i32_to_i64")
+
+
+# ---------------------------------------------------------------------------------------------
+# packed sub-graphs + emitters
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class PackedRU:
+    a1: int
+    c7: ConvW
+    a2: int
+    c1: ConvW
+
+
+def _pack_ru(eng: Engine, ru) -> PackedRU:
+    s1, c7, s2, c1 = ru.block[0], ru.block[1], ru.block[2], ru.block[3]
+    return PackedRU(eng.pack_vec(s1.alpha), eng.pack_wnconv(c7), eng.pack_vec(s2.alpha), eng.pack_wnconv(c1))
+
+
+@dataclass
+class PackedEncoder:
+    stem: ConvW
+    blocks: list      # [(ru0, ru1, ru2, alpha_down, down ConvW)]
+    a_final: int
+    head: ConvW
+    strides: list
+
+    @staticmethod
+    def pack(eng: Engine, enc) -> "PackedEncoder":
+        layers = list(enc.block)
+        stem = eng.pack_wnconv(layers[0])
+        blocks, strides = [], []
+        for eb in layers[1:-2]:
+            b = eb.block
+            blocks.append((_pack_ru(eng, b[0]), _pack_ru(eng, b[1]), _pack_ru(eng, b[2]), eng.pack_vec(b[3].alpha),
+                           eng.pack_wnconv(b[4])))
+            strides.append(b[4].stride)
+        return PackedEncoder(stem, blocks, eng.pack_vec(layers[-2].alpha), eng.pack_wnconv(layers[-1]), strides)
+
+    def out_len(self, T: int) -> int:
+        Lx = T
+        for (_, _, _, _, dn) in self.blocks:
+            Lx = (Lx + 2 * dn.padding - (dn.k - 1) - 1) // dn.stride + 1
+        hd = self.head
+        return (Lx + 2 * hd.padding - (hd.k - 1) - 1) // hd.stride + 1
+
+
+def _emit_ru(em: Emitter, ru: PackedRU, x_raw, x_act, B, Lx, next_alpha, need_raw, prec):
+    """ResidualUnit: y = x + conv1(snake(conv7(snake(x)))).  x_act = snake1(x_raw) already exists.
+    Returns (y_raw or None, y_act = snake_next(y))."""
+    C_ = ru.c7.cout
+    h_act = em.new(B * Lx * C_)
+    em.conv(ru.c7, x_act, B, Lx, out_act=h_act, alpha=ru.a2, prec=prec)
+    em.drop(x_act)
+    y_raw = em.new(B * Lx * C_) if need_raw else None
+    y_act = em.new(B * Lx * C_)
+    em.conv(ru.c1, h_act, B, Lx, res=x_raw, out_raw=y_raw, out_act=y_act, alpha=next_alpha, prec=prec)
+    em.drop(h_act, x_raw)
+    return y_raw, y_act
+
+
+def emit_encoder(em: Emitter, pe: PackedEncoder, x, B, T, prec):
+    """x: [B, T] -> returns (z buffer [B, Tl, C], Tl)."""
+    c0 = pe.stem.cout
+    Lx = T
+    x_raw = em.new(B * Lx * c0)
+    x_act = em.new(B * Lx * c0)
+    em.stem(pe.stem, x, x_raw, x_act, pe.blocks[0][0].a1, B, Lx)
+    for bi, (r0, r1, r2, a_dn, dn) in enumerate(pe.blocks):
+        x_raw, x_act = _emit_ru(em, r0, x_raw, x_act, B, Lx, r1.a1, True, prec)
+        x_raw, x_act = _emit_ru(em, r1, x_raw, x_act, B, Lx, r2.a1, True, prec)
+        x_raw, x_act = _emit_ru(em, r2, x_raw, x_act, B, Lx, a_dn, False, prec)
+        Lo = (Lx + 2 * dn.padding - (dn.k - 1) - 1) // dn.stride + 1
+        last = bi == len(pe.blocks) - 1
+        n_raw = None if last else em.new(B * Lo * dn.cout)
+        n_act = em.new(B * Lo * dn.cout)
+        em.conv(dn, x_act, B, Lx, out_raw=n_raw, out_act=n_act,
+                alpha=pe.a_final if last else pe.blocks[bi + 1][0].a1, prec=prec)
+        em.drop(x_act)
+        x_raw, x_act, Lx = n_raw, n_act, Lo
+    hd = pe.head
+    Lo = (Lx + 2 * hd.padding - (hd.k - 1) - 1) // hd.stride + 1
+    z = em.new(B * Lo * hd.cout)
+    em.conv(hd, x_act, B, Lx, out_raw=z, prec=prec)
+    em.drop(x_act)
+    return z, Lo
+
+
+@dataclass
+class PackedDecoder:
+    stem: ConvW
+    blocks: list   # [(alpha_up, up ConvW, ru0, ru1, ru2)]
+    a_final: int
+    head: ConvW
+
+    @staticmethod
+    def pack(eng: Engine, dec) -> "PackedDecoder":
+        layers = list(dec.model)
+        stem = eng.pack_wnconv(layers[0])
+        blocks = []
+        for db in layers[1:-3]:
+            b = db.block
+            blocks.append((eng.pack_vec(b[0].alpha), eng.pack_wnconv(b[1]), _pack_ru(eng, b[2]), _pack_ru(eng, b[3]),
+                           _pack_ru(eng, b[4])))
+        return PackedDecoder(stem, blocks, eng.pack_vec(layers[-3].alpha), eng.pack_wnconv(layers[-2]))
+
+    def out_len(self, Tl: int) -> int:
+        Lx = Tl + 2 * self.stem.padding - (self.stem.k - 1)
+        for (_, up, *_r) in self.blocks:
+            Lx = (Lx - 1) * up.stride - 2 * up.padding + up.k
+        return Lx + 2 * self.head.padding - (self.head.k - 1)
+
+
+def emit_decoder(em: Emitter, pd: PackedDecoder, z, y, B, Tl, prec, free_input=True):
+    """z: [B, Tl, C] buffer -> y: [B, Lout] buffer."""
+    Lx = Tl
+    x_act = em.new(B * Lx * pd.stem.cout)
+    em.conv(pd.stem, z, B, Lx, out_act=x_act, alpha=pd.blocks[0][0], prec=prec)
+    if free_input:
+        em.drop(z)
+    for bi, (a_up, up, r0, r1, r2) in enumerate(pd.blocks):
+        Lo = (Lx - 1) * up.stride - 2 * up.padding + up.k
+        x_raw = em.new(B * Lo * up.cout)
+        n_act = em.new(B * Lo * up.cout)
+        em.convT(up, x_act, B, Lx, out_raw=x_raw, out_act=n_act, alpha=r0.a1, prec=prec)
+        em.drop(x_act)
+        x_act, Lx = n_act, Lo
+        nxt = pd.blocks[bi + 1][0] if bi + 1 < len(pd.blocks) else pd.a_final
+        x_raw, x_act = _emit_ru(em, r0, x_raw, x_act, B, Lx, r1.a1, True, prec)
+        x_raw, x_act = _emit_ru(em, r1, x_raw, x_act, B, Lx, r2.a1, True, prec)
+        x_raw, x_act = _emit_ru(em, r2, x_raw, x_act, B, Lx, nxt, False, prec)
+    em.head(pd.head, x_act, y, B, Lx)
+    em.drop(x_act)
+    return Lx
+
+
+@dataclass
+class PackedPredictor:
+    """CrossPredictor + TokenNorm + scale + proj_down/up + ResidualVQEMA of ProposedEval."""
+    pe: int
+    lnq_g: int
+    lnq_b: int
+    lnkv_g: int
+    lnkv_b: int
+    wq: ConvW
+    wkv: ConvW
+    wo: ConvW
+    lnf_g: int
+    lnf_b: int
+    w1: ConvW
+    w2: ConvW
+    heads: int
+    dh: int
+    c: int
+    # codec-level
+    tn_g: int = -1
+    tn_b: int = -1
+    scale: float = 0.08
+    down: ConvW = None
+    up: ConvW = None
+    books: int = -1
+    n_books: int = 0
+    code_dim: int = 0
+
+    @staticmethod
+    def pack_predictor(eng: Engine, pr, max_chunk=64) -> "PackedPredictor":
+        c = pr.q_proj.weight.shape[0]
+        pe = eng.pack_vec(pr.pos.pe[:max_chunk].contiguous())
+        wkv = torch.cat([pr.k_proj.weight.detach(), pr.v_proj.weight.detach()], dim=0)
+        return PackedPredictor(
+            pe=pe,
+            lnq_g=eng.pack_vec(pr.ln_q.weight), lnq_b=eng.pack_vec(pr.ln_q.bias),
+            lnkv_g=eng.pack_vec(pr.ln_kv.weight), lnkv_b=eng.pack_vec(pr.ln_kv.bias),
+            wq=eng.pack_plain(pr.q_proj.weight), wkv=eng.pack_plain(wkv), wo=eng.pack_plain(pr.out.weight),
+            lnf_g=eng.pack_vec(pr.ffn[0].weight), lnf_b=eng.pack_vec(pr.ffn[0].bias),
+            w1=eng.pack_plain(pr.ffn[1].weight, pr.ffn[1].bias), w2=eng.pack_plain(pr.ffn[3].weight, pr.ffn[3].bias),
+            heads=pr.h, dh=pr.dh, c=c)
+
+
+def emit_predict_rows(em: Emitter, pp: PackedPredictor, qn, ctx, N, Tl, chunk, qn_is_table, prec):
+    """Everything after attention for N rows: y = out(ctx) + qn; z_pred = y + ffn(y).
+    qn: LayerNorm-ed queries ([chunk, C] table when qn_is_table else [N, C]).  Frees ctx."""
+    c = pp.c
+    y1 = em.new(N * c)
+    em.conv(pp.wo, ctx, 1, N, res=qn, out_raw=y1, res_mode=1 if qn_is_table else 0, Tl=Tl, chunk=chunk, prec=prec)
+    em.drop(ctx)
+    h = em.new(N * c)
+    em.layernorm(pp.lnf_g, pp.lnf_b, y1, L.ROWS_DENSE, h, N, c, Tl, chunk)
+    f1 = em.new(N * pp.w1.cout)
+    em.conv(pp.w1, h, 1, N, out_act=f1, act=L.ACT_GELU, prec=prec)
+    em.drop(h)
+    z_pred = em.new(N * c)
+    em.conv(pp.w2, f1, 1, N, res=y1, out_raw=z_pred, prec=prec)
+    em.drop(f1, y1)
+    return z_pred
+
+
+def emit_residual_code(em: Emitter, pp: PackedPredictor, zt, zt_mode, z_pred, N, B, Tl, chunk, books_use, idx,
+                       row_mode, z_hat, prec):
+    """r = zt - z_pred; rD = proj_down(scale*tanh(LN(r))); qD = RVQ(rD); z_hat = proj_up(qD) + z_pred."""
+    c = pp.c
+    rn = em.new(N * c)
+    em.layernorm(pp.tn_g, pp.tn_b, zt, zt_mode, rn, N, c, Tl, chunk, sub=z_pred, tanh_post=1, post_scale=pp.scale)
+    rd = em.new(N * pp.code_dim)
+    em.conv(pp.down, rn, 1, N, out_raw=rd, prec=prec)
+    em.drop(rn)
+    qd = em.new(N * pp.code_dim)
+    em.rvq(pp.books, books_use, rd, qd, idx, N, row_mode, B, Tl, chunk)
+    em.drop(rd)
+    em.conv(pp.up, qd, 1, N, res=z_pred, out_raw=z_hat, prec=prec)
+    em.drop(qd)
+
+
+def emit_latent_coder(em: Emitter, pp: PackedPredictor, qa, zt, z_run, idx, B, Tl, chunk, books_use, prec):
+    """The reference's 5-chunk AR loop (Evaluation/dac_vcpwq_proposed6_latency.py:462-477) as two
+    dependent passes: pass 1 = all tokens with a zero query input, pass 2 = the first
+    token of chunks 1.. with the previous chunk's last reconstructed latent as query input."""
+    c = pp.c
+    N = B * Tl
+    # K/V for every token
+    kvn = em.new(N * c)
+    em.layernorm(pp.lnkv_g, pp.lnkv_b, qa, L.ROWS_DENSE, kvn, N, c, Tl, chunk, pe=pp.pe, pe_mode=L.PE_CHUNK_POS)
+    kv = em.new(N * 2 * c)
+    em.conv(pp.wkv, kvn, 1, N, out_raw=kv, prec=prec)
+    em.drop(kvn)
+    # pass 1: queries are LN_q(pe[pos]) -- a [chunk, C] table
+    qn_tab = em.new(chunk * c)
+    em.layernorm(pp.lnq_g, pp.lnq_b, None, L.ROWS_ZERO, qn_tab, chunk, c, Tl, chunk, pe=pp.pe, pe_mode=L.PE_ROW_N)
+    q_tab = em.new(chunk * c)
+    em.conv(pp.wq, qn_tab, 1, chunk, out_raw=q_tab, prec=prec)
+    ctx = em.new(N * c)
+    em.attention(q_tab, 0, kv, ctx, B, Tl, chunk, pp.heads, pp.dh)
+    em.drop(q_tab)
+    z_pred = emit_predict_rows(em, pp, qn_tab, ctx, N, Tl, chunk, True, prec)
+    em.drop(qn_tab)
+    emit_residual_code(em, pp, zt, L.ROWS_DENSE, z_pred, N, B, Tl, chunk, books_use, idx, L.ROWS_DENSE, z_run, prec)
+    em.drop(z_pred)
+    # pass 2: chunk heads
+    nfix = (Tl + chunk - 1) // chunk - 1
+    if nfix > 0:
+        N2 = B * nfix
+        qn2 = em.new(N2 * c)
+        em.layernorm(pp.lnq_g, pp.lnq_b, z_run, L.ROWS_HEAD_PREV, qn2, N2, c, Tl, chunk, pe=pp.pe,
+                     pe_mode=L.PE_ROW0)
+        q2 = em.new(N2 * c)
+        em.conv(pp.wq, qn2, 1, N2, out_raw=q2, prec=prec)
+        ctx2 = em.new(N2 * c)
+        em.attention(q2, 1, kv, ctx2, B, Tl, chunk, pp.heads, pp.dh)
+        em.drop(q2)
+        z_pred2 = emit_predict_rows(em, pp, qn2, ctx2, N2, Tl, chunk, False, prec)
+        em.drop(qn2)
+        z_hat2 = em.new(N2 * c)
+        emit_residual_code(em, pp, zt, L.ROWS_HEAD, z_pred2, N2, B, Tl, chunk, books_use, idx, L.ROWS_HEAD, z_hat2,
+                           prec)
+        em.drop(z_pred2)
+        em.scatter_heads(z_hat2, z_run, B, Tl, chunk, c)
+        em.drop(z_hat2)
+    em.drop(kv)

@@ -1,0 +1,576 @@
+"""Drop-in PyTorch modules for the reference's encode -> quantize -> decode path.
+
+Same constructor arguments, attribute names, call signatures and state-dict keys as
+the modules the reference scripts assemble
+(Evaluation/dac_vcpwq_proposed6_latency.py:339-487, :527-535; the ``dac`` package's
+Encoder / ResidualVectorQuantize / Decoder), so a checkpoint
+written by Training/compare_dacvsproposal_*.py loads with ``load_state_dict`` and the
+Evaluation / PLC scripts can call ``forward_eval`` / ``encode_latents`` / ``T_DEC``
+unchanged.  The arithmetic does NOT run in PyTorch: ``forward`` hands raw device
+pointers to libb2c.so (hand-written sm_100a CUDA) on the current CUDA stream.
+Forward only (``torch.no_grad`` semantics); CPU tensors raise -- there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import (Emitter, Engine, PackedDecoder, PackedEncoder, PackedPredictor, emit_decoder, emit_encoder,
+                     emit_latent_coder, emit_predict_rows)
+
+CODE_DIM = 96       # Evaluation/dac_vcpwq_proposed6_latency.py:336
+AR_CHUNK_TOK = 16   # :337
+
+
+# ------------------------------------------------------------------------------------------
+# parameter containers (names / shapes follow torch's old-style weight_norm and the dac package)
+# ------------------------------------------------------------------------------------------
+class _Fused(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(f"{type(self).__name__} runs fused inside its parent's CUDA program; call the parent")
+
+
+class WNConv1d(_Fused):
+    transposed = False
+
+    def __init__(self, cin, cout, k, stride=1, dilation=1, padding=0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = cin, cout, k
+        self.stride, self.dilation, self.padding = stride, dilation, padding
+        conv = nn.Conv1d(cin, cout, k)  # default init of the wrapped conv, then g = ||v||
+        self.bias = nn.Parameter(conv.bias.detach().clone())
+        v = conv.weight.detach().clone()
+        self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).view(-1, 1, 1))
+        self.weight_v = nn.Parameter(v)
+
+
+class WNConvTranspose1d(_Fused):
+    transposed = True
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = cin, cout, k
+        self.stride, self.dilation, self.padding = stride, 1, padding
+        conv = nn.ConvTranspose1d(cin, cout, k, stride=stride, padding=padding)
+        self.bias = nn.Parameter(conv.bias.detach().clone())
+        v = conv.weight.detach().clone()
+        self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).view(-1, 1, 1))
+        self.weight_v = nn.Parameter(v)
+
+
+class Snake1d(_Fused):
+    def __init__(self, channels):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, channels, 1))
+
+
+class ResidualUnit(_Fused):
+    def __init__(self, dim, dilation):
+        super().__init__()
+        self.block = nn.Sequential(Snake1d(dim), WNConv1d(dim, dim, 7, dilation=dilation, padding=3 * dilation),
+                                   Snake1d(dim), WNConv1d(dim, dim, 1))
+
+
+class EncoderBlock(_Fused):
+    def __init__(self, dim, stride):
+        super().__init__()
+        self.block = nn.Sequential(ResidualUnit(dim // 2, 1), ResidualUnit(dim // 2, 3), ResidualUnit(dim // 2, 9),
+                                   Snake1d(dim // 2),
+                                   WNConv1d(dim // 2, dim, 2 * stride, stride=stride, padding=math.ceil(stride / 2)))
+
+
+class DecoderBlock(_Fused):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.block = nn.Sequential(Snake1d(cin),
+                                   WNConvTranspose1d(cin, cout, 2 * stride, stride=stride,
+                                                     padding=math.ceil(stride / 2)),
+                                   ResidualUnit(cout, 1), ResidualUnit(cout, 3), ResidualUnit(cout, 9))
+
+
+# ------------------------------------------------------------------------------------------
+# engine plumbing shared by the top-level modules
+# ------------------------------------------------------------------------------------------
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise L.B2CError("b200 codec: input tensor is on %s; this implementation only runs on a B200 "
+                             "(sm_100a) CUDA device and has no CPU fallback" % t.device)
+
+
+class _Top(nn.Module):
+    """A module that owns an Engine (packed weights + cached programs)."""
+
+    #: contraction arithmetic: 'f32' (CUDA-core FFMA), 'bf16x3' / 'bf16' (tcgen05)
+    precision = "f32"
+    #: signals per program launch (bounds the activation workspace)
+    micro_batch = 32
+
+    def _engine(self, device) -> Engine:
+        ver = tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+        st = self.__dict__.get("_b2c_state")
+        if st is None or st[0] != ver or st[1].device != device:
+            eng = Engine(device)
+            packed = self._pack(eng)
+            st = (ver, eng, packed)
+            self.__dict__["_b2c_state"] = st
+        return st[1], st[2]
+
+    def _pack(self, eng):  # pragma: no cover
+        raise NotImplementedError
+
+    def _prec(self, key=None):
+        p = self.precision
+        if isinstance(p, dict):
+            p = p.get(key, "f32")
+        return L.PRECISIONS[p]
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop("_b2c_state", None)
+        return d
+
+
+def _as_f32(x):
+    return x.detach().to(torch.float32).contiguous()
+
+
+def _convs(module):
+    return [m for m in module.modules() if isinstance(m, (WNConv1d, WNConvTranspose1d))]
+
+
+def encoder_out_len(enc, T: int) -> int:
+    n = T
+    for m in _convs(enc):
+        n = (n + 2 * m.padding - m.dilation * (m.kernel_size - 1) - 1) // m.stride + 1
+    return n
+
+
+def decoder_out_len(dec, Tl: int) -> int:
+    n = Tl
+    for m in _convs(dec):
+        if m.transposed:
+            n = (n - 1) * m.stride - 2 * m.padding + m.kernel_size
+        else:
+            n = (n + 2 * m.padding - m.dilation * (m.kernel_size - 1) - 1) // m.stride + 1
+    return n
+
+
+# ------------------------------------------------------------------------------------------
+# dac.Encoder / dac.Decoder / dac.ResidualVectorQuantize replacements
+# ------------------------------------------------------------------------------------------
+class Encoder(_Top):
+    """``A_ENC`` / ``T_ENC``: x [B, 1, T] -> z [B, d_latent, T/320]."""
+
+    def __init__(self, d_model=64, strides=(2, 4, 5, 8), d_latent=1024):
+        super().__init__()
+        layers = [WNConv1d(1, d_model, 7, padding=3)]
+        for s in strides:
+            d_model *= 2
+            layers.append(EncoderBlock(d_model, s))
+        layers += [Snake1d(d_model), WNConv1d(d_model, d_latent, 3, padding=1)]
+        self.block = nn.Sequential(*layers)
+        self.enc_dim = d_model
+
+    def _pack(self, eng):
+        return PackedEncoder.pack(eng, self)
+
+    @torch.no_grad()
+    def forward(self, x):
+        _require_cuda(x)
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"Encoder expects [B, 1, T], got {tuple(x.shape)}")
+        eng, pk = self._engine(x.device)
+        B, _, T = x.shape
+        Tl = pk.out_len(T)
+        if B == 0 or Tl <= 0:
+            raise ValueError(f"Encoder: empty batch or frame too short (B={B}, T={T})")
+        xin = _as_f32(x)
+        c = pk.head.cout
+        out = torch.empty(B, c, Tl, device=x.device, dtype=torch.float32)
+        mb = min(B, self.micro_batch)
+        for b0 in range(0, B, mb):
+            nb = min(mb, B - b0)
+            key = ("enc", nb, T, self._prec("enc"))
+            prog = eng.programs.get(key)
+            if prog is None:
+                em = Emitter(eng)
+                z, tl = emit_encoder(em, pk, em.ext(1), nb, T, self._prec("enc"))
+                em.transpose(z, em.ext(2), nb, tl, c)
+                prog = eng.programs[key] = em.finish(2)
+            eng.run(prog, [xin[b0:].data_ptr(), out[b0:].data_ptr()])
+        return out.to(x.dtype)
+
+
+class Decoder(_Top):
+    """``T_DEC``: z [B, C, Tl] -> y [B, 1, 320*Tl - 8]."""
+
+    def __init__(self, input_channel=1024, channels=1536, rates=(8, 5, 4, 2), d_out=1):
+        super().__init__()
+        layers = [WNConv1d(input_channel, channels, 7, padding=3)]
+        out_dim = channels
+        for i, s in enumerate(rates):
+            layers.append(DecoderBlock(channels // 2 ** i, channels // 2 ** (i + 1), s))
+            out_dim = channels // 2 ** (i + 1)
+        layers += [Snake1d(out_dim), WNConv1d(out_dim, d_out, 7, padding=3), nn.Tanh()]
+        self.model = nn.Sequential(*layers)
+
+    def _pack(self, eng):
+        return PackedDecoder.pack(eng, self)
+
+    @torch.no_grad()
+    def forward(self, z):
+        _require_cuda(z)
+        if z.dim() != 3:
+            raise ValueError(f"Decoder expects [B, C, Tl], got {tuple(z.shape)}")
+        eng, pk = self._engine(z.device)
+        B, c, Tl = z.shape
+        if c != pk.stem.cin:
+            raise ValueError(f"Decoder expects {pk.stem.cin} channels, got {c}")
+        if B == 0 or Tl == 0:
+            raise ValueError("Decoder: empty input")
+        Lo = pk.out_len(Tl)
+        zin = _as_f32(z)
+        y = torch.empty(B, 1, Lo, device=z.device, dtype=torch.float32)
+        mb = min(B, self.micro_batch)
+        for b0 in range(0, B, mb):
+            nb = min(mb, B - b0)
+            key = ("dec", nb, Tl, self._prec("dec"))
+            prog = eng.programs.get(key)
+            if prog is None:
+                em = Emitter(eng)
+                zc = em.new(nb * Tl * c)
+                em.transpose(em.ext(1), zc, nb, c, Tl)
+                emit_decoder(em, pk, zc, em.ext(2), nb, Tl, self._prec("dec"))
+                prog = eng.programs[key] = em.finish(2)
+            eng.run(prog, [zin[b0:].data_ptr(), y[b0:].data_ptr()])
+        return y.to(z.dtype)
+
+
+class VectorQuantize(_Fused):
+    def __init__(self, input_dim, codebook_size, codebook_dim):
+        super().__init__()
+        self.codebook_size, self.codebook_dim = codebook_size, codebook_dim
+        self.in_proj = WNConv1d(input_dim, codebook_dim, 1)
+        self.out_proj = WNConv1d(codebook_dim, input_dim, 1)
+        self.codebook = nn.Embedding(codebook_size, codebook_dim)
+
+
+class ResidualVectorQuantize(_Top):
+    """``A_QUANT``: z [B, C, Tl] -> (z_q, codes [B, n_q, Tl] int64, latents, commitment_loss, codebook_loss).
+    Eval semantics of dac's ResidualVectorQuantize.forward; the two losses are returned as zeros and
+    ``latents`` as None (the reference callers unpack ``qa, *_`` -- :458)."""
+
+    def __init__(self, input_dim=1024, n_codebooks=32, codebook_size=1024, codebook_dim=8, quantizer_dropout=0.0):
+        super().__init__()
+        self.n_codebooks, self.codebook_dim, self.codebook_size = n_codebooks, codebook_dim, codebook_size
+        self.quantizers = nn.ModuleList(
+            [VectorQuantize(input_dim, codebook_size, codebook_dim) for _ in range(n_codebooks)])
+        self.quantizer_dropout = quantizer_dropout
+
+    def _pack(self, eng):
+        return eng.pack_dac_rvq(list(self.quantizers))
+
+    @torch.no_grad()
+    def forward(self, z, n_quantizers=None):
+        _require_cuda(z)
+        eng, wid = self._engine(z.device)
+        B, c, Tl = z.shape
+        n_q = self.n_codebooks if n_quantizers is None else max(1, min(int(n_quantizers), self.n_codebooks))
+        zin = _as_f32(z)
+        zq = torch.empty(B, c, Tl, device=z.device, dtype=torch.float32)
+        codes = torch.empty(B, n_q, Tl, device=z.device, dtype=torch.int64)
+        key = ("dacq", B, Tl, n_q)
+        prog = eng.programs.get(key)
+        if prog is None:
+            em = Emitter(eng)
+            zc, qc = em.new(B * Tl * c), em.new(B * Tl * c)
+            ci = em.new(B * n_q * Tl)
+            em.transpose(em.ext(1), zc, B, c, Tl)
+            em.dac_rvq(wid, n_q, zc, qc, ci, B, Tl)
+            em.transpose(qc, em.ext(2), B, Tl, c)
+            em.widen(ci, em.ext(3), B * n_q * Tl)
+            prog = eng.programs[key] = em.finish(3)
+        eng.run(prog, [zin.data_ptr(), zq.data_ptr(), codes.data_ptr()])
+        zero = torch.zeros((), device=z.device)
+        return zq.to(z.dtype), codes, None, zero, zero
+
+
+class DAC(nn.Module):
+    """Container with the attributes the reference reads off ``dac.DAC.load(...)``:
+    ``.encoder .quantizer .decoder .encode(x, n_quantizers) .decode(z)`` (:528-535, :569-570)."""
+
+    def __init__(self):
+        super().__init__()
+        self.sample_rate, self.hop_length = 24000, 320
+        self.encoder = Encoder()
+        self.quantizer = ResidualVectorQuantize()
+        self.decoder = Decoder()
+
+    def encode(self, x, n_quantizers=None):
+        return self.quantizer(self.encoder(x), n_quantizers)
+
+    def decode(self, z):
+        return self.decoder(z)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's own layers
+# ------------------------------------------------------------------------------------------
+class PosEnc1D(_Fused):
+    def __init__(self, c, max_len=8192):  # :340-347
+        super().__init__()
+        pe = torch.zeros(max_len, c)
+        pos = torch.arange(0, max_len).unsqueeze(1)
+        div = torch.exp(torch.arange(0, c, 2) * (-math.log(10000.0) / c))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe)
+
+
+class TokenNorm(_Fused):
+    def __init__(self, c):
+        super().__init__()
+        self.ln = nn.LayerNorm(c)
+
+
+class CrossPredictor(_Top):
+    """:362-407.  Standalone ``forward(zt_prev, za)`` handles one chunk of <= 16 tokens."""
+
+    def __init__(self, c, heads=8, mlp_mul=2, dropout=0.1):
+        super().__init__()
+        assert c % heads == 0
+        self.pos = PosEnc1D(c)
+        self.h, self.dh = heads, c // heads
+        self.ln_q, self.ln_kv = nn.LayerNorm(c), nn.LayerNorm(c)
+        self.q_proj, self.k_proj = nn.Linear(c, c, False), nn.Linear(c, c, False)
+        self.v_proj, self.out = nn.Linear(c, c, False), nn.Linear(c, c, False)
+        self.drop = nn.Dropout(dropout)
+        self.ffn = nn.Sequential(nn.LayerNorm(c), nn.Linear(c, mlp_mul * c), nn.GELU(), nn.Linear(mlp_mul * c, c))
+
+    def _pack(self, eng):
+        return PackedPredictor.pack_predictor(eng, self)
+
+    @torch.no_grad()
+    def forward(self, zt_prev, za):
+        _require_cuda(zt_prev, za)
+        if zt_prev.shape != za.shape or zt_prev.dim() != 3:
+            raise ValueError("CrossPredictor expects two [B, C, Tc] tensors of the same shape")
+        B, c, Tc = zt_prev.shape
+        if Tc > 16:
+            raise L.B2CError("CrossPredictor: chunks longer than 16 tokens (the PLC full-length use) are not built yet")
+        eng, pp = self._engine(zt_prev.device)
+        prec = self._prec("pred")
+        a, k = _as_f32(zt_prev), _as_f32(za)
+        out = torch.empty(B, c, Tc, device=za.device, dtype=torch.float32)
+        key = ("pred", B, Tc, prec)
+        prog = eng.programs.get(key)
+        if prog is None:
+            em = Emitter(eng)
+            N = B * Tc
+            zp, zk = em.new(N * c), em.new(N * c)
+            em.transpose(em.ext(1), zp, B, c, Tc)
+            em.transpose(em.ext(2), zk, B, c, Tc)
+            qn, kvn = em.new(N * c), em.new(N * c)
+            em.layernorm(pp.lnq_g, pp.lnq_b, zp, L.ROWS_DENSE, qn, N, c, Tc, Tc, pe=pp.pe, pe_mode=L.PE_CHUNK_POS)
+            em.layernorm(pp.lnkv_g, pp.lnkv_b, zk, L.ROWS_DENSE, kvn, N, c, Tc, Tc, pe=pp.pe, pe_mode=L.PE_CHUNK_POS)
+            em.drop(zp, zk)
+            q, kv = em.new(N * c), em.new(N * 2 * c)
+            em.conv(pp.wq, qn, 1, N, out_raw=q, prec=prec)
+            em.conv(pp.wkv, kvn, 1, N, out_raw=kv, prec=prec)
+            em.drop(kvn)
+            ctx = em.new(N * c)
+            em.attention(q, 2, kv, ctx, B, Tc, Tc, pp.heads, pp.dh)
+            em.drop(q, kv)
+            zpred = emit_predict_rows(em, pp, qn, ctx, N, Tc, Tc, False, prec)
+            em.transpose(zpred, em.ext(3), B, Tc, c)
+            prog = eng.programs[key] = em.finish(3)
+        eng.run(prog, [a.data_ptr(), k.data_ptr(), out.data_ptr()])
+        return out.to(za.dtype)
+
+
+class ResidualVQEMA(_Top):
+    """:409-435.  ``forward(z [B, D, T], n_books_use)`` -> q_sum [B, D, T]; the indices the reference
+    discards are kept in ``last_indices`` ([B, books_use, T] int64)."""
+
+    def __init__(self, dim: int, n_books: int, n_embed: int):
+        super().__init__()
+        self.books = nn.ParameterList(
+            [nn.Parameter(torch.randn(n_embed, dim) / math.sqrt(dim)) for _ in range(n_books)])
+        self.last_indices = None
+
+    @staticmethod
+    def _nearest_l2(x, emb):
+        """argmax_k (x . e_k - 0.5 |e_k|^2), first maximum wins (:417-419).  x [N, D], emb [K, D] on CUDA."""
+        from .ops import nearest_code
+        return nearest_code(x, emb)
+
+    def _pack(self, eng):
+        return eng.pack_books(list(self.books))
+
+    @torch.no_grad()
+    def forward(self, z, n_books_use=None, return_indices=False):
+        _require_cuda(z)
+        n_books = len(self.books)
+        use = n_books if n_books_use is None else min(int(n_books_use), n_books)
+        B, D, T = z.shape
+        if B == 0 or T == 0:
+            raise ValueError("ResidualVQEMA: empty input")
+        eng, wid = self._engine(z.device)
+        zin = _as_f32(z)
+        out = torch.empty(B, D, T, device=z.device, dtype=torch.float32)
+        idx = torch.empty(B, use, T, device=z.device, dtype=torch.int64)
+        key = ("vq", B, T, use)
+        prog = eng.programs.get(key)
+        if prog is None:
+            em = Emitter(eng)
+            N = B * T
+            x, q = em.new(N * D), em.new(N * D)
+            ii = em.new(max(B * use * T, 1))
+            em.transpose(em.ext(1), x, B, D, T)
+            em.rvq(wid, use, x, q, ii, N, L.ROWS_DENSE, B, T, T)
+            em.transpose(q, em.ext(2), B, T, D)
+            if use > 0:
+                em.widen(ii, em.ext(3), B * use * T)
+            prog = eng.programs[key] = em.finish(3)
+        eng.run(prog, [zin.data_ptr(), out.data_ptr(), idx.data_ptr()])
+        self.last_indices = idx
+        out = out.to(z.dtype)
+        return (out, idx) if return_indices else out
+
+
+class ProposedEval(_Top):
+    """:437-487 (and AllPredAR.forward_step's forward, Training/compare_dacvsproposal_3.py:300-340).
+
+    A_ENC / A_QUANT / T_ENC / T_DEC must be this package's Encoder / ResidualVectorQuantize / Encoder /
+    Decoder.  ``forward_eval`` runs ONE fused CUDA program per micro-batch: both encoders, the DAC
+    quantizer, the two-pass predictor + residual VQ, and the decoder, with channel-last activations
+    that never leave the device.  ``last_indices`` [B, books_use, Tl] and ``last_audio_codes``
+    [B, 32, Tl] hold the code indices of the latest call."""
+
+    def __init__(self, A_ENC, A_QUANT, T_ENC, T_DEC, c_lat, rvq_books, rvq_embed):
+        super().__init__()
+        self.A_ENC, self.A_QUANT, self.T_ENC, self.T_DEC = A_ENC, A_QUANT, T_ENC, T_DEC
+        for m in (A_ENC, A_QUANT, T_ENC, T_DEC):
+            for p in m.parameters():
+                p.requires_grad_(False)
+        self.predict = CrossPredictor(c=c_lat)
+        self.tokennorm = TokenNorm(c_lat)
+        self.scale = nn.Parameter(torch.tensor(0.08))
+        self.proj_down = nn.Conv1d(c_lat, CODE_DIM, 1)
+        self.proj_up = nn.Conv1d(CODE_DIM, c_lat, 1)
+        self.vq = ResidualVQEMA(dim=CODE_DIM, n_books=rvq_books, n_embed=rvq_embed)
+        self.last_indices = None
+        self.last_audio_codes = None
+
+    # -- packing ------------------------------------------------------------------------
+    def _pack(self, eng):
+        for name, m, cls in (("A_ENC", self.A_ENC, Encoder), ("A_QUANT", self.A_QUANT, ResidualVectorQuantize),
+                             ("T_ENC", self.T_ENC, Encoder), ("T_DEC", self.T_DEC, Decoder)):
+            if not isinstance(m, cls):
+                raise L.B2CError(f"ProposedEval.{name} must be this package's {cls.__name__} "
+                                 f"(got {type(m).__name__}); there is no PyTorch fallback path")
+        pp = PackedPredictor.pack_predictor(eng, self.predict)
+        pp.tn_g, pp.tn_b = eng.pack_vec(self.tokennorm.ln.weight), eng.pack_vec(self.tokennorm.ln.bias)
+        pp.scale = float(self.scale.detach().float().clamp(5e-3, 0.5).item())   # :473
+        pp.down = eng.pack_plain(self.proj_down.weight, self.proj_down.bias)
+        pp.up = eng.pack_plain(self.proj_up.weight, self.proj_up.bias)
+        pp.books = eng.pack_books(list(self.vq.books))
+        pp.n_books = len(self.vq.books)
+        pp.code_dim = self.vq.books[0].shape[1]
+        return dict(a_enc=PackedEncoder.pack(eng, self.A_ENC), a_q=eng.pack_dac_rvq(list(self.A_QUANT.quantizers)),
+                    n_q=self.A_QUANT.n_codebooks, t_enc=PackedEncoder.pack(eng, self.T_ENC),
+                    t_dec=PackedDecoder.pack(eng, self.T_DEC), pp=pp)
+
+    def _books_use(self, books_use):
+        n = len(self.vq.books)
+        return n if books_use is None else min(int(books_use), n)
+
+    def latent_len(self, T):
+        return encoder_out_len(self.T_ENC, T)
+
+    def out_len(self, T):
+        """Decoded length for a T-sample frame (320 * (T // 320) - 8 for the 24 kHz model)."""
+        return decoder_out_len(self.T_DEC, self.latent_len(T))
+
+    # -- program ------------------------------------------------------------------------
+    def program(self, eng, pk, nb, T, use, decode=True, latents_cm=False):
+        """ext slots: 1 a [nb,T], 2 t [nb,T], 3 y [nb,Lout], 4 idx i32 [nb,use,Tl], 5 audio codes i32 [nb,n_q,Tl],
+        6 z_run ([nb,Tl,C] channel-last, or [nb,C,Tl] when latents_cm)."""
+        pe, pd, pt = self._prec("enc"), self._prec("dec"), self._prec("pred")
+        key = ("codec", nb, T, use, decode, latents_cm, pe, pd, pt)
+        prog = eng.programs.get(key)
+        if prog is not None:
+            return prog
+        em = Emitter(eng)
+        c = pk["pp"].c
+        za, Tl = emit_encoder(em, pk["a_enc"], em.ext(1), nb, T, pe)
+        qa = em.new(nb * Tl * c)
+        em.dac_rvq(pk["a_q"], pk["n_q"], za, qa, em.ext(5), nb, Tl)
+        em.drop(za)
+        zt, Tl2 = emit_encoder(em, pk["t_enc"], em.ext(2), nb, T, pe)
+        assert Tl2 == Tl
+        z_run = em.new(nb * Tl * c)
+        emit_latent_coder(em, pk["pp"], qa, zt, z_run, em.ext(4), nb, Tl, AR_CHUNK_TOK, use, pt)
+        em.drop(qa, zt)
+        if latents_cm:
+            em.transpose(z_run, em.ext(6), nb, Tl, c)
+        if decode:
+            emit_decoder(em, pk["t_dec"], z_run, em.ext(3), nb, Tl, pd)
+        prog = eng.programs[key] = em.finish(6, Tl=Tl, Lout=pk["t_dec"].out_len(Tl))
+        return prog
+
+    def _run(self, a_1T, t_1T, books_use, decode, want_latents):
+        _require_cuda(a_1T, t_1T)
+        if a_1T.shape != t_1T.shape or a_1T.dim() != 3 or a_1T.shape[1] != 1:
+            raise ValueError(f"expected two [B, 1, T] tensors, got {tuple(a_1T.shape)} and {tuple(t_1T.shape)}")
+        dev = a_1T.device
+        eng, pk = self._engine(dev)
+        B, _, T = a_1T.shape
+        use = self._books_use(books_use)
+        Tl = pk["t_enc"].out_len(T)
+        if B == 0 or Tl <= 0:
+            raise ValueError(f"empty batch or frame too short (B={B}, T={T})")
+        c, n_q = pk["pp"].c, pk["n_q"]
+        Lout = pk["t_dec"].out_len(Tl)
+        a, t = _as_f32(a_1T), _as_f32(t_1T)
+        y = torch.empty(B, 1, Lout, device=dev, dtype=torch.float32) if decode else None
+        idx = torch.empty(B, use, Tl, device=dev, dtype=torch.int32)
+        codes = torch.empty(B, n_q, Tl, device=dev, dtype=torch.int32)
+        z = torch.empty(B, c, Tl, device=dev, dtype=torch.float32) if want_latents else None
+        mb = min(B, self.micro_batch)
+        for b0 in range(0, B, mb):
+            nb = min(mb, B - b0)
+            prog = self.program(eng, pk, nb, T, use, decode=decode, latents_cm=want_latents)
+            eng.run(prog, [a[b0:].data_ptr(), t[b0:].data_ptr(), y[b0:].data_ptr() if decode else 0,
+                           idx[b0:].data_ptr(), codes[b0:].data_ptr(), z[b0:].data_ptr() if want_latents else 0])
+        self.last_indices, self.last_audio_codes = idx, codes
+        return y, z
+
+    @torch.no_grad()
+    def encode_latents(self, a_1T, t_1T, books_use=None):   # :451-478
+        _, z = self._run(a_1T, t_1T, books_use, decode=False, want_latents=True)
+        return z.to(a_1T.dtype)
+
+    @torch.no_grad()
+    def forward_eval(self, a_1T, t_1T, books_use=None):     # :480-487
+        y, _ = self._run(a_1T, t_1T, books_use, decode=True, want_latents=False)
+        return y.to(a_1T.dtype)
+
+    @torch.no_grad()
+    def forward_step(self, a_1T, tc_1T):
+        """Forward of AllPredAR.forward_step (Training/compare_dacvsproposal_3.py:300-340), no gradients."""
+        y = self.forward_eval(a_1T, tc_1T)
+        n = min(y.shape[-1], tc_1T.shape[-1])
+        return {"y_hat": y[..., :n], "tgt": tc_1T[..., :n]}
+
+    forward = forward_eval
+
+
+def build_proposed(rvq_books: int, rvq_embed: int) -> ProposedEval:
+    """build_backbones_for_eval (:527-535) + ProposedEval(...) (:661-662) with random-init weights."""
+    da, dt = DAC(), DAC()
+    return ProposedEval(da.encoder, da.quantizer, dt.encoder, dt.decoder, 1024, rvq_books, rvq_embed)
