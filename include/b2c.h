@@ -149,6 +149,24 @@ int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n);
 /* Enqueue the program on `stream` (a cudaStream_t).  ext[i] is the device pointer of slot i+1. */
 int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext);
 
+/* Run the program once with a cudaEvent pair around every launch (a measuring aid for bench.py and
+ * profiles/: never used on the timed path).  Fills up to cap entries:
+ *   ms[i] device time of launch i; kind[i] one of B2C_KIND_*; flops[i] / bytes[i] the ALGORITHMIC
+ *   work of that launch (2*M*N*K for contractions; minimal global reads+writes).  Returns the number
+ *   of launches.  Synchronises the stream. */
+#define B2C_KIND_CONV_F32 1
+#define B2C_KIND_CONV_TC 2
+#define B2C_KIND_STEM 3
+#define B2C_KIND_HEAD 4
+#define B2C_KIND_LAYERNORM 5
+#define B2C_KIND_ATTENTION 6
+#define B2C_KIND_RVQ 7
+#define B2C_KIND_NEAREST 8
+#define B2C_KIND_DAC_RVQ 9
+#define B2C_KIND_MOVE 10
+int b2c_prog_profile(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext,
+                     float* ms, int* kind, double* flops, double* bytes, int cap);
+
 typedef struct {
   void* host;   /* pinned or pageable host buffer */
   int slot;     /* external slot (>= 1) whose device buffer is the other end */

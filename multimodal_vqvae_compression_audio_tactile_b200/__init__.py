@@ -5,3 +5,6 @@ from ._lib import B2CError, LIB_PATH, load  # noqa: F401
 from .modules import (AR_CHUNK_TOK, CODE_DIM, DAC, CrossPredictor, Decoder, Encoder, PosEnc1D, ProposedEval,  # noqa: F401
                       ResidualVectorQuantize, ResidualVQEMA, TokenNorm, build_proposed)
 from .ops import nearest_code  # noqa: F401
+
+#: contraction arithmetic bench.py / smoke() use by default (see DESIGN.md "Precision")
+DEFAULT_PRECISION = "f32"

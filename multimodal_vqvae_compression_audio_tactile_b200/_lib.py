@@ -15,6 +15,9 @@ PREC_F32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 ROWS_DENSE, ROWS_HEAD, ROWS_HEAD_PREV, ROWS_ZERO = 0, 1, 2, 3
 PE_NONE, PE_CHUNK_POS, PE_ROW0, PE_ROW_N = 0, 1, 2, 3
 
+KIND_NAMES = {1: "conv_f32", 2: "conv_tc", 3: "stem", 4: "head", 5: "layernorm", 6: "attention", 7: "rvq",
+              8: "nearest", 9: "dac_rvq", 10: "move"}
+
 PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 
@@ -64,6 +67,9 @@ SIGNATURES = {
     "b2c_prog_transpose": (_i, [C.c_void_p, _ref, _ref, _i, _i, _i]),
     "b2c_prog_i32_to_i64": (_i, [C.c_void_p, _ref, _ref, C.c_size_t]),
     "b2c_prog_run": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i]),
+    "b2c_prog_profile": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
+                             C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                             _i]),
     "b2c_prog_run_host": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                                C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i]),
 }

@@ -576,10 +576,11 @@ static int launch_conv_f32(const ConvArgs& a, cudaStream_t st, int sm_count) {
   return B2C_OK;
 }
 
-static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R) {
+static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = nullptr) {
   b2c_ctx* ctx = p->ctx;
   for (size_t oi = 0; oi < p->ops.size(); ++oi) {
     Op& op = p->ops[oi];
+    if (ev) cudaEventRecord(ev[2 * oi], st);
     switch (op.type) {
       case OP_STEM: {
         const Weight& w = ctx->w[op.wid];
@@ -728,10 +729,88 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R) {
         break;
       }
     }
+    if (ev) cudaEventRecord(ev[2 * oi + 1], st);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "op %zu (type %d): %s", oi, (int)op.type, cudaGetErrorString(e));
   }
   return B2C_OK;
+}
+
+// algorithmic work of one launch: flops of the contraction, minimal global bytes
+static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, double* bytes) {
+  *flops = 0; *bytes = 0; *kind = B2C_KIND_MOVE;
+  switch (op.type) {
+    case OP_CONV:
+    case OP_CONV_TC: {
+      const ConvArgs& a = op.conv;
+      double rows = (double)a.B * a.Lout;
+      *kind = op.type == OP_CONV ? B2C_KIND_CONV_F32 : B2C_KIND_CONV_TC;
+      *flops = 2.0 * rows * a.Cout * a.Cin * a.KT;
+      double outs = (op.r[2] != B2C_NULL_REF ? 1 : 0) + (op.r[3] != B2C_NULL_REF ? 1 : 0) + (op.r[1] != B2C_NULL_REF ? 1 : 0);
+      *bytes = 4.0 * ((double)a.B * a.Lin * a.Cin + rows * a.Cout * outs + (double)a.n_phase * a.KT * a.Cin * a.Cout);
+      break;
+    }
+    case OP_STEM: {
+      const Weight& w = ctx->w[op.wid];
+      double n = (double)op.i[0] * op.i[1];
+      *kind = B2C_KIND_STEM; *flops = 2.0 * n * 7 * w.cout;
+      *bytes = 4.0 * (n + n * w.cout * ((op.r[1] != B2C_NULL_REF) + (op.r[2] != B2C_NULL_REF)));
+      break;
+    }
+    case OP_HEAD: {
+      const Weight& w = ctx->w[op.wid];
+      double n = (double)op.i[0] * op.i[1];
+      *kind = B2C_KIND_HEAD; *flops = 2.0 * n * 7 * w.cin; *bytes = 4.0 * (n * w.cin + n);
+      break;
+    }
+    case OP_LN: *kind = B2C_KIND_LAYERNORM; *flops = 8.0 * op.ln.N * op.ln.C; *bytes = 4.0 * 2 * (double)op.ln.N * op.ln.C; break;
+    case OP_ATTN: {
+      const AttnArgs& a = op.attn;
+      double nq = a.q_mode == 1 ? (double)a.B * a.nfix : (double)a.B * a.Tl;
+      *kind = B2C_KIND_ATTENTION; *flops = 4.0 * nq * a.chunk * a.heads * 128;
+      *bytes = 4.0 * ((double)a.B * a.Tl * 2 * a.heads * 128 + 2 * nq * a.heads * 128);
+      break;
+    }
+    case OP_RVQ:
+    case OP_NEAREST: {
+      const RvqArgs& r = op.rvq;
+      *kind = op.type == OP_RVQ ? B2C_KIND_RVQ : B2C_KIND_NEAREST;
+      *flops = 2.0 * r.N * r.D * r.K * r.books_use;
+      // 4*(3*N*D + K*D) + 2*N per book for the residual VQ; the bare search reads x and emb, writes idx
+      *bytes = op.type == OP_RVQ ? r.books_use * (4.0 * (3.0 * r.N * r.D + (double)r.K * r.D) + 2.0 * r.N)
+                                 : 4.0 * ((double)r.N * r.D + (double)r.K * r.D + r.N);
+      break;
+    }
+    case OP_DACRVQ: {
+      const DacRvqArgs& d = op.dac;
+      *kind = B2C_KIND_DAC_RVQ; *flops = 2.0 * d.N * d.n_q * (16.0 * d.C + 8.0 * d.K);
+      *bytes = 4.0 * (2.0 * d.N * d.C + (double)d.n_q * d.stage_stride + (double)d.N * d.n_q);
+      break;
+    }
+    case OP_SCATTER: *bytes = 8.0 * op.i[0] * op.i[4] * op.i[3]; break;
+    case OP_TRANSPOSE: *bytes = 8.0 * op.i[0] * op.i[1] * op.i[2]; break;
+    case OP_WIDEN: *bytes = 12.0 * op.n; break;
+  }
+}
+
+extern "C" int b2c_prog_profile(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes,
+                                void* const* ext, int n_ext, float* ms, int* kind, double* flops, double* bytes,
+                                int cap) {
+  if (!p || !ms || !kind || !flops || !bytes) return fail(B2C_ERR_ARG, "b2c_prog_profile: NULL argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  Resolver R{reinterpret_cast<char*>(workspace), workspace_bytes, ext, n_ext};
+  int rc = run_ops(p, st, R, ev.data());
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (rc == B2C_OK && se != cudaSuccess) rc = fail(B2C_ERR_CUDA, "b2c_prog_profile: %s", cudaGetErrorString(se));
+  for (size_t i = 0; i < n && (int)i < cap && rc == B2C_OK; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[2 * i], ev[2 * i + 1]);
+    op_work(p->ctx, p->ops[i], &kind[i], &flops[i], &bytes[i]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc == B2C_OK ? (int)n : rc;
 }
 
 extern "C" int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext,

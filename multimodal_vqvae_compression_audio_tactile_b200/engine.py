@@ -188,6 +188,21 @@ class Engine:
         L.check(self.lib.b2c_prog_run(prog.handle, C.c_void_p(stream), C.c_void_p(ws.data_ptr()), ws.numel(), arr,
                                       len(ext_ptrs)), "b2c_prog_run")
 
+    def profile(self, prog: Program, ext_ptrs):
+        """Per-launch device times with cudaEvent pairs (measuring aid, not the timed path).
+        -> list of dicts {kind, ms, flops, bytes}."""
+        ws = self.workspace(prog.ws_bytes)
+        arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
+        cap = prog.info["launches"] + 8
+        ms = (C.c_float * cap)()
+        kind = (C.c_int * cap)()
+        fl = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        n = L.check(self.lib.b2c_prog_profile(prog.handle, C.c_void_p(stream), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                              arr, len(ext_ptrs), ms, kind, fl, by, cap), "b2c_prog_profile")
+        return [dict(kind=L.KIND_NAMES.get(kind[i], "?"), ms=ms[i], flops=fl[i], bytes=by[i]) for i in range(min(n, cap))]
+
     def run_host(self, prog: Program, ext_ptrs, h2d, d2h):
         """h2d / d2h: lists of (host_ptr, slot, nbytes).  Synchronises the stream."""
         ws = self.workspace(prog.ws_bytes)

@@ -561,6 +561,54 @@ class ProposedEval(_Top):
         return y.to(a_1T.dtype)
 
     @torch.no_grad()
+    def forward_eval_host(self, a_host, t_host, books_use=None, device=None, y_out=None, idx_out=None):
+        """Host-buffer entry point (b2c_prog_run_host): a_host / t_host are CPU fp32 [B, 1, T] tensors
+        (pinned for full PCIe speed); every micro-batch is copied to the device, coded, decoded and the
+        reconstruction + code indices are copied back.  Returns (y [B,1,Lout] fp32, idx [B,use,Tl] int32)
+        CPU tensors and counts the bytes moved in ``last_host_bytes`` = (h2d, d2h)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if a_host.is_cuda or t_host.is_cuda:
+            raise ValueError("forward_eval_host takes host tensors; use forward_eval for device tensors")
+        if a_host.shape != t_host.shape or a_host.dim() != 3 or a_host.shape[1] != 1:
+            raise ValueError("expected two [B, 1, T] host tensors")
+        a_host, t_host = a_host.float().contiguous(), t_host.float().contiguous()
+        eng, pk = self._engine(dev)
+        B, _, T = a_host.shape
+        use = self._books_use(books_use)
+        Tl = pk["t_enc"].out_len(T)
+        if B == 0 or Tl <= 0:
+            raise ValueError(f"empty batch or frame too short (B={B}, T={T})")
+        Lout, n_q = pk["t_dec"].out_len(Tl), pk["n_q"]
+        if y_out is None:
+            y_out = torch.empty(B, 1, Lout, dtype=torch.float32, pin_memory=True)
+        if idx_out is None:
+            idx_out = torch.empty(B, use, Tl, dtype=torch.int32, pin_memory=True)
+        mb = min(B, self.micro_batch)
+        key = ("hoststage", mb, T, use)
+        st = eng.programs.get(key)
+        if st is None:
+            st = eng.programs[key] = dict(
+                a=torch.empty(mb, T, device=dev), t=torch.empty(mb, T, device=dev),
+                y=torch.empty(mb, Lout, device=dev), idx=torch.empty(mb, max(use, 1), Tl, device=dev, dtype=torch.int32),
+                codes=torch.empty(mb, n_q, Tl, device=dev, dtype=torch.int32))
+        h2d_b = d2h_b = 0
+        with torch.cuda.device(dev):
+            for b0 in range(0, B, mb):
+                nb = min(mb, B - b0)
+                prog = self.program(eng, pk, nb, T, use, decode=True, latents_cm=False)
+                ext = [st["a"].data_ptr(), st["t"].data_ptr(), st["y"].data_ptr(), st["idx"].data_ptr(),
+                       st["codes"].data_ptr(), 0]
+                h2d = [(a_host[b0:].data_ptr(), 1, nb * T * 4), (t_host[b0:].data_ptr(), 2, nb * T * 4)]
+                d2h = [(y_out[b0:].data_ptr(), 3, nb * Lout * 4)]
+                if use > 0:
+                    d2h.append((idx_out[b0:].data_ptr(), 4, nb * use * Tl * 4))
+                eng.run_host(prog, ext, h2d, d2h)
+                h2d_b += sum(x[2] for x in h2d)
+                d2h_b += sum(x[2] for x in d2h)
+        self.last_host_bytes = (h2d_b, d2h_b)
+        return y_out, idx_out
+
+    @torch.no_grad()
     def forward_step(self, a_1T, tc_1T):
         """Forward of AllPredAR.forward_step (Training/compare_dacvsproposal_3.py:300-340), no gradients."""
         y = self.forward_eval(a_1T, tc_1T)
