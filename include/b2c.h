@@ -38,7 +38,7 @@ typedef struct b2c_ctx b2c_ctx;
 typedef struct b2c_prog b2c_prog;
 typedef uint64_t b2c_ref;
 
-#define B2C_ABI_VERSION 1
+#define B2C_ABI_VERSION 2
 #define B2C_NULL_REF ((b2c_ref)0xFFFFFFFFFFFFFFFFull)
 #define B2C_REF(slot, off) ((((b2c_ref)(slot)) << 56) | (b2c_ref)(off))
 
@@ -59,6 +59,12 @@ typedef uint64_t b2c_ref;
 #define B2C_PREC_F32 0    /* FP32 FFMA on CUDA cores (bit-faithful to fp32 up to summation order) */
 #define B2C_PREC_BF16X3 1 /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate (>= 16 mantissa bits) */
 #define B2C_PREC_BF16 2   /* tcgen05 single-pass bf16, fp32 accumulate */
+
+/* storage of an ACTIVATION buffer (out_act of a producer == x of the consuming contraction).
+ * Residual / boundary tensors (out_raw, res, module inputs and outputs) are always fp32. */
+#define B2C_FMT_F32 0
+#define B2C_FMT_BF16X2 1 /* two bf16 planes: hi at the reference, lo at + n_elements; x = hi + lo (16 mantissa bits) */
+#define B2C_FMT_BF16 2   /* one bf16 plane */
 
 /* row addressing modes of the token-wise ops (predictor two-pass schedule) */
 #define B2C_ROWS_DENSE 0     /* row n                                               */
@@ -105,25 +111,33 @@ int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out);
 int b2c_prog_destroy(b2c_prog* prog);
 int b2c_prog_num_launches(const b2c_prog* prog);
 
-/* dac Encoder stem: Conv1d(1, cout, k=7, p=3) on x [B, L] -> [B, L, cout]. */
+/* 1 when the tcgen05 implicit-GEMM kernel takes this layer (precision BF16X3 / BF16), 0 when only the FP32
+ * CUDA-core kernel does, negative on a bad argument.  Callers pick activation formats with it. */
+int b2c_conv_tc_eligible(const b2c_ctx* ctx, int wid, int Lin, int stride, int dilation);
+
+/* dac Encoder stem: Conv1d(1, cout, k=7, p=3) on x [B, L] -> [B, L, cout] (out_act stored as act_fmt). */
 int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act, int alpha_wid, int B,
-                  int L);
+                  int L, int act_fmt);
 /* Conv1d (any k, stride, dilation, zero padding) or Linear (k = 1) as an implicit GEMM:
  *   x [B, Lin, cin] -> [B, Lout, cout];  v = conv + bias (+ res);  out_raw = v;  out_act = act(v).
  *   res_mode 0: res has the output's shape; 1: res is a [chunk, cout] table indexed by (lo % Tl) % chunk. */
 int b2c_prog_conv(b2c_prog* p, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act, int act,
                   int alpha_wid, int B, int Lin, int stride, int dilation, int padding, int res_mode, int Tl,
-                  int chunk, int precision);
+                  int chunk, int precision, int x_fmt, int act_fmt);
+/*   precision F32: x_fmt and act_fmt must be B2C_FMT_F32.  BF16X3: x must be BF16X2.  BF16: x BF16 or BF16X2
+ *   (the hi plane is read).  A tensor-core precision on a layer b2c_conv_tc_eligible() rejects is an error:
+ *   there is no silent change of arithmetic. */
 /* ConvTranspose1d (k = 2*stride, padding = ceil(stride/2)), x [B, Lin, cin] -> [B, Lout, cout]. */
 int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act, int alpha_wid, int B,
-                   int Lin, int precision);
+                   int Lin, int precision, int x_fmt, int act_fmt);
 /* dac Decoder head: Conv1d(cin, 1, k=7, p=3) + tanh on x [B, L, cin] -> y [B, L]. */
-int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L);
+int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int x_fmt);
 /* LayerNorm over C of rows gathered by a_mode from a (minus sub, plus pe row), optional scale*tanh.
  * nn.LayerNorm eps = 1e-5.  (CrossPredictor.ln_q/ln_kv/ffn[0] :394-395,:377; TokenNorm :357-360 with
  * tanh and the clamped scalar, :472-474) */
 int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub, int pe_wid,
-                       int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk);
+                       int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk,
+                       int out_fmt);
 /* softmax(Q K^T / sqrt(dh)) V inside each chunk (:401-402).
  *   kv [B*Tl, 2*heads*dh] (K | V).  q_mode 0: q is a [chunk, heads*dh] table (row = position in chunk),
  *   out rows dense [B*Tl].  q_mode 1: q is [B*nfix, heads*dh], one query per chunk head, out [B*nfix]. */
@@ -143,6 +157,8 @@ int b2c_prog_dac_rvq(b2c_prog* p, int wid, int n_q, b2c_ref z, b2c_ref zq, b2c_r
 int b2c_prog_scatter_heads(b2c_prog* p, b2c_ref src, b2c_ref dst, int B, int Tl, int chunk, int C);
 /* [B, R, C] -> [B, C, R] */
 int b2c_prog_transpose(b2c_prog* p, b2c_ref in, b2c_ref out, int B, int R, int C);
+/* change the storage format of an n-element activation buffer (fp32 <-> bf16 planes) */
+int b2c_prog_convert(b2c_prog* p, b2c_ref src, int src_fmt, b2c_ref dst, int dst_fmt, size_t n);
 /* widen int32 -> int64 (PyTorch index dtype at the module boundary) */
 int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n);
 

@@ -12,6 +12,8 @@ NULL_REF = 0xFFFFFFFFFFFFFFFF
 
 ACT_NONE, ACT_SNAKE, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 PREC_F32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+FMT_F32, FMT_BF16X2, FMT_BF16 = 0, 1, 2
+ABI_VERSION = 2
 ROWS_DENSE, ROWS_HEAD, ROWS_HEAD_PREV, ROWS_ZERO = 0, 1, 2, 3
 PE_NONE, PE_CHUNK_POS, PE_ROW0, PE_ROW_N = 0, 1, 2, 3
 
@@ -19,6 +21,17 @@ KIND_NAMES = {1: "conv_f32", 2: "conv_tc", 3: "stem", 4: "head", 5: "layernorm",
               8: "nearest", 9: "dac_rvq", 10: "move"}
 
 PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+#: activation storage a contraction of this precision reads
+FMT_OF_PREC = {PREC_F32: FMT_F32, PREC_BF16X3: FMT_BF16X2, PREC_BF16: FMT_BF16}
+#: named precision plans: stage -> arithmetic.  "tc": everything that decides a code index keeps >= 16
+#: mantissa bits (bf16 hi/lo split, 3 MMAs); the decoder, downstream of the quantizer, runs single-pass bf16.
+PLANS = {
+    "f32": {"enc": "f32", "pred": "f32", "dec": "f32"},
+    "tc": {"enc": "bf16x3", "pred": "bf16x3", "dec": "bf16"},
+    "tc_exact": {"enc": "bf16x3", "pred": "bf16x3", "dec": "bf16x3"},
+    "bf16": {"enc": "bf16", "pred": "bf16", "dec": "bf16"},
+    "bf16x3": {"enc": "bf16x3", "pred": "bf16x3", "dec": "bf16x3"},
+}
 
 
 def ref(slot: int, off: int = 0) -> int:
@@ -54,11 +67,13 @@ SIGNATURES = {
     "b2c_prog_create": (_i, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2c_prog_destroy": (_i, [C.c_void_p]),
     "b2c_prog_num_launches": (_i, [C.c_void_p]),
-    "b2c_prog_stem": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i]),
-    "b2c_prog_conv": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
-    "b2c_prog_convT": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
-    "b2c_prog_head": (_i, [C.c_void_p, _i, _ref, _ref, _i, _i]),
-    "b2c_prog_layernorm": (_i, [C.c_void_p, _i, _i, _ref, _i, _ref, _i, _i, _i, C.c_float, _ref, _i, _i, _i, _i]),
+    "b2c_conv_tc_eligible": (_i, [C.c_void_p, _i, _i, _i, _i]),
+    "b2c_prog_stem": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
+    "b2c_prog_conv": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "b2c_prog_convT": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i]),
+    "b2c_prog_head": (_i, [C.c_void_p, _i, _ref, _ref, _i, _i, _i]),
+    "b2c_prog_layernorm": (_i, [C.c_void_p, _i, _i, _ref, _i, _ref, _i, _i, _i, C.c_float, _ref, _i, _i, _i, _i, _i]),
+    "b2c_prog_convert": (_i, [C.c_void_p, _ref, _i, _ref, _i, C.c_size_t]),
     "b2c_prog_attention": (_i, [C.c_void_p, _ref, _i, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_rvq": (_i, [C.c_void_p, _i, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_nearest": (_i, [C.c_void_p, _ref, _ref, _ref, _ref, _i, _i, _i, _i]),
@@ -89,8 +104,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.b2c_abi_version() != 1:
-        raise B2CError(f"libb2c.so ABI {lib.b2c_abi_version()} != 1: rebuild")
+    if lib.b2c_abi_version() != ABI_VERSION:
+        raise B2CError(f"libb2c.so ABI {lib.b2c_abi_version()} != {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
 

@@ -253,7 +253,7 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
 // programs
 // ------------------------------------------------------------------------------------------
 enum OpType { OP_STEM, OP_CONV, OP_HEAD, OP_LN, OP_ATTN, OP_RVQ, OP_NEAREST, OP_DACRVQ, OP_SCATTER, OP_TRANSPOSE,
-              OP_WIDEN, OP_CONV_TC };
+              OP_WIDEN, OP_CONV_TC, OP_CONVERT };
 
 struct Op {
   OpType type;
@@ -268,6 +268,7 @@ struct Op {
   int i[8] = {0};
   size_t n = 0;
   int precision = 0;
+  int x_fmt = 0, act_fmt = 0;
 };
 
 struct b2c_prog {
@@ -298,15 +299,26 @@ static void blank_refs(Op& op) {
   for (auto& r : op.r) r = B2C_NULL_REF;
 }
 
+static bool fmt_ok(int f) { return f == B2C_FMT_F32 || f == B2C_FMT_BF16X2 || f == B2C_FMT_BF16; }
+
+extern "C" int b2c_conv_tc_eligible(const b2c_ctx* ctx, int wid, int Lin, int stride, int dilation) {
+  if (!ctx || wid < 0 || wid >= (int)ctx->w.size() || ctx->w[wid].kind != W_CONV)
+    return fail(B2C_ERR_ARG, "b2c_conv_tc_eligible: bad weight id %d", wid);
+  const Weight& w = ctx->w[wid];
+  return tc_conv_eligible(w.tc, w.cin, w.cout, w.transposed ? 1 : stride, w.transposed ? 1 : dilation, Lin) ? 1 : 0;
+}
+
 extern "C" int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act,
-                             int alpha_wid, int B, int L) {
+                             int alpha_wid, int B, int L, int act_fmt) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_stem: NULL program");
   const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_stem");
   if (!w) return B2C_ERR_ARG;
   if (w->cin != 1 || w->k != 7 || w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_stem: expects Conv1d(1, C, 7)");
   if (act == B2C_ACT_SNAKE && !get_w(p, alpha_wid, W_VEC, "b2c_prog_stem(alpha)")) return B2C_ERR_ARG;
   if (B <= 0 || L <= 0) return fail(B2C_ERR_ARG, "b2c_prog_stem: empty batch or length");
+  if (!fmt_ok(act_fmt)) return fail(B2C_ERR_ARG, "b2c_prog_stem: bad activation format %d", act_fmt);
   Op op;
+  op.act_fmt = act_fmt;
   op.type = OP_STEM;
   blank_refs(op);
   op.r[0] = x; op.r[1] = out_raw; op.r[2] = out_act;
@@ -318,7 +330,7 @@ extern "C" int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b
 
 static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act,
                     int act, int alpha_wid, int B, int Lin, int stride, int dilation, int padding, int res_mode,
-                    int Tl, int chunk, int precision) {
+                    int Tl, int chunk, int precision, int x_fmt, int act_fmt) {
   if (!p) return fail(B2C_ERR_ARG, "%s: NULL program", who);
   const Weight* w = get_w(p, wid, W_CONV, who);
   if (!w) return B2C_ERR_ARG;
@@ -327,8 +339,17 @@ static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref re
   if (w->cin % 16 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cin=%d must be a multiple of 16", who, w->cin);
   if (w->cout % 2 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cout=%d must be even", who, w->cout);
   if (res_mode == 1 && (Tl <= 0 || chunk <= 0)) return fail(B2C_ERR_ARG, "%s: table residual needs Tl and chunk", who);
+  if (!fmt_ok(x_fmt) || !fmt_ok(act_fmt)) return fail(B2C_ERR_ARG, "%s: bad activation format", who);
+  if (precision == B2C_PREC_F32 && (x_fmt != B2C_FMT_F32 || act_fmt != B2C_FMT_F32))
+    return fail(B2C_ERR_ARG, "%s: the FP32 kernel reads and writes fp32 activations (got x_fmt %d, act_fmt %d)", who, x_fmt, act_fmt);
+  if (precision == B2C_PREC_BF16X3 && x_fmt != B2C_FMT_BF16X2)
+    return fail(B2C_ERR_ARG, "%s: precision bf16x3 needs x as two bf16 planes (got x_fmt %d)", who, x_fmt);
+  if (precision == B2C_PREC_BF16 && x_fmt == B2C_FMT_F32)
+    return fail(B2C_ERR_ARG, "%s: precision bf16 needs x as bf16 plane(s)", who);
+  if (precision < 0 || precision > B2C_PREC_BF16) return fail(B2C_ERR_ARG, "%s: bad precision %d", who, precision);
   Op op;
   op.type = OP_CONV;
+  op.x_fmt = x_fmt; op.act_fmt = act_fmt;
   blank_refs(op);
   op.r[0] = x; op.r[1] = res; op.r[2] = out_raw; op.r[3] = out_act;
   op.wid = wid; op.wid2 = alpha_wid;
@@ -352,10 +373,11 @@ static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref re
   }
   if ((long)B * a.n_phase > 65535) return fail(B2C_ERR_UNSUPPORTED, "%s: batch*phases %ld exceeds grid.z", who, (long)B * a.n_phase);
   if (precision != B2C_PREC_F32) {
-    int rc = tc_conv_plan(a, w->tc, precision, p->ctx->sm_count, &op.tc);
-    if (rc == 0) op.type = OP_CONV_TC;
-    else if (rc < 0) return fail(B2C_ERR_UNSUPPORTED, "%s: tensor-core plan failed (%d)", who, rc);
-    // rc > 0: shape not eligible for the tcgen05 kernel -> FP32 CUDA-core kernel (still sm_100a CUDA)
+    int rc = tc_conv_plan(a, w->tc, precision, act_fmt, p->ctx->sm_count, &op.tc);
+    if (rc != 0)
+      return fail(B2C_ERR_UNSUPPORTED, "%s: layer is not eligible for the tcgen05 kernel (plan code %d); ask "
+                  "b2c_conv_tc_eligible() and use B2C_PREC_F32 for it", who, rc);
+    op.type = OP_CONV_TC;
   }
   p->ops.push_back(op);
   return B2C_OK;
@@ -363,34 +385,36 @@ static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref re
 
 extern "C" int b2c_prog_conv(b2c_prog* p, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act,
                              int act, int alpha_wid, int B, int Lin, int stride, int dilation, int padding,
-                             int res_mode, int Tl, int chunk, int precision) {
+                             int res_mode, int Tl, int chunk, int precision, int x_fmt, int act_fmt) {
   if (p) {
     const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_conv");
     if (!w) return B2C_ERR_ARG;
     if (w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_conv: weight %d is a ConvTranspose1d", wid);
   }
   return add_conv(p, "b2c_prog_conv", wid, x, res, out_raw, out_act, act, alpha_wid, B, Lin, stride, dilation,
-                  padding, res_mode, Tl, chunk, precision);
+                  padding, res_mode, Tl, chunk, precision, x_fmt, act_fmt);
 }
 
 extern "C" int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act,
-                              int alpha_wid, int B, int Lin, int precision) {
+                              int alpha_wid, int B, int Lin, int precision, int x_fmt, int act_fmt) {
   if (p) {
     const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_convT");
     if (!w) return B2C_ERR_ARG;
     if (!w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_convT: weight %d is not a ConvTranspose1d", wid);
   }
   return add_conv(p, "b2c_prog_convT", wid, x, B2C_NULL_REF, out_raw, out_act, act, alpha_wid, B, Lin, 1, 1, 0, 0, 0,
-                  0, precision);
+                  0, precision, x_fmt, act_fmt);
 }
 
-extern "C" int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L) {
+extern "C" int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int x_fmt) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_head: NULL program");
   const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_head");
   if (!w) return B2C_ERR_ARG;
   if (w->cout != 1 || w->k != 7 || w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_head: expects Conv1d(C, 1, 7)");
   if (B <= 0 || L <= 0) return fail(B2C_ERR_ARG, "b2c_prog_head: empty batch or length");
+  if (!fmt_ok(x_fmt)) return fail(B2C_ERR_ARG, "b2c_prog_head: bad activation format %d", x_fmt);
   Op op;
+  op.x_fmt = x_fmt;
   op.type = OP_HEAD;
   blank_refs(op);
   op.r[0] = x; op.r[1] = y;
@@ -404,12 +428,13 @@ static int nfix_of(int Tl, int chunk) { return (Tl + chunk - 1) / chunk - 1; }
 
 extern "C" int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub,
                                   int pe_wid, int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C,
-                                  int Tl, int chunk) {
+                                  int Tl, int chunk, int out_fmt) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: NULL program");
   if (!get_w(p, gamma_wid, W_VEC, "b2c_prog_layernorm(gamma)") || !get_w(p, beta_wid, W_VEC, "b2c_prog_layernorm(beta)"))
     return B2C_ERR_ARG;
   if (pe_mode != B2C_PE_NONE && !get_w(p, pe_wid, W_VEC, "b2c_prog_layernorm(pe)")) return B2C_ERR_ARG;
   if (N <= 0 || C <= 0 || Tl <= 0 || chunk <= 0) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: bad sizes");
+  if (!fmt_ok(out_fmt)) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: bad activation format %d", out_fmt);
   Op op;
   op.type = OP_LN;
   blank_refs(op);
@@ -418,7 +443,7 @@ extern "C" int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_
   LnArgs& l = op.ln;
   memset(&l, 0, sizeof(l));
   l.N = N; l.C = C; l.Tl = Tl; l.chunk = chunk; l.nfix = nfix_of(Tl, chunk) > 0 ? nfix_of(Tl, chunk) : 1;
-  l.a_mode = a_mode; l.pe_mode = pe_mode; l.tanh_post = tanh_post; l.post_scale = post_scale;
+  l.a_mode = a_mode; l.pe_mode = pe_mode; l.tanh_post = tanh_post; l.post_scale = post_scale; l.out_fmt = out_fmt;
   p->ops.push_back(op);
   return B2C_OK;
 }
@@ -526,6 +551,21 @@ extern "C" int b2c_prog_transpose(b2c_prog* p, b2c_ref in, b2c_ref out, int B, i
   return B2C_OK;
 }
 
+extern "C" int b2c_prog_convert(b2c_prog* p, b2c_ref src, int src_fmt, b2c_ref dst, int dst_fmt, size_t n) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_convert: NULL program");
+  if (!fmt_ok(src_fmt) || !fmt_ok(dst_fmt) || n == 0) return fail(B2C_ERR_ARG, "b2c_prog_convert: bad argument");
+  if ((src_fmt == B2C_FMT_F32) == (dst_fmt == B2C_FMT_F32))
+    return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_convert: only fp32 <-> bf16 plane conversions (got %d -> %d)", src_fmt, dst_fmt);
+  Op op;
+  op.type = OP_CONVERT;
+  blank_refs(op);
+  op.r[0] = src; op.r[1] = dst;
+  op.x_fmt = src_fmt; op.act_fmt = dst_fmt;
+  op.n = n;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
 extern "C" int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_i32_to_i64: NULL program");
   Op op;
@@ -586,29 +626,32 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         const Weight& w = ctx->w[op.wid];
         const float* x = R.get<const float>(op.r[0]);
         float* o_raw = R.get<float>(op.r[1]);
-        float* o_act = R.get<float>(op.r[2]);
+        void* o_act = R.get<char>(op.r[2]);
         const float* alpha = op.i[2] == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
         if (R.bad || !x) return fail(B2C_ERR_WORKSPACE, "op %zu (stem): unresolved buffer", oi);
         int B = op.i[0], L = op.i[1];
         dim3 grid((L + 63) / 64, B);
         size_t sm = (64 + 8 + 7 * w.cout) * sizeof(float);
-        stem_k7_f32<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, o_act, alpha, L, w.cout, op.i[2]);
+        stem_k7_f32<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, o_act, alpha, L, w.cout, op.i[2], op.act_fmt,
+                                           (size_t)B * L * w.cout);
         break;
       }
       case OP_CONV:
       case OP_CONV_TC: {
         const Weight& w = ctx->w[op.wid];
         ConvArgs a = op.conv;
-        a.x = R.get<const float>(op.r[0]);
+        const void* x_any = R.get<const char>(op.r[0]);
+        void* act_any = R.get<char>(op.r[3]);
+        a.x = reinterpret_cast<const float*>(x_any);
         a.res = R.get<const float>(op.r[1]);
         a.out_raw = R.get<float>(op.r[2]);
-        a.out_act = R.get<float>(op.r[3]);
+        a.out_act = reinterpret_cast<float*>(act_any);
         a.w = w.dev;
         a.bias = w.bias;
         a.alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
         if (R.bad || !a.x || (!a.out_raw && !a.out_act)) return fail(B2C_ERR_WORKSPACE, "op %zu (conv): unresolved buffer", oi);
         if (op.type == OP_CONV_TC) {
-          int rc = tc_conv_launch(op.tc, a, w.tc, st);
+          int rc = tc_conv_launch(op.tc, a, x_any, act_any, w.tc, st);
           if (rc) return fail(B2C_ERR_CUDA, "op %zu (conv, tcgen05): launch failed (%d)", oi, rc);
         } else {
           int rc = launch_conv_f32(a, st, ctx->sm_count);
@@ -618,19 +661,20 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
       }
       case OP_HEAD: {
         const Weight& w = ctx->w[op.wid];
-        const float* x = R.get<const float>(op.r[0]);
+        const void* x = R.get<const char>(op.r[0]);
         float* y = R.get<float>(op.r[1]);
         if (R.bad || !x || !y) return fail(B2C_ERR_WORKSPACE, "op %zu (head): unresolved buffer", oi);
         int B = op.i[0], L = op.i[1];
         dim3 grid((L + 63) / 64, B);
-        head_k7_tanh_f32<<<grid, 256, 7 * w.cin * sizeof(float), st>>>(x, w.dev, w.bias, y, L, w.cin);
+        head_k7_tanh_f32<<<grid, 256, 7 * w.cin * sizeof(float), st>>>(x, w.dev, w.bias, y, L, w.cin, op.x_fmt,
+                                                                       (size_t)B * L * w.cin);
         break;
       }
       case OP_LN: {
         LnArgs l = op.ln;
         l.a = R.get<const float>(op.r[0]);
         l.sub = R.get<const float>(op.r[1]);
-        l.out = R.get<float>(op.r[2]);
+        l.out = R.get<char>(op.r[2]);
         l.gamma = ctx->w[op.wid].dev;
         l.beta = ctx->w[op.wid2].dev;
         l.pe = l.pe_mode != PE_NONE ? ctx->w[op.wid3].dev : nullptr;
@@ -721,6 +765,21 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         transpose_brc_f32<<<grid, dim3(32, 8), 0, st>>>(in, out, op.i[1], op.i[2]);
         break;
       }
+      case OP_CONVERT: {
+        const void* src = R.get<const char>(op.r[0]);
+        void* dst = R.get<char>(op.r[1]);
+        if (R.bad || !src || !dst) return fail(B2C_ERR_WORKSPACE, "op %zu (convert): unresolved buffer", oi);
+        if (op.x_fmt == B2C_FMT_F32) {
+          __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dst);
+          split_planes_f32<<<(unsigned)((op.n / 4 + 256) / 256), 256, 0, st>>>(
+              reinterpret_cast<const float*>(src), hi, op.act_fmt == B2C_FMT_BF16X2 ? hi + op.n : nullptr, op.n);
+        } else {
+          const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(src);
+          merge_planes_f32<<<(unsigned)((op.n + 255) / 256), 256, 0, st>>>(
+              hi, op.x_fmt == B2C_FMT_BF16X2 ? hi + op.n : nullptr, reinterpret_cast<float*>(dst), op.n);
+        }
+        break;
+      }
       case OP_WIDEN: {
         const int* in = R.get<const int>(op.r[0]);
         long long* out = R.get<long long>(op.r[1]);
@@ -790,6 +849,7 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
     case OP_SCATTER: *bytes = 8.0 * op.i[0] * op.i[4] * op.i[3]; break;
     case OP_TRANSPOSE: *bytes = 8.0 * op.i[0] * op.i[1] * op.i[2]; break;
     case OP_WIDEN: *bytes = 12.0 * op.n; break;
+    case OP_CONVERT: *bytes = 8.0 * op.n; break;
   }
 }
 

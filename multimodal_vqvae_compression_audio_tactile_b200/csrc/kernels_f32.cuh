@@ -3,12 +3,42 @@
 // the reference's CPU fp32) and the on-GPU cross-check for the tcgen05 kernels.
 // Activations are channel-last: [batch][position][channel].
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b2c {
 
 enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_GELU = 2, ACT_TANH = 3 };
+// activation storage: fp32, two bf16 planes (hi | lo, lo = hi + n elements; x = hi + lo to 16 mantissa
+// bits), or the bf16 hi plane alone
+enum { FMT_F32 = 0, FMT_PLANES = 1, FMT_HI = 2 };
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// store one activation value at element offset o of a buffer of n elements in format fmt
+__device__ __forceinline__ void store_fmt(void* base, int fmt, size_t n, size_t o, float v) {
+  if (fmt == FMT_F32) {
+    reinterpret_cast<float*>(base)[o] = v;
+  } else {
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    reinterpret_cast<__nv_bfloat16*>(base)[o] = h;
+    if (fmt == FMT_PLANES) reinterpret_cast<__nv_bfloat16*>(base)[n + o] = l;
+  }
+}
+__device__ __forceinline__ float load_fmt(const void* base, int fmt, size_t n, size_t o) {
+  if (fmt == FMT_F32) return __ldg(reinterpret_cast<const float*>(base) + o);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base);
+  float v = __bfloat162float(b[o]);
+  if (fmt == FMT_PLANES) v += __bfloat162float(b[n + o]);
+  return v;
+}
 enum { ROWS_DENSE = 0, ROWS_HEAD = 1, ROWS_HEAD_PREV = 2, ROWS_ZERO = 3 };
 enum { PE_NONE = 0, PE_CHUNK_POS = 1, PE_ROW0 = 2, PE_ROW_N = 3 };
 
@@ -212,8 +242,8 @@ __global__ void __launch_bounds__(256, 2) conv_gemm_f32(const ConvArgs a) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_k7_f32(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ out_raw,
-                                                    float* __restrict__ out_act, const float* __restrict__ alpha,
-                                                    int L, int Cout, int act) {
+                                                    void* __restrict__ out_act, const float* __restrict__ alpha,
+                                                    int L, int Cout, int act, int act_fmt, size_t act_n) {
   constexpr int TP = 64;
   extern __shared__ float sm[];
   float* xs = sm;             // TP + 6
@@ -235,7 +265,7 @@ __global__ void __launch_bounds__(256) stem_k7_f32(const float* __restrict__ x, 
     if (bias) acc = __fadd_rn(acc, __ldg(bias + co));
     size_t o = ((size_t)b * L + l) * Cout + co;
     if (out_raw) out_raw[o] = acc;
-    if (out_act) out_act[o] = apply_act(acc, act, act == ACT_SNAKE ? __ldg(alpha + co) : 0.f);
+    if (out_act) store_fmt(out_act, act_fmt, act_n, o, apply_act(acc, act, act == ACT_SNAKE ? __ldg(alpha + co) : 0.f));
   }
 }
 
@@ -244,16 +274,16 @@ __global__ void __launch_bounds__(256) stem_k7_f32(const float* __restrict__ x, 
 // output is CONTIGUOUS, so y[l] = tanh(b + <w_flat, x_flat[(l-3)*Cin ...]>): one warp per output,
 // coalesced reads, HBM/L1-bound.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_k7_tanh_f32(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) head_k7_tanh_f32(const void* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ y, int L,
-                                                         int Cin) {
+                                                         int Cin, int x_fmt, size_t x_n) {
   extern __shared__ float wsm[];
   const int n = 7 * Cin;
   for (int i = threadIdx.x; i < n; i += blockDim.x) wsm[i] = __ldg(w + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const float* xb = x + (size_t)b * L * Cin;
+  const size_t xoff = (size_t)b * L * Cin;
   const long total = (long)L * Cin;
   constexpr int PPW = 8;
   const int l_base = (blockIdx.x * 8 + warp) * PPW;
@@ -264,7 +294,7 @@ __global__ void __launch_bounds__(256) head_k7_tanh_f32(const float* __restrict_
     float acc = 0.f;
     for (int f = lane; f < n; f += 32) {
       long g = base + f;
-      float xv = (g >= 0 && g < total) ? __ldg(xb + g) : 0.f;
+      float xv = (g >= 0 && g < total) ? load_fmt(x, x_fmt, x_n, xoff + g) : 0.f;
       acc = fmaf(xv, wsm[f], acc);
     }
 #pragma unroll
@@ -283,10 +313,11 @@ struct LnArgs {
   const float* pe;
   const float* gamma;
   const float* beta;
-  float* out;
+  void* out;
   int N, C, Tl, chunk, nfix;
   int a_mode, pe_mode, tanh_post;
   float post_scale;
+  int out_fmt;
 };
 
 __device__ __forceinline__ long gather_row(int n, int mode, int Tl, int chunk, int nfix) {
@@ -332,7 +363,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_f32(const LnArgs p) {
   for (int c = lane; c < C; c += 32) {
     float v = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(val(c), rstd), nb), __ldg(p.gamma + c)), __ldg(p.beta + c));
     if (p.tanh_post) v = __fmul_rn(p.post_scale, tanhf(v));
-    p.out[(long)n * C + c] = v;
+    store_fmt(p.out, p.out_fmt, (size_t)p.N * C, (size_t)n * C + c, v);
   }
 }
 

@@ -1,14 +1,585 @@
-// tcgen05 / TMEM / TMA kernels (sm_100a) -- placeholder interface, filled in below.
+// tcgen05 / TMEM / TMA implicit-GEMM Conv1d for sm_100a.
+//
+//   D[128 positions x BN out-channels] (fp32, TMEM) += A[128 x BK] (activations, bf16, smem via TMA)
+//                                                      * B[BN x BK]^T (weights, bf16, smem via TMA)
+// over (tap, input-channel block).  Activations are channel-last so both operands are K-major and a
+// tap is a row offset of the TMA box; zero padding is the TMA out-of-bounds fill.  Warp roles:
+// warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..9 = epilogue
+// (tcgen05.ld -> bias / residual / snake -> global).  Persistent CTAs, static tile round-robin,
+// two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Precision modes: single-pass bf16, or "bf16x3": x = hi + lo (two bf16 planes, 16 mantissa bits),
+// D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulate.
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <vector>
+
 #include "kernels_f32.cuh"
 
 namespace b2c {
-struct TcWeight { void* hi = nullptr; void* lo = nullptr; };
-struct TcConvPlan { int dummy = 0; };
-inline void tc_weight_free(TcWeight&) {}
-inline int tc_weight_pack(const float*, int, int, int, int, TcWeight*, size_t*) { return 0; }
-inline int tc_conv_plan(const ConvArgs&, const TcWeight&, int, int, TcConvPlan*) { return 1; }
-inline int tc_conv_launch(const TcConvPlan&, const ConvArgs&, const TcWeight&, cudaStream_t) { return -1; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (clock64() - t0 < 3000000000LL)   // ~1.5 s at 1.9 GHz
+    if (mbar_try_wait(bar, parity)) return;
+  printf("b2c conv_tc: mbarrier timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// K-major, swizzled shared-memory matrix descriptor (sm_100 UMMA): one swizzle atom along K
+// (BK * 2 bytes == swizzle span), 8-row groups SBO bytes apart.  Advancing along K inside the
+// atom = adding bytes to the start address (the swizzle is a function of the address bits).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                              // leading byte offset (unused: one atom along K)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+  d |= (uint64_t)(layout_type & 7u) << 61;             // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  return d;
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+struct TcConvParams {
+  const float* bias;
+  const float* res;
+  float* out_raw;
+  void* out_act;        // FMT_F32: float*; FMT_PLANES / FMT_HI: bf16 hi plane, lo plane = hi + act_plane_elems
+  const float* alpha;
+  long act_plane_elems;
+  int B, Lin, Cin, Cout, KT, in_step, dil, n_phase, Lj, out_step, Lout;
+  int in_off[8], out_off[8];
+  int act, res_mode, Tl, chunk, out_fmt;
+  int BN, BK, n_kblk, stages, tiles_j, n_ntiles, total_tiles;
+  int tmem_cols, acc_stride;
+  uint32_t a_bytes, b_bytes, sbo, layout_type;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 320;
+
+template <int X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (p.a_bytes + p.b_bytes) * (X3 ? 2u : 1u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (X3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_tfull[a]), 1); mbar_init(smem_u32(&bar_tempty[a]), 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int n_kiter = p.KT * p.n_kblk;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_ntiles;
+        int mt = tile / p.n_ntiles;
+        const int jt = mt % p.tiles_j;
+        mt /= p.tiles_j;
+        const int ph = mt % p.n_phase;
+        const int b = mt / p.n_phase;
+        const int j0 = jt * TC_BM;
+        for (int tap = 0; tap < p.KT; ++tap) {
+          const int brow = (ph * p.KT + tap) * p.Cout + nt * p.BN;
+          for (int cb = 0; cb < p.n_kblk; ++cb, ++it) {
+            const uint32_t s = it % p.stages, par = (it / p.stages) & 1u;
+            mbar_wait(smem_u32(&bar_empty[s]), par ^ 1u, 1);
+            const uint32_t full = smem_u32(&bar_full[s]);
+            mbar_expect_tx(full, stage_bytes);
+            const uint32_t sa = smem0 + s * stage_bytes;
+            const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
+            const int c0 = cb * p.BK;
+            if (p.in_step == 1) {
+              const int row = j0 + tap * p.dil + p.in_off[ph];
+              tma_load_3d(sa, &tmA_hi, full, c0, row, b);
+              if (X3) tma_load_3d(sa + p.a_bytes, &tmA_lo, full, c0, row, b);
+            } else {
+              const int kk = tap + p.in_off[ph];                 // dil == 1 for strided convs
+              int q = kk / p.in_step, r = kk - q * p.in_step;
+              if (r < 0) { r += p.in_step; q -= 1; }
+              tma_load_4d(sa, &tmA_hi, full, c0, r, j0 + q, b);
+              if (X3) tma_load_4d(sa + p.a_bytes, &tmA_lo, full, c0, r, j0 + q, b);
+            }
+            tma_load_2d(sb, &tmB_hi, full, c0, brow);
+            if (X3) tma_load_2d(sb + p.b_bytes, &tmB_lo, full, c0, brow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+      const int ksteps = p.BK / 16;
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        mbar_wait(smem_u32(&bar_tempty[acc]), apar ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        for (int ki = 0; ki < n_kiter; ++ki, ++it) {
+          const uint32_t s = it % p.stages, par = (it / p.stages) & 1u;
+          mbar_wait(smem_u32(&bar_full[s]), par, 3);
+          tc_fence_after();
+          const uint32_t sa = smem0 + s * stage_bytes;
+          const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = umma_desc(sa + k * 32, p.sbo, p.layout_type);
+            const uint64_t db = umma_desc(sb + k * 32, p.sbo, p.layout_type);
+            umma_bf16(d_tmem, da, db, idesc, (ki | k) != 0);
+            if (X3) {
+              const uint64_t da_lo = umma_desc(sa + p.a_bytes + k * 32, p.sbo, p.layout_type);
+              const uint64_t db_lo = umma_desc(sb + p.b_bytes + k * 32, p.sbo, p.layout_type);
+              umma_bf16(d_tmem, da, db_lo, idesc, 1);
+              umma_bf16(d_tmem, da_lo, db, idesc, 1);
+            }
+          }
+          umma_commit(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
+        }
+        umma_commit(smem_u32(&bar_tfull[acc]));   // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, TMEM lane quadrant = warp % 4 =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cols_per_half = p.BN >> 1;
+    const int row = quad * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % p.n_ntiles;
+      int mt = tile / p.n_ntiles;
+      const int jt = mt % p.tiles_j;
+      mt /= p.tiles_j;
+      const int ph = mt % p.n_phase;
+      const int b = mt / p.n_phase;
+      const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      mbar_wait(smem_u32(&bar_tfull[acc]), apar, 4);
+      tc_fence_after();
+      const int j = jt * TC_BM + row;
+      const int lo = j * p.out_step + p.out_off[ph];
+      const bool valid = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+      const size_t orow = ((size_t)b * p.Lout + (valid ? lo : 0)) * p.Cout;
+      size_t rrow = orow;
+      if (p.res_mode == 1) rrow = (size_t)(((valid ? lo : 0) % p.Tl) % p.chunk) * p.Cout;
+      const uint32_t t_row = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16);
+      for (int c = 0; c < cols_per_half; c += 16) {
+        const int col = half * cols_per_half + c;
+        float v[16];
+        tmem_ld16(t_row + col, v);
+        if (!valid) continue;
+        const int co = nt * p.BN + col;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co + i));
+            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+          }
+        }
+        if (p.res) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + rrow + co + i));
+            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+          }
+        }
+        if (p.out_raw) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(p.out_raw + orow + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (p.out_act) {
+          float w[16];
+          if (p.act == ACT_SNAKE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = snake_f(v[i], __ldg(p.alpha + co + i));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = apply_act(v[i], p.act, 0.f);
+          }
+          if (p.out_fmt == FMT_F32) {
+            float* o = reinterpret_cast<float*>(p.out_act);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(o + orow + co + i) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+          } else {
+            uint32_t hi[8], lo2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(w[2 * i], h0, l0);
+              split_bf16(w[2 * i + 1], h1, l1);
+              hi[i] = pack_bf16(h0, h1);
+              lo2[i] = pack_bf16(l0, l1);
+            }
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow + co;
+            *reinterpret_cast<uint4*>(oh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(oh + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            if (p.out_fmt == FMT_PLANES) {
+              __nv_bfloat16* ol = oh + p.act_plane_elems;
+              *reinterpret_cast<uint4*>(ol) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+              *reinterpret_cast<uint4*>(ol + 8) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// fp32 [n] -> bf16 hi plane [n] | lo plane [n]
+__global__ void split_planes_f32(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + i) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+    if (lo) *reinterpret_cast<uint2*>(lo + i) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+  } else {
+    for (; i < n; ++i) {
+      __nv_bfloat16 h, l;
+      split_bf16(x[i], h, l);
+      hi[i] = h;
+      if (lo) lo[i] = l;
+    }
+  }
+}
+
+// bf16 hi plane (+ lo plane) -> fp32
+__global__ void merge_planes_f32(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                 float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __bfloat162float(hi[i]);
+  if (lo) v += __bfloat162float(lo[i]);
+  out[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TcWeight {
+  __nv_bfloat16* hi = nullptr;   // [n_phase*KT*Cout][Cin], K-major
+  __nv_bfloat16* lo = nullptr;
+  int rows = 0, cin = 0;
+};
+
+inline void tc_weight_free(TcWeight& w) {
+  if (w.hi) cudaFree(w.hi);
+  if (w.lo) cudaFree(w.lo);
+  w.hi = w.lo = nullptr;
+}
+
+inline uint16_t f32_to_bf16_rn_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32_host(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// packed: fp32 [n_phase][KT][Cin][Cout] (the FP32 kernel's layout) -> bf16 hi/lo [n_phase][KT][Cout][Cin]
+inline int tc_weight_pack(const float* packed, int n_phase, int kt, int cin, int cout, TcWeight* out, size_t* bytes) {
+  if (cin % 32 != 0 || cout % 32 != 0) return 0;   // not a tensor-core layer (stem, head, tiny projections)
+  size_t n = (size_t)n_phase * kt * cin * cout;
+  std::vector<uint16_t> hi(n), lo(n);
+  for (int pt = 0; pt < n_phase * kt; ++pt)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        float w = packed[((size_t)pt * cin + ci) * cout + co];
+        uint16_t h = f32_to_bf16_rn_host(w);
+        uint16_t l = f32_to_bf16_rn_host(w - bf16_to_f32_host(h));
+        size_t o = ((size_t)pt * cout + co) * cin + ci;
+        hi[o] = h;
+        lo[o] = l;
+      }
+  if (cudaMalloc((void**)&out->hi, n * 2) != cudaSuccess) return -1;
+  if (cudaMalloc((void**)&out->lo, n * 2) != cudaSuccess) return -1;
+  if (cudaMemcpy(out->hi, hi.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  if (cudaMemcpy(out->lo, lo.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  out->rows = n_phase * kt * cout;
+  out->cin = cin;
+  if (bytes) *bytes += n * 4;
+  return 0;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+struct TcConvPlan {
+  TcConvParams p;
+  int x3 = 0;
+  int in_fmt = FMT_PLANES;
+  int grid = 0;
+  size_t smem = 0;
+  // tensor-map cache (re-encoded when the activation pointer changes)
+  const void* cached_x = nullptr;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  bool b_ready = false;
+};
+
+inline int largest_bn(int cout) {
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+inline bool tc_conv_eligible(const TcWeight& w, int cin, int cout, int stride, int dilation, int Lin) {
+  if (!w.hi || cin % 32 != 0 || !largest_bn(cout)) return false;
+  if (stride > 1 && (dilation != 1 || Lin % stride != 0)) return false;
+  return true;
+}
+
+// returns 0 = planned; >0 = shape not eligible; <0 = error
+inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int out_fmt, int sm_count, TcConvPlan* plan) {
+  if (!w.hi) return 1;
+  if (a.Cin % 32 != 0) return 2;
+  if (a.in_step > 1 && (a.dil != 1 || a.Lin % a.in_step != 0)) return 3;
+  const int bn = largest_bn(a.Cout);
+  if (!bn) return 4;
+  if (!tc_encode_fn()) return -10;
+  TcConvParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  plan->x3 = precision == 1 ? 1 : 0;
+  plan->in_fmt = plan->x3 ? FMT_PLANES : FMT_HI;
+  p.B = a.B; p.Lin = a.Lin; p.Cin = a.Cin; p.Cout = a.Cout; p.KT = a.KT; p.in_step = a.in_step; p.dil = a.dil;
+  p.n_phase = a.n_phase; p.Lj = a.Lj; p.out_step = a.out_step; p.Lout = a.Lout;
+  for (int i = 0; i < 8; ++i) { p.in_off[i] = a.in_off[i]; p.out_off[i] = a.out_off[i]; }
+  p.act = a.act; p.res_mode = a.res_mode; p.Tl = a.Tl; p.chunk = a.chunk; p.out_fmt = out_fmt;
+  p.act_plane_elems = (long)a.B * a.Lout * a.Cout;
+  p.BN = bn;
+  p.BK = (a.Cin % 64 == 0) ? 64 : 32;
+  p.n_kblk = a.Cin / p.BK;
+  p.a_bytes = TC_BM * p.BK * 2;
+  p.b_bytes = bn * p.BK * 2;
+  p.sbo = 8 * p.BK * 2;
+  p.layout_type = p.BK == 64 ? 2u : 4u;
+  const uint32_t stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) return 5;
+  p.stages = stages;
+  p.tiles_j = (a.Lj + TC_BM - 1) / TC_BM;
+  p.n_ntiles = a.Cout / bn;
+  long total = (long)a.B * a.n_phase * p.tiles_j * p.n_ntiles;
+  if (total > 0x7fffffffL) return 6;
+  p.total_tiles = (int)total;
+  p.acc_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+  p.tmem_cols = 2 * p.acc_stride;
+  plan->grid = (int)(total < sm_count ? total : sm_count);
+  plan->smem = (size_t)stages * stage + 1024;
+  plan->cached_x = nullptr;
+  plan->b_ready = false;
+  return 0;
+}
+
+inline int tc_encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                     const cuuint32_t* box, int bk) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = tc_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                              strides_b, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 100;
+}
+
+// x: bf16 hi plane of the input activations [B, Lin, Cin]; the lo plane follows at + B*Lin*Cin elements.
+inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const void* x_planes, void* out_act, const TcWeight& w,
+                          cudaStream_t st) {
+  TcConvParams p = plan.p;
+  p.bias = a.bias; p.res = a.res; p.out_raw = a.out_raw; p.out_act = out_act; p.alpha = a.alpha;
+  if (plan.cached_x != x_planes) {
+    const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(x_planes);
+    const __nv_bfloat16* xl = xh + (size_t)p.B * p.Lin * p.Cin;
+    int rc;
+    if (p.in_step == 1) {
+      cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Lin, (cuuint64_t)p.B};
+      cuuint64_t str[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
+      cuuint32_t box[3] = {(cuuint32_t)p.BK, TC_BM, 1};
+      rc = tc_encode(&plan.mA_hi, xh, 3, dims, str, box, p.BK);
+      if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 3, dims, str, box, p.BK);
+    } else {
+      const int S = p.in_step;
+      cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)S, (cuuint64_t)(p.Lin / S), (cuuint64_t)p.B};
+      cuuint64_t str[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)S * p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
+      cuuint32_t box[4] = {(cuuint32_t)p.BK, 1, TC_BM, 1};
+      rc = tc_encode(&plan.mA_hi, xh, 4, dims, str, box, p.BK);
+      if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 4, dims, str, box, p.BK);
+    }
+    if (rc) return rc;
+    plan.cached_x = x_planes;
+  }
+  if (!plan.b_ready) {
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)w.rows};
+    cuuint64_t str[1] = {(cuuint64_t)p.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
+    int rc = tc_encode(&plan.mB_hi, w.hi, 2, dims, str, box, p.BK);
+    if (!rc) rc = tc_encode(&plan.mB_lo, w.lo, 2, dims, str, box, p.BK);
+    if (rc) return rc;
+    plan.b_ready = true;
+  }
+  cudaError_t e;
+  if (plan.x3) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return -2;
+    conv_tc_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+  } else {
+    e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return -2;
+    conv_tc_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+  }
+  return 0;
+}
+
 inline int tc_nearest_launch(const RvqArgs&, int, int, cudaStream_t) { return 1; }
+
 }  // namespace b2c

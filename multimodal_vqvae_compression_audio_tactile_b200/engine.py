@@ -250,34 +250,80 @@ class Emitter:
         return Program(self.h, self.arena.peak + ALIGN, n_ext, dict(info, launches=self.lib.b2c_prog_num_launches(self.h)))
 
     # ops
-    def stem(self, w: ConvW, x, out_raw, out_act, alpha, B, Lx):
+    def stem(self, w: ConvW, x, out_raw, out_act, alpha, B, Lx, act_fmt=L.FMT_F32):
         L.check(self.lib.b2c_prog_stem(self.h, w.wid, self._r(x), self._r(out_raw), self._r(out_act),
                                        L.ACT_SNAKE if alpha is not None else L.ACT_NONE,
-                                       alpha if alpha is not None else -1, B, Lx), "b2c_prog_stem")
+                                       alpha if alpha is not None else -1, B, Lx, act_fmt), "b2c_prog_stem")
+
+    def convert(self, src, src_fmt, dst, dst_fmt, n):
+        L.check(self.lib.b2c_prog_convert(self.h, self._r(src), src_fmt, self._r(dst), dst_fmt, n),
+                "b2c_prog_convert")
+
+    def tc_ok(self, w: ConvW, Lin, prec) -> bool:
+        """Does the tcgen05 kernel take this layer at this precision?  (else: the FP32 CUDA-core kernel)"""
+        if prec == L.PREC_F32:
+            return False
+        return L.check(self.lib.b2c_conv_tc_eligible(self.eng.ctx, w.wid, Lin, w.stride, w.dilation),
+                       "b2c_conv_tc_eligible") == 1
+
+    def _contract(self, w: ConvW, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit):
+        """Shared by conv / convT: run the contraction at `prec` when the tensor-core kernel takes the
+        layer, else on the FP32 kernel, converting activation storage on either side when the caller's
+        formats differ from what that kernel reads / writes."""
+        if not self.tc_ok(w, Lin, prec):
+            prec = L.PREC_F32
+        need = L.FMT_OF_PREC[prec]
+        n_in, n_out = B * Lin * w.cin, B * Lout * w.cout
+        tmp_in = tmp_out = None
+        x_ok = x_fmt == need or (prec == L.PREC_BF16 and x_fmt == L.FMT_BF16X2)
+        if not x_ok:
+            if L.FMT_F32 not in (x_fmt, need):
+                raise L.B2CError(f"activation format {x_fmt} cannot feed a precision-{prec} contraction")
+            tmp_in = self.new(n_in)
+            self.convert(x, x_fmt, tmp_in, need, n_in)
+            x, x_fmt = tmp_in, need
+        k_act_fmt, k_out_act = act_fmt, out_act
+        if out_act is not None and prec == L.PREC_F32 and act_fmt != L.FMT_F32:
+            tmp_out = self.new(n_out)
+            k_act_fmt, k_out_act = L.FMT_F32, tmp_out
+        if out_act is None:
+            k_act_fmt = L.FMT_F32
+        emit(x, x_fmt, k_out_act, k_act_fmt, prec)
+        if tmp_out is not None:
+            self.convert(tmp_out, L.FMT_F32, out_act, act_fmt, n_out)
+        self.drop(tmp_in, tmp_out)
 
     def conv(self, w: ConvW, x, B, Lin, *, res=None, out_raw=None, out_act=None, act=L.ACT_NONE, alpha=None,
-             res_mode=0, Tl=0, chunk=0, prec=L.PREC_F32, stride=None, dilation=None, padding=None):
+             res_mode=0, Tl=0, chunk=0, prec=L.PREC_F32, x_fmt=L.FMT_F32, act_fmt=L.FMT_F32):
         if alpha is not None:
             act = L.ACT_SNAKE
-        L.check(self.lib.b2c_prog_conv(self.h, w.wid, self._r(x), self._r(res), self._r(out_raw), self._r(out_act),
-                                       act, alpha if alpha is not None else -1, B, Lin,
-                                       w.stride if stride is None else stride,
-                                       w.dilation if dilation is None else dilation,
-                                       w.padding if padding is None else padding, res_mode, Tl, chunk, prec),
-                "b2c_prog_conv")
+        Lout = (Lin + 2 * w.padding - w.dilation * (w.k - 1) - 1) // w.stride + 1
 
-    def convT(self, w: ConvW, x, B, Lin, *, out_raw=None, out_act=None, alpha=None, prec=L.PREC_F32):
-        L.check(self.lib.b2c_prog_convT(self.h, w.wid, self._r(x), self._r(out_raw), self._r(out_act),
-                                        L.ACT_SNAKE if alpha is not None else L.ACT_NONE,
-                                        alpha if alpha is not None else -1, B, Lin, prec), "b2c_prog_convT")
+        def emit(xb, xf, ob, of, pr):
+            L.check(self.lib.b2c_prog_conv(self.h, w.wid, self._r(xb), self._r(res), self._r(out_raw), self._r(ob),
+                                           act, alpha if alpha is not None else -1, B, Lin, w.stride, w.dilation,
+                                           w.padding, res_mode, Tl, chunk, pr, xf, of), "b2c_prog_conv")
 
-    def head(self, w: ConvW, x, y, B, Lx):
-        L.check(self.lib.b2c_prog_head(self.h, w.wid, self._r(x), self._r(y), B, Lx), "b2c_prog_head")
+        self._contract(w, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit)
+
+    def convT(self, w: ConvW, x, B, Lin, *, out_raw=None, out_act=None, alpha=None, prec=L.PREC_F32,
+              x_fmt=L.FMT_F32, act_fmt=L.FMT_F32):
+        Lout = (Lin - 1) * w.stride - 2 * w.padding + w.k
+
+        def emit(xb, xf, ob, of, pr):
+            L.check(self.lib.b2c_prog_convT(self.h, w.wid, self._r(xb), self._r(out_raw), self._r(ob),
+                                            L.ACT_SNAKE if alpha is not None else L.ACT_NONE,
+                                            alpha if alpha is not None else -1, B, Lin, pr, xf, of), "b2c_prog_convT")
+
+        self._contract(w, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit)
+
+    def head(self, w: ConvW, x, y, B, Lx, x_fmt=L.FMT_F32):
+        L.check(self.lib.b2c_prog_head(self.h, w.wid, self._r(x), self._r(y), B, Lx, x_fmt), "b2c_prog_head")
 
     def layernorm(self, gamma, beta, a, a_mode, out, N, Cc, Tl, chunk, *, sub=None, pe=-1, pe_mode=L.PE_NONE,
-                  tanh_post=0, post_scale=1.0):
+                  tanh_post=0, post_scale=1.0, out_fmt=L.FMT_F32):
         L.check(self.lib.b2c_prog_layernorm(self.h, gamma, beta, self._r(a), a_mode, self._r(sub), pe, pe_mode,
-                                            tanh_post, post_scale, self._r(out), N, Cc, Tl, chunk),
+                                            tanh_post, post_scale, self._r(out), N, Cc, Tl, chunk, out_fmt),
                 "b2c_prog_layernorm")
 
     def attention(self, q, q_mode, kv, out, B, Tl, chunk, heads, dh):
@@ -355,12 +401,14 @@ def _emit_ru(em: Emitter, ru: PackedRU, x_raw, x_act, B, Lx, next_alpha, need_ra
     """ResidualUnit: y = x + conv1(snake(conv7(snake(x)))).  x_act = snake1(x_raw) already exists.
     Returns (y_raw or None, y_act = snake_next(y))."""
     C_ = ru.c7.cout
+    f = L.FMT_OF_PREC[prec]
     h_act = em.new(B * Lx * C_)
-    em.conv(ru.c7, x_act, B, Lx, out_act=h_act, alpha=ru.a2, prec=prec)
+    em.conv(ru.c7, x_act, B, Lx, out_act=h_act, alpha=ru.a2, prec=prec, x_fmt=f, act_fmt=f)
     em.drop(x_act)
     y_raw = em.new(B * Lx * C_) if need_raw else None
     y_act = em.new(B * Lx * C_)
-    em.conv(ru.c1, h_act, B, Lx, res=x_raw, out_raw=y_raw, out_act=y_act, alpha=next_alpha, prec=prec)
+    em.conv(ru.c1, h_act, B, Lx, res=x_raw, out_raw=y_raw, out_act=y_act, alpha=next_alpha, prec=prec, x_fmt=f,
+            act_fmt=f)
     em.drop(h_act, x_raw)
     return y_raw, y_act
 
@@ -371,7 +419,8 @@ def emit_encoder(em: Emitter, pe: PackedEncoder, x, B, T, prec):
     Lx = T
     x_raw = em.new(B * Lx * c0)
     x_act = em.new(B * Lx * c0)
-    em.stem(pe.stem, x, x_raw, x_act, pe.blocks[0][0].a1, B, Lx)
+    f = L.FMT_OF_PREC[prec]
+    em.stem(pe.stem, x, x_raw, x_act, pe.blocks[0][0].a1, B, Lx, act_fmt=f)
     for bi, (r0, r1, r2, a_dn, dn) in enumerate(pe.blocks):
         x_raw, x_act = _emit_ru(em, r0, x_raw, x_act, B, Lx, r1.a1, True, prec)
         x_raw, x_act = _emit_ru(em, r1, x_raw, x_act, B, Lx, r2.a1, True, prec)
@@ -381,13 +430,13 @@ def emit_encoder(em: Emitter, pe: PackedEncoder, x, B, T, prec):
         n_raw = None if last else em.new(B * Lo * dn.cout)
         n_act = em.new(B * Lo * dn.cout)
         em.conv(dn, x_act, B, Lx, out_raw=n_raw, out_act=n_act,
-                alpha=pe.a_final if last else pe.blocks[bi + 1][0].a1, prec=prec)
+                alpha=pe.a_final if last else pe.blocks[bi + 1][0].a1, prec=prec, x_fmt=f, act_fmt=f)
         em.drop(x_act)
         x_raw, x_act, Lx = n_raw, n_act, Lo
     hd = pe.head
     Lo = (Lx + 2 * hd.padding - (hd.k - 1) - 1) // hd.stride + 1
     z = em.new(B * Lo * hd.cout)
-    em.conv(hd, x_act, B, Lx, out_raw=z, prec=prec)
+    em.conv(hd, x_act, B, Lx, out_raw=z, prec=prec, x_fmt=f)
     em.drop(x_act)
     return z, Lo
 
@@ -420,22 +469,23 @@ class PackedDecoder:
 def emit_decoder(em: Emitter, pd: PackedDecoder, z, y, B, Tl, prec, free_input=True):
     """z: [B, Tl, C] buffer -> y: [B, Lout] buffer."""
     Lx = Tl
+    f = L.FMT_OF_PREC[prec]
     x_act = em.new(B * Lx * pd.stem.cout)
-    em.conv(pd.stem, z, B, Lx, out_act=x_act, alpha=pd.blocks[0][0], prec=prec)
+    em.conv(pd.stem, z, B, Lx, out_act=x_act, alpha=pd.blocks[0][0], prec=prec, x_fmt=L.FMT_F32, act_fmt=f)
     if free_input:
         em.drop(z)
     for bi, (a_up, up, r0, r1, r2) in enumerate(pd.blocks):
         Lo = (Lx - 1) * up.stride - 2 * up.padding + up.k
         x_raw = em.new(B * Lo * up.cout)
         n_act = em.new(B * Lo * up.cout)
-        em.convT(up, x_act, B, Lx, out_raw=x_raw, out_act=n_act, alpha=r0.a1, prec=prec)
+        em.convT(up, x_act, B, Lx, out_raw=x_raw, out_act=n_act, alpha=r0.a1, prec=prec, x_fmt=f, act_fmt=f)
         em.drop(x_act)
         x_act, Lx = n_act, Lo
         nxt = pd.blocks[bi + 1][0] if bi + 1 < len(pd.blocks) else pd.a_final
         x_raw, x_act = _emit_ru(em, r0, x_raw, x_act, B, Lx, r1.a1, True, prec)
         x_raw, x_act = _emit_ru(em, r1, x_raw, x_act, B, Lx, r2.a1, True, prec)
         x_raw, x_act = _emit_ru(em, r2, x_raw, x_act, B, Lx, nxt, False, prec)
-    em.head(pd.head, x_act, y, B, Lx)
+    em.head(pd.head, x_act, y, B, Lx, x_fmt=f)
     em.drop(x_act)
     return Lx
 
@@ -487,16 +537,17 @@ def emit_predict_rows(em: Emitter, pp: PackedPredictor, qn, ctx, N, Tl, chunk, q
     """Everything after attention for N rows: y = out(ctx) + qn; z_pred = y + ffn(y).
     qn: LayerNorm-ed queries ([chunk, C] table when qn_is_table else [N, C]).  Frees ctx."""
     c = pp.c
+    f = L.FMT_OF_PREC[prec]
     y1 = em.new(N * c)
     em.conv(pp.wo, ctx, 1, N, res=qn, out_raw=y1, res_mode=1 if qn_is_table else 0, Tl=Tl, chunk=chunk, prec=prec)
     em.drop(ctx)
     h = em.new(N * c)
-    em.layernorm(pp.lnf_g, pp.lnf_b, y1, L.ROWS_DENSE, h, N, c, Tl, chunk)
+    em.layernorm(pp.lnf_g, pp.lnf_b, y1, L.ROWS_DENSE, h, N, c, Tl, chunk, out_fmt=f)
     f1 = em.new(N * pp.w1.cout)
-    em.conv(pp.w1, h, 1, N, out_act=f1, act=L.ACT_GELU, prec=prec)
+    em.conv(pp.w1, h, 1, N, out_act=f1, act=L.ACT_GELU, prec=prec, x_fmt=f, act_fmt=f)
     em.drop(h)
     z_pred = em.new(N * c)
-    em.conv(pp.w2, f1, 1, N, res=y1, out_raw=z_pred, prec=prec)
+    em.conv(pp.w2, f1, 1, N, res=y1, out_raw=z_pred, prec=prec, x_fmt=f)
     em.drop(f1, y1)
     return z_pred
 
@@ -505,10 +556,12 @@ def emit_residual_code(em: Emitter, pp: PackedPredictor, zt, zt_mode, z_pred, N,
                        row_mode, z_hat, prec):
     """r = zt - z_pred; rD = proj_down(scale*tanh(LN(r))); qD = RVQ(rD); z_hat = proj_up(qD) + z_pred."""
     c = pp.c
+    f = L.FMT_OF_PREC[prec]
     rn = em.new(N * c)
-    em.layernorm(pp.tn_g, pp.tn_b, zt, zt_mode, rn, N, c, Tl, chunk, sub=z_pred, tanh_post=1, post_scale=pp.scale)
+    em.layernorm(pp.tn_g, pp.tn_b, zt, zt_mode, rn, N, c, Tl, chunk, sub=z_pred, tanh_post=1, post_scale=pp.scale,
+                 out_fmt=f)
     rd = em.new(N * pp.code_dim)
-    em.conv(pp.down, rn, 1, N, out_raw=rd, prec=prec)
+    em.conv(pp.down, rn, 1, N, out_raw=rd, prec=prec, x_fmt=f)
     em.drop(rn)
     qd = em.new(N * pp.code_dim)
     em.rvq(pp.books, books_use, rd, qd, idx, N, row_mode, B, Tl, chunk)
@@ -524,10 +577,12 @@ def emit_latent_coder(em: Emitter, pp: PackedPredictor, qa, zt, z_run, idx, B, T
     c = pp.c
     N = B * Tl
     # K/V for every token
+    f = L.FMT_OF_PREC[prec]
     kvn = em.new(N * c)
-    em.layernorm(pp.lnkv_g, pp.lnkv_b, qa, L.ROWS_DENSE, kvn, N, c, Tl, chunk, pe=pp.pe, pe_mode=L.PE_CHUNK_POS)
+    em.layernorm(pp.lnkv_g, pp.lnkv_b, qa, L.ROWS_DENSE, kvn, N, c, Tl, chunk, pe=pp.pe, pe_mode=L.PE_CHUNK_POS,
+                 out_fmt=f)
     kv = em.new(N * 2 * c)
-    em.conv(pp.wkv, kvn, 1, N, out_raw=kv, prec=prec)
+    em.conv(pp.wkv, kvn, 1, N, out_raw=kv, prec=prec, x_fmt=f)
     em.drop(kvn)
     # pass 1: queries are LN_q(pe[pos]) -- a [chunk, C] table
     qn_tab = em.new(chunk * c)

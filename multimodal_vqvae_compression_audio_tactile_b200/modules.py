@@ -104,7 +104,8 @@ def _require_cuda(*tensors):
 class _Top(nn.Module):
     """A module that owns an Engine (packed weights + cached programs)."""
 
-    #: contraction arithmetic: 'f32' (CUDA-core FFMA), 'bf16x3' / 'bf16' (tcgen05)
+    #: contraction arithmetic plan (_lib.PLANS): 'f32' (CUDA-core FFMA everywhere), 'tc' (tcgen05: bf16 hi/lo
+    #: split x3 upstream of the quantizer, single-pass bf16 decoder), 'tc_exact', 'bf16', 'bf16x3'
     precision = "f32"
     #: signals per program launch (bounds the activation workspace)
     micro_batch = 32
@@ -122,11 +123,15 @@ class _Top(nn.Module):
     def _pack(self, eng):  # pragma: no cover
         raise NotImplementedError
 
-    def _prec(self, key=None):
+    def _prec(self, key):
+        """precision of stage `key` ('enc' | 'pred' | 'dec'): `precision` is a plan name (_lib.PLANS) or a
+        {stage: arithmetic} dict."""
         p = self.precision
-        if isinstance(p, dict):
-            p = p.get(key, "f32")
-        return L.PRECISIONS[p]
+        if isinstance(p, str):
+            if p not in L.PLANS:
+                raise ValueError(f"unknown precision plan {p!r}; choose from {sorted(L.PLANS)}")
+            p = L.PLANS[p]
+        return L.PRECISIONS[p.get(key, "f32")]
 
     def __getstate__(self):
         d = dict(self.__dict__)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.b2c_abi_version() == 1
+    assert lib.b2c_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define B2C_ABI_VERSION (\d+)", hdr).group(1))
 
 
 def test_no_cpu_fallback(lib):
