@@ -113,6 +113,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -146,7 +156,10 @@ struct TcConvParams {
 
 constexpr int TC_BM = 128;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int TC_STG_LD = 36;                        // floats per staging row: 32 columns + 4 pad (bank-conflict free)
+constexpr int TC_STG_BYTES = 2 * TC_BM * TC_STG_LD * 4;
 
 template <int X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -169,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tma_prefetch_desc(&tmB_hi);
     if (X3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_tfull[a]), 1); mbar_init(smem_u32(&bar_tempty[a]), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_tfull[a]), 1); mbar_init(smem_u32(&bar_tempty[a]), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -258,12 +271,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: 8 warps, TMEM lane quadrant = warp % 4 =====================
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int cols_per_half = p.BN >> 1;
-    const int row = quad * 32 + lane;
-    uint32_t tcount = 0;
+    // ===================== epilogue: 16 warps =====================
+    // Per 32-column chunk of the accumulator: (1) every warp copies its TMEM quadrant (thread = row, 8
+    // columns) into a padded fp32 staging tile in shared memory; (2) after a named barrier the 512 threads
+    // re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the bias / residual loads
+    // and the raw / activated stores are coalesced.  Two staging tiles alternate: one barrier per chunk.
+    const int ew = warp - 2;
+    const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    const int cg8 = ew >> 2;              // which 8 columns of the chunk this warp copies
+    const int et = threadIdx.x - 64;      // 0..511
+    const int cq = et & 7;                // float4 column group of the chunk in the row-major phase
+    const int r0 = et >> 3;               // rows r0 and r0 + 64
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
+    const int nchunks = p.BN >> 5;
+    uint32_t tcount = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % p.n_ntiles;
       int mt = tile / p.n_ntiles;
@@ -272,78 +293,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ph = mt % p.n_phase;
       const int b = mt / p.n_phase;
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      bool valid[2];
+      size_t orow[2], rrow[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int j = jt * TC_BM + r0 + 64 * i;
+        const int lo = j * p.out_step + p.out_off[ph];
+        valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+        const int los = valid[i] ? lo : 0;
+        orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
+        rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
+      }
       mbar_wait(smem_u32(&bar_tfull[acc]), apar, 4);
       tc_fence_after();
-      const int j = jt * TC_BM + row;
-      const int lo = j * p.out_step + p.out_off[ph];
-      const bool valid = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
-      const size_t orow = ((size_t)b * p.Lout + (valid ? lo : 0)) * p.Cout;
-      size_t rrow = orow;
-      if (p.res_mode == 1) rrow = (size_t)(((valid ? lo : 0) % p.Tl) % p.chunk) * p.Cout;
-      const uint32_t t_row = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16);
-      for (int c = 0; c < cols_per_half; c += 16) {
-        const int col = half * cols_per_half + c;
-        float v[16];
-        tmem_ld16(t_row + col, v);
-        if (!valid) continue;
-        const int co = nt * p.BN + col;
-        if (p.bias) {
+      const uint32_t t_src = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
+      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+        float* sb = stg + (chunk_ctr & 1u) * (TC_BM * TC_STG_LD);
+        const int co = nt * p.BN + c * 32 + cq * 4;
+        float4 rr[2];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co + i));
-            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
-          }
+        for (int i = 0; i < 2; ++i)
+          rr[i] = (p.res && valid[i]) ? __ldg(reinterpret_cast<const float4*>(p.res + rrow[i] + co))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+          float v[8];
+          tmem_ld8(t_src + c * 32, v);
+          float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
-        if (p.res) {
+        if (c == nchunks - 1) tc_fence_before();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (c == nchunks - 1 && et == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));   // accumulator drained
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb;
+        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+        if (p.out_act && p.act == ACT_SNAKE) al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + rrow + co + i));
-            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-          }
-        }
-        if (p.out_raw) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(p.out_raw + orow + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        if (p.out_act) {
-          float w[16];
-          if (p.act == ACT_SNAKE) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = snake_f(v[i], __ldg(p.alpha + co + i));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = apply_act(v[i], p.act, 0.f);
-          }
-          if (p.out_fmt == FMT_F32) {
-            float* o = reinterpret_cast<float*>(p.out_act);
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(o + orow + co + i) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
-          } else {
-            uint32_t hi[8], lo2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(w[2 * i], h0, l0);
-              split_bf16(w[2 * i + 1], h1, l1);
-              hi[i] = pack_bf16(h0, h1);
-              lo2[i] = pack_bf16(l0, l1);
+        for (int i = 0; i < 2; ++i) {
+          if (!valid[i]) continue;
+          float4 a = *reinterpret_cast<const float4*>(sb + (r0 + 64 * i) * TC_STG_LD + cq * 4);
+          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+          if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
+          if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
+          if (p.out_act) {
+            float4 w;
+            if (p.act == ACT_SNAKE) {
+              w.x = snake_f(a.x, al.x); w.y = snake_f(a.y, al.y); w.z = snake_f(a.z, al.z); w.w = snake_f(a.w, al.w);
+            } else {
+              w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
+              w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
             }
-            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow + co;
-            *reinterpret_cast<uint4*>(oh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(oh + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            if (p.out_fmt == FMT_PLANES) {
-              __nv_bfloat16* ol = oh + p.act_plane_elems;
-              *reinterpret_cast<uint4*>(ol) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-              *reinterpret_cast<uint4*>(ol + 8) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+            if (p.out_fmt == FMT_F32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + orow[i] + co) = w;
+            } else {
+              __nv_bfloat16 h[4], l[4];
+              split_bf16(w.x, h[0], l[0]); split_bf16(w.y, h[1], l[1]);
+              split_bf16(w.z, h[2], l[2]); split_bf16(w.w, h[3], l[3]);
+              __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow[i] + co;
+              *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+              if (p.out_fmt == FMT_PLANES)
+                *reinterpret_cast<uint2*>(oh + p.act_plane_elems) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
     }
   }
   tc_fence_before();
@@ -497,14 +510,23 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   p.act = a.act; p.res_mode = a.res_mode; p.Tl = a.Tl; p.chunk = a.chunk; p.out_fmt = out_fmt;
   p.act_plane_elems = (long)a.B * a.Lout * a.Cout;
   p.BN = bn;
-  p.BK = (a.Cin % 64 == 0) ? 64 : 32;
+  // shared memory: pipeline stages + the epilogue's two staging tiles + 1 KB of alignment slack, under the
+  // 227 KB per-CTA limit (the kernel's static shared memory is ~1.3 KB).  Prefer 128-byte K slices (BK = 64)
+  // when at least 3 stages fit, else 64-byte slices (BK = 32).
+  const int budget = 232448 - 2048 - TC_STG_BYTES - 1024;
+  uint32_t stage = 0;
+  int stages = 0;
+  for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= 32; bk -= 32) {
+    p.BK = bk;
+    p.a_bytes = TC_BM * bk * 2;
+    p.b_bytes = bn * bk * 2;
+    stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
+    stages = budget / (int)stage;
+    if (stages >= 3 || bk == 32) break;
+  }
   p.n_kblk = a.Cin / p.BK;
-  p.a_bytes = TC_BM * p.BK * 2;
-  p.b_bytes = bn * p.BK * 2;
   p.sbo = 8 * p.BK * 2;
   p.layout_type = p.BK == 64 ? 2u : 4u;
-  const uint32_t stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
-  int stages = (int)((200 * 1024) / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) return 5;
   p.stages = stages;
@@ -516,7 +538,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   p.acc_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
   p.tmem_cols = 2 * p.acc_stride;
   plan->grid = (int)(total < sm_count ? total : sm_count);
-  plan->smem = (size_t)stages * stage + 1024;
+  plan->smem = (size_t)stages * stage + TC_STG_BYTES + 1024;
   plan->cached_x = nullptr;
   plan->b_ready = false;
   return 0;
