@@ -174,6 +174,12 @@ extern "C" int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n) {
   w.n = n;
   int rc = upload(ctx, data, n, &w.dev);
   if (rc) return rc;
+  {  // reciprocal 1 / (v + 1e-9) in fp32, read by the snake epilogue of the tensor-core kernel
+    std::vector<float> inv(n);
+    for (size_t i = 0; i < n; ++i) inv[i] = 1.0f / (data[i] + 1e-9f);
+    rc = upload(ctx, inv.data(), n, &w.aux);
+    if (rc) return rc;
+  }
   ctx->w.push_back(w);
   return (int)ctx->w.size() - 1;
 }
@@ -651,7 +657,8 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         a.alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
         if (R.bad || !a.x || (!a.out_raw && !a.out_act)) return fail(B2C_ERR_WORKSPACE, "op %zu (conv): unresolved buffer", oi);
         if (op.type == OP_CONV_TC) {
-          int rc = tc_conv_launch(op.tc, a, x_any, act_any, w.tc, st);
+          const float* inv_alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].aux : nullptr;
+          int rc = tc_conv_launch(op.tc, a, inv_alpha, x_any, act_any, w.tc, st);
           if (rc) return fail(B2C_ERR_CUDA, "op %zu (conv, tcgen05): launch failed (%d)", oi, rc);
         } else {
           int rc = launch_conv_f32(a, st, ctx->sm_count);

@@ -51,6 +51,24 @@ __device__ __forceinline__ float snake_f(float v, float alpha) {
   float s = sinf(__fmul_rn(alpha, v));
   return __fadd_rn(v, __fmul_rn(inv, __fmul_rn(s, s)));
 }
+// sin(t)^2 for the tensor-core epilogues: t - k*pi by a 3-term Cody-Waite split, then an odd degree-9
+// polynomial on [-pi/2, pi/2] (the sign of sin does not matter).  Max abs error 2.6e-7 for |t| <= 60
+// (fp32 sinf squared: 1.2e-7), ~14 instructions instead of ~45.
+__device__ __forceinline__ float sin2_fast(float t) {
+  const float kf = fmaf(t, 0.31830987334251404f, 12582912.f) - 12582912.f;   // rint(t / pi)
+  float r = fmaf(kf, -3.140625f, t);
+  r = fmaf(kf, -9.67502593994140625e-4f, r);
+  r = fmaf(kf, -1.509957990978376e-07f, r);
+  const float u = r * r;
+  float q = fmaf(u, 2.600054131107754e-06f, -0.00019806614727713168f);
+  q = fmaf(u, q, 0.008333017118275166f);
+  q = fmaf(u, q, -0.16666656732559204f);
+  const float sn = fmaf(u * r, q, r);
+  return sn * sn;
+}
+// snake with the reciprocal 1/(alpha + 1e-9) precomputed per channel
+__device__ __forceinline__ float snake_fast(float v, float alpha, float inv) { return fmaf(inv, sin2_fast(alpha * v), v); }
+
 __device__ __forceinline__ float gelu_f(float v) {
   // nn.GELU() (erf form): 0.5 x (1 + erf(x / sqrt 2))
   return __fmul_rn(__fmul_rn(v, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(v, 0.70710678118654752440f))));

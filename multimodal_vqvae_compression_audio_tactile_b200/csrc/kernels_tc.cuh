@@ -145,6 +145,7 @@ struct TcConvParams {
   float* out_raw;
   void* out_act;        // FMT_F32: float*; FMT_PLANES / FMT_HI: bf16 hi plane, lo plane = hi + act_plane_elems
   const float* alpha;
+  const float* inv_alpha;   // 1 / (alpha + 1e-9), fp32, precomputed at pack time
   long act_plane_elems;
   int B, Lin, Cin, Cout, KT, in_step, dil, n_phase, Lj, out_step, Lout;
   int in_off[8], out_off[8];
@@ -315,6 +316,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int i = 0; i < 2; ++i)
           rr[i] = (p.res && valid[i]) ? __ldg(reinterpret_cast<const float4*>(p.res + rrow[i] + co))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
+        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+        if (p.out_act && p.act == ACT_SNAKE) {
+          al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
+          ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+        }
         {
           float v[8];
           tmem_ld8(t_src + c * 32, v);
@@ -325,9 +332,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (c == nchunks - 1) tc_fence_before();
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (c == nchunks - 1 && et == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));   // accumulator drained
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb;
-        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-        if (p.out_act && p.act == ACT_SNAKE) al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (!valid[i]) continue;
@@ -338,7 +342,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (p.out_act) {
             float4 w;
             if (p.act == ACT_SNAKE) {
-              w.x = snake_f(a.x, al.x); w.y = snake_f(a.y, al.y); w.z = snake_f(a.z, al.z); w.w = snake_f(a.w, al.w);
+              w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
+              w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
             } else {
               w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
               w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
@@ -346,13 +351,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (p.out_fmt == FMT_F32) {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + orow[i] + co) = w;
             } else {
-              __nv_bfloat16 h[4], l[4];
-              split_bf16(w.x, h[0], l[0]); split_bf16(w.y, h[1], l[1]);
-              split_bf16(w.z, h[2], l[2]); split_bf16(w.w, h[3], l[3]);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
               __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow[i] + co;
-              *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-              if (p.out_fmt == FMT_PLANES)
-                *reinterpret_cast<uint2*>(oh + p.act_plane_elems) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+              *reinterpret_cast<uint2*>(oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
+                                                         *reinterpret_cast<const uint32_t*>(&h23));
+              if (p.out_fmt == FMT_PLANES) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
+                *reinterpret_cast<uint2*>(oh + p.act_plane_elems) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+              }
             }
           }
         }
@@ -555,10 +564,11 @@ inline int tc_encode(CUtensorMap* m, const void* base, int rank, const cuuint64_
 }
 
 // x: bf16 hi plane of the input activations [B, Lin, Cin]; the lo plane follows at + B*Lin*Cin elements.
-inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const void* x_planes, void* out_act, const TcWeight& w,
-                          cudaStream_t st) {
+inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_alpha, const void* x_planes,
+                          void* out_act, const TcWeight& w, cudaStream_t st) {
   TcConvParams p = plan.p;
   p.bias = a.bias; p.res = a.res; p.out_raw = a.out_raw; p.out_act = out_act; p.alpha = a.alpha;
+  p.inv_alpha = inv_alpha;
   if (plan.cached_x != x_planes) {
     const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(x_planes);
     const __nv_bfloat16* xl = xh + (size_t)p.B * p.Lin * p.Cin;
