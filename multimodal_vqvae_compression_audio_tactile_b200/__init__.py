@@ -7,4 +7,4 @@ from .modules import (AR_CHUNK_TOK, CODE_DIM, DAC, CrossPredictor, Decoder, Enco
 from .ops import nearest_code  # noqa: F401
 
 #: contraction arithmetic bench.py / smoke() use by default (see DESIGN.md "Precision")
-DEFAULT_PRECISION = "f32"
+DEFAULT_PRECISION = "tc"

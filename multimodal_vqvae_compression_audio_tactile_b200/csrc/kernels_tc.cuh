@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -97,6 +98,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
   d |= (uint64_t)(layout_type & 7u) << 61;             // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   return d;
 }
+// The constant high part of the descriptor; the low word is (smem byte address >> 4), so moving the
+// start address by n bytes is an integer add of n >> 4 (shared memory addresses are < 2^18).
+__device__ __forceinline__ uint64_t umma_desc_base(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(layout_type & 7u) << 61);
+}
 // instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -108,6 +114,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Converged-warp variants: every lane executes them, elect.sync picks the one lane that issues.  ptxas then
+// emits a predicated UTCHMMA with uniform-register operands instead of a per-active-thread serialisation loop.
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, p;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -153,6 +178,9 @@ struct TcConvParams {
   int BN, BK, n_kblk, stages, tiles_j, n_ntiles, total_tiles;
   int tmem_cols, acc_stride;
   uint32_t a_bytes, b_bytes, sbo, layout_type;
+  // slab kernel (conv_tc2_kernel): MT m-tiles per work item share one activation slab and every weight tile
+  int MT, groups_j, slab_rows, box_rows, n_aloads, SA, SB;
+  uint32_t row_bytes, a_plane_bytes;
 };
 
 constexpr int TC_BM = 128;
@@ -161,6 +189,94 @@ constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 constexpr int TC_STG_LD = 36;                        // floats per staging row: 32 columns + 4 pad (bank-conflict free)
 constexpr int TC_STG_BYTES = 2 * TC_BM * TC_STG_LD * 4;
+
+
+// Epilogue of one 128 x BN accumulator (16 warps).  Per 32-column chunk: (1) every warp copies its TMEM
+// quadrant (thread = row, 8 columns) into a padded fp32 staging tile in shared memory; (2) after a named
+// barrier the 512 threads re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the
+// bias / residual loads and the raw / activated stores are coalesced.  Two staging tiles alternate: one
+// barrier per chunk.  When tempty_bar != 0 it is arrived on once the accumulator has been drained.
+__device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
+                                                 int b, int ph, int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
+  const int ew = warp - 2;
+  const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+  const int cg8 = ew >> 2;              // which 8 columns of the chunk this warp copies
+  const int et = threadIdx.x - 64;      // 0..511
+  const int cq = et & 7;                // float4 column group of the chunk in the row-major phase
+  const int r0 = et >> 3;               // rows r0 and r0 + 64
+  const int nchunks = p.BN >> 5;
+  bool valid[2];
+  size_t orow[2], rrow[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = jt * TC_BM + r0 + 64 * i;
+    const int lo = j * p.out_step + p.out_off[ph];
+    valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+    const int los = valid[i] ? lo : 0;
+    orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
+    rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
+  }
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
+  for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+    float* sb = stg + (chunk_ctr & 1u) * (TC_BM * TC_STG_LD);
+    const int co = nt * p.BN + c * 32 + cq * 4;
+    float4 rr[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      rr[i] = (p.res && valid[i]) ? __ldg(reinterpret_cast<const float4*>(p.res + rrow[i] + co))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
+    if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+    if (p.out_act && p.act == ACT_SNAKE) {
+      al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
+      ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+    }
+    {
+      float v[8];
+      tmem_ld8(t_src + c * 32, v);
+      float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    const bool last = (c == nchunks - 1) && tempty_bar != 0;
+    if (last) tc_fence_before();
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (last && et == 0) mbar_arrive(tempty_bar);   // accumulator (set) drained
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (!valid[i]) continue;
+      float4 a = *reinterpret_cast<const float4*>(sb + (r0 + 64 * i) * TC_STG_LD + cq * 4);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
+      if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
+      if (p.out_act) {
+        float4 w;
+        if (p.act == ACT_SNAKE) {
+          w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
+          w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+        } else {
+          w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
+          w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
+        }
+        if (p.out_fmt == FMT_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + orow[i] + co) = w;
+        } else {
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
+          __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow[i] + co;
+          *reinterpret_cast<uint2*>(oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
+                                                     *reinterpret_cast<const uint32_t*>(&h23));
+          if (p.out_fmt == FMT_PLANES) {
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
+            *reinterpret_cast<uint2*>(oh + p.act_plane_elems) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          }
+        }
+      }
+    }
+  }
+}
 
 template <int X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -240,9 +356,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop so that descriptors and addresses live in uniform
+    // registers; only lane 0 issues tcgen05.mma / tcgen05.commit.
+    {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
       const int ksteps = p.BK / 16;
+      const uint64_t dbase = umma_desc_base(p.sbo, p.layout_type);
+      const uint32_t a_lo_off = p.a_bytes >> 4, b_lo_off = p.b_bytes >> 4;
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
@@ -255,20 +375,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes;
           const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = umma_desc(sa + k * 32, p.sbo, p.layout_type);
-            const uint64_t db = umma_desc(sb + k * 32, p.sbo, p.layout_type);
-            umma_bf16(d_tmem, da, db, idesc, (ki | k) != 0);
+          uint64_t da = dbase | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          uint64_t db = dbase | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
+            umma_bf16_w(d_tmem, da, db, idesc, (ki | k) != 0);
             if (X3) {
-              const uint64_t da_lo = umma_desc(sa + p.a_bytes + k * 32, p.sbo, p.layout_type);
-              const uint64_t db_lo = umma_desc(sb + p.b_bytes + k * 32, p.sbo, p.layout_type);
-              umma_bf16(d_tmem, da, db_lo, idesc, 1);
-              umma_bf16(d_tmem, da_lo, db, idesc, 1);
+              umma_bf16_w(d_tmem, da, db + b_lo_off, idesc, 1);
+              umma_bf16_w(d_tmem, da + a_lo_off, db, idesc, 1);
             }
           }
-          umma_commit(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
+          umma_commit_w(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
         }
-        umma_commit(smem_u32(&bar_tfull[acc]));   // accumulator complete -> epilogue
+        umma_commit_w(smem_u32(&bar_tfull[acc]));   // accumulator complete -> epilogue
       }
     }
   } else {
@@ -277,14 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // columns) into a padded fp32 staging tile in shared memory; (2) after a named barrier the 512 threads
     // re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the bias / residual loads
     // and the raw / activated stores are coalesced.  Two staging tiles alternate: one barrier per chunk.
-    const int ew = warp - 2;
-    const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-    const int cg8 = ew >> 2;              // which 8 columns of the chunk this warp copies
-    const int et = threadIdx.x - 64;      // 0..511
-    const int cq = et & 7;                // float4 column group of the chunk in the row-major phase
-    const int r0 = et >> 3;               // rows r0 and r0 + 64
     float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
-    const int nchunks = p.BN >> 5;
     uint32_t tcount = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % p.n_ntiles;
@@ -294,78 +405,191 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ph = mt % p.n_phase;
       const int b = mt / p.n_phase;
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-      bool valid[2];
-      size_t orow[2], rrow[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int j = jt * TC_BM + r0 + 64 * i;
-        const int lo = j * p.out_step + p.out_off[ph];
-        valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
-        const int los = valid[i] ? lo : 0;
-        orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
-        rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
-      }
       mbar_wait(smem_u32(&bar_tfull[acc]), apar, 4);
       tc_fence_after();
-      const uint32_t t_src = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
-      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-        float* sb = stg + (chunk_ctr & 1u) * (TC_BM * TC_STG_LD);
-        const int co = nt * p.BN + c * 32 + cq * 4;
-        float4 rr[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          rr[i] = (p.res && valid[i]) ? __ldg(reinterpret_cast<const float4*>(p.res + rrow[i] + co))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
-        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-        if (p.out_act && p.act == ACT_SNAKE) {
-          al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
-          ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+      tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]), warp,
+                       lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab kernel (stride-1 convs, ConvTranspose1d phases, linears).  The generic kernel above re-reads the
+// activation tile once per tap and the weight tile once per 128 positions, which makes the long, narrow
+// layers L2-bandwidth bound.  Here a work item is MT consecutive 128-position tiles x one BN channel
+// block:
+//   * per input-channel block ONE activation slab of MT*128 + (KT-1)*dil rows is loaded; tap t of m-tile m
+//     is the same shared memory at a row offset (m*128 + t*dil): only the UMMA descriptor start address
+//     moves (the 128B/64B swizzle is a function of the absolute smem address, which TMA used when writing);
+//   * every (tap, channel block) weight tile is loaded once and feeds the MT accumulators (MT*BN TMEM
+//     columns, double buffered).
+// Two rings: activation slabs (SA slots) and weight tiles (SB slots).
+// ---------------------------------------------------------------------------------------------
+constexpr int TC2_MAX_SA = 4;
+constexpr int TC2_MAX_SB = 8;
+
+template <int X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_afull[TC2_MAX_SA];
+  __shared__ __align__(8) uint64_t bar_aempty[TC2_MAX_SA];
+  __shared__ __align__(8) uint64_t bar_bfull[TC2_MAX_SB];
+  __shared__ __align__(8) uint64_t bar_bempty[TC2_MAX_SB];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t planes = X3 ? 2u : 1u;
+  const uint32_t a_slot = p.a_plane_bytes * planes;
+  const uint32_t b_slot = p.b_bytes * planes;
+  const uint32_t smemB = smem0 + p.SA * a_slot;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (X3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aempty[i]), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t set_cols = (uint32_t)(p.MT * p.acc_stride);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // Steps = (work item, input-channel block) in order.  The slab of step s+1 is requested BEFORE the weight
+    // tiles of step s, so the (large, possibly DRAM-resident) activation slab has a whole step of lead time
+    // instead of the few weight tiles the B ring would otherwise allow.
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      auto issue_slab = [&](int item, int cb) {
+        int r = item / p.n_ntiles;
+        const int jg = r % p.groups_j;
+        r /= p.groups_j;
+        const int ph = r % p.n_phase;
+        const int b = r / p.n_phase;
+        const int row0 = jg * p.MT * TC_BM + p.in_off[ph];
+        const uint32_t sa = ia % p.SA, par = (ia / p.SA) & 1u;
+        mbar_wait(smem_u32(&bar_aempty[sa]), par ^ 1u, 1);
+        const uint32_t full = smem_u32(&bar_afull[sa]);
+        mbar_expect_tx(full, a_slot);
+        const uint32_t dst = smem0 + sa * a_slot;
+        for (int ld = 0; ld < p.n_aloads; ++ld) {
+          const uint32_t off = (uint32_t)(ld * p.box_rows) * p.row_bytes;
+          tma_load_3d(dst + off, &tmA_hi, full, cb * p.BK, row0 + ld * p.box_rows, b);
+          if (X3) tma_load_3d(dst + p.a_plane_bytes + off, &tmA_lo, full, cb * p.BK, row0 + ld * p.box_rows, b);
         }
-        {
-          float v[8];
-          tmem_ld8(t_src + c * 32, v);
-          float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
-          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (c == nchunks - 1) tc_fence_before();
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (c == nchunks - 1 && et == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));   // accumulator drained
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (!valid[i]) continue;
-          float4 a = *reinterpret_cast<const float4*>(sb + (r0 + 64 * i) * TC_STG_LD + cq * 4);
-          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-          if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
-          if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
-          if (p.out_act) {
-            float4 w;
-            if (p.act == ACT_SNAKE) {
-              w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
-              w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
-            } else {
-              w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
-              w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
-            }
-            if (p.out_fmt == FMT_F32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + orow[i] + co) = w;
-            } else {
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
-              __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow[i] + co;
-              *reinterpret_cast<uint2*>(oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
-                                                         *reinterpret_cast<const uint32_t*>(&h23));
-              if (p.out_fmt == FMT_PLANES) {
-                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
-                const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
-                *reinterpret_cast<uint2*>(oh + p.act_plane_elems) =
-                    make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-              }
-            }
+        ++ia;
+      };
+      if ((int)blockIdx.x < p.total_tiles) issue_slab(blockIdx.x, 0);
+      for (int item = blockIdx.x; item < p.total_tiles; item += gridDim.x) {
+        const int nt = item % p.n_ntiles;
+        const int ph = (item / (p.n_ntiles * p.groups_j)) % p.n_phase;
+        for (int cb = 0; cb < p.n_kblk; ++cb) {
+          if (cb + 1 < p.n_kblk) issue_slab(item, cb + 1);
+          else if (item + (int)gridDim.x < p.total_tiles) issue_slab(item + gridDim.x, 0);
+          const int c0 = cb * p.BK;
+          for (int tap = 0; tap < p.KT; ++tap, ++ib) {
+            const uint32_t sb = ib % p.SB, par = (ib / p.SB) & 1u;
+            mbar_wait(smem_u32(&bar_bempty[sb]), par ^ 1u, 2);
+            const uint32_t full = smem_u32(&bar_bfull[sb]);
+            mbar_expect_tx(full, b_slot);
+            const int brow = (ph * p.KT + tap) * p.Cout + nt * p.BN;
+            const uint32_t dst = smemB + sb * b_slot;
+            tma_load_2d(dst, &tmB_hi, full, c0, brow);
+            if (X3) tma_load_2d(dst + p.b_bytes, &tmB_lo, full, c0, brow);
           }
         }
       }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, lane 0 issues) =====================
+    {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+      const int ksteps = p.BK / 16;
+      const uint64_t dbase = umma_desc_base(p.sbo, p.layout_type);
+      const uint32_t a_lo_off = p.a_plane_bytes >> 4, b_lo_off = p.b_bytes >> 4;
+      const uint32_t tap_step = ((uint32_t)p.dil * p.row_bytes) >> 4;        // descriptor units per tap
+      const uint32_t mtile_step = ((uint32_t)TC_BM * p.row_bytes) >> 4;      // descriptor units per m-tile
+      uint32_t ia = 0, ib = 0, tcount = 0;
+      for (int item = blockIdx.x; item < p.total_tiles; item += gridDim.x, ++tcount) {
+        const int jg = (item / p.n_ntiles) % p.groups_j;
+        const int n_m = min(p.MT, p.tiles_j - jg * p.MT);
+        const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        mbar_wait(smem_u32(&bar_tempty[acc]), apar ^ 1u, 3);
+        tc_fence_after();
+        const uint32_t d_set = tmem_base + acc * set_cols;
+        for (int cb = 0; cb < p.n_kblk; ++cb, ++ia) {
+          const uint32_t sa = ia % p.SA, apr = (ia / p.SA) & 1u;
+          mbar_wait(smem_u32(&bar_afull[sa]), apr, 4);
+          tc_fence_after();
+          const uint64_t da_slab = dbase | (uint64_t)(((smem0 + sa * a_slot) & 0x3FFFFu) >> 4);
+          for (int tap = 0; tap < p.KT; ++tap, ++ib) {
+            const uint32_t sb = ib % p.SB, bpr = (ib / p.SB) & 1u;
+            mbar_wait(smem_u32(&bar_bfull[sb]), bpr, 5);
+            tc_fence_after();
+            const uint64_t db0 = dbase | (uint64_t)(((smemB + sb * b_slot) & 0x3FFFFu) >> 4);
+            uint64_t da_m = da_slab + (uint64_t)(tap * tap_step);
+            for (int m = 0; m < n_m; ++m, da_m += mtile_step) {
+              const uint32_t d_tmem = d_set + m * p.acc_stride;
+              uint64_t da = da_m, db = db0;
+              for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
+                umma_bf16_w(d_tmem, da, db, idesc, (cb | tap | k) != 0);
+                if (X3) {
+                  umma_bf16_w(d_tmem, da, db + b_lo_off, idesc, 1);
+                  umma_bf16_w(d_tmem, da + a_lo_off, db, idesc, 1);
+                }
+              }
+            }
+            umma_commit_w(smem_u32(&bar_bempty[sb]));
+          }
+          umma_commit_w(smem_u32(&bar_aempty[sa]));
+        }
+        umma_commit_w(smem_u32(&bar_tfull[acc]));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)p.SA * a_slot +
+                                          (size_t)p.SB * b_slot);
+    uint32_t tcount = 0, chunk_ctr = 0;
+    for (int item = blockIdx.x; item < p.total_tiles; item += gridDim.x, ++tcount) {
+      const int nt = item % p.n_ntiles;
+      int r = item / p.n_ntiles;
+      const int jg = r % p.groups_j;
+      r /= p.groups_j;
+      const int ph = r % p.n_phase;
+      const int b = r / p.n_phase;
+      const int n_m = min(p.MT, p.tiles_j - jg * p.MT);
+      const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      mbar_wait(smem_u32(&bar_tfull[acc]), apar, 6);
+      tc_fence_after();
+      for (int m = 0; m < n_m; ++m)
+        tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * set_cols + m * p.acc_stride, b, ph, jg * p.MT + m, nt,
+                         m == n_m - 1 ? smem_u32(&bar_tempty[acc]) : 0u, warp, lane);
     }
   }
   tc_fence_before();
@@ -479,6 +703,7 @@ inline PFN_encodeTiled tc_encode_fn() {
 
 struct TcConvPlan {
   TcConvParams p;
+  int slab = 0;   // 1: conv_tc2_kernel (activation slab + MT m-tiles), 0: conv_tc_kernel
   int x3 = 0;
   int in_fmt = FMT_PLANES;
   int grid = 0;
@@ -488,6 +713,26 @@ struct TcConvPlan {
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   bool b_ready = false;
 };
+
+// B2C_TC_SLAB=0 in the environment keeps every layer on the generic kernel (a debugging / A-B switch)
+inline bool tc_slab_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_TC_SLAB");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// B2C_TC_SLAB=2 forces the slab kernel on every stride-1 layer it can take
+inline bool tc_slab_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_TC_SLAB");
+    v = (e && e[0] == '2') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 inline int largest_bn(int cout) {
   for (int bn = 256; bn >= 32; bn -= 32)
@@ -550,6 +795,61 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   plan->smem = (size_t)stages * stage + TC_STG_BYTES + 1024;
   plan->cached_x = nullptr;
   plan->b_ready = false;
+  plan->slab = 0;
+  // Measured on B200 (tools/tc_selftest.py, batch 32): the slab kernel wins where the generic kernel's MMA is
+  // narrow (N <= 128) and the contraction is long enough to amortise the slab (k = 7 at 96 / 128 channels);
+  // wider layers are MMA-issue bound and prefer the generic kernel's N = 192 / 256 instructions.
+  const bool slab_pays = a.KT >= 3 && (a.Cout == 96 || a.Cout == 128);
+  if (a.in_step == 1 && tc_slab_enabled() && (slab_pays || tc_slab_forced())) {
+    // slab kernel: narrower channel blocks, several m-tiles per work item
+    const int bn2 = a.Cout % 128 == 0 ? 128 : (a.Cout % 96 == 0 ? 96 : (a.Cout % 64 == 0 ? 64 : bn));
+    const int stride2 = bn2 <= 64 ? 64 : (bn2 <= 128 ? 128 : 256);
+    int mt = 256 / stride2;
+    if (mt > 4) mt = 4;
+    while (mt > 1 && mt > p.tiles_j) mt >>= 1;
+    const int planes = plan->x3 ? 2 : 1;
+    for (; mt >= 1 && !plan->slab; mt >>= 1) {
+      for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= 32 && !plan->slab; bk -= 32) {
+        int rows = mt * TC_BM + (a.KT - 1) * a.dil;
+        const int n_loads = (rows + 255) / 256;
+        const int q = 16 * n_loads;
+        rows = (rows + q - 1) / q * q;
+        const int box_rows = rows / n_loads;
+        if (box_rows > 256) continue;
+        const uint32_t a_plane = (uint32_t)rows * bk * 2;
+        const uint32_t a_slot = a_plane * planes;
+        const uint32_t b_bytes = (uint32_t)bn2 * bk * 2;
+        const uint32_t b_slot = b_bytes * planes;
+        // three slab slots (one in use, one landed, one in flight) when they leave room for >= 4 weight tiles
+        int SA = 3;
+        if ((long)budget - 3L * a_slot < 4L * b_slot) {
+          if (mt > 1) continue;   // fewer m-tiles per item rather than a two-slot slab ring
+          SA = 2;
+        }
+        const long rest = (long)budget - (long)SA * a_slot;
+        if (rest < 3L * b_slot) continue;
+        int SB = (int)(rest / b_slot);
+        if (SB > TC2_MAX_SB) SB = TC2_MAX_SB;
+        p.BN = bn2; p.BK = bk; p.n_kblk = a.Cin / bk;
+        p.a_bytes = TC_BM * bk * 2; p.b_bytes = b_bytes;
+        p.sbo = 8 * bk * 2; p.layout_type = bk == 64 ? 2u : 4u;
+        p.n_ntiles = a.Cout / bn2;
+        p.acc_stride = stride2;
+        p.MT = mt; p.groups_j = (p.tiles_j + mt - 1) / mt;
+        p.slab_rows = rows; p.box_rows = box_rows; p.n_aloads = n_loads; p.SA = SA; p.SB = SB;
+        p.row_bytes = bk * 2; p.a_plane_bytes = a_plane;
+        p.tmem_cols = 2 * mt * stride2;
+        if (p.tmem_cols < 32) p.tmem_cols = 32;
+        long items = (long)a.B * a.n_phase * p.groups_j * p.n_ntiles;
+        if (items > 0x7fffffffL) continue;
+        p.total_tiles = (int)items;
+        p.stages = 0;
+        plan->grid = (int)(items < sm_count ? items : sm_count);
+        plan->smem = (size_t)SA * a_slot + (size_t)SB * b_slot + TC_STG_BYTES + 1024;
+        plan->slab = 1;
+      }
+    }
+  }
   return 0;
 }
 
@@ -576,7 +876,7 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
     if (p.in_step == 1) {
       cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Lin, (cuuint64_t)p.B};
       cuuint64_t str[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
-      cuuint32_t box[3] = {(cuuint32_t)p.BK, TC_BM, 1};
+      cuuint32_t box[3] = {(cuuint32_t)p.BK, (cuuint32_t)(plan.slab ? p.box_rows : TC_BM), 1};
       rc = tc_encode(&plan.mA_hi, xh, 3, dims, str, box, p.BK);
       if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 3, dims, str, box, p.BK);
     } else {
@@ -600,6 +900,18 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
     plan.b_ready = true;
   }
   cudaError_t e;
+  if (plan.slab) {
+    if (plan.x3) {
+      e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+      if (e != cudaSuccess) return -2;
+      conv_tc2_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    } else {
+      e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+      if (e != cudaSuccess) return -2;
+      conv_tc2_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    }
+    return 0;
+  }
   if (plan.x3) {
     e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;

@@ -106,7 +106,7 @@ class _Top(nn.Module):
 
     #: contraction arithmetic plan (_lib.PLANS): 'f32' (CUDA-core FFMA everywhere), 'tc' (tcgen05: bf16 hi/lo
     #: split x3 upstream of the quantizer, single-pass bf16 decoder), 'tc_exact', 'bf16', 'bf16x3'
-    precision = "f32"
+    precision = "tc"
     #: signals per program launch (bounds the activation workspace)
     micro_batch = 32
 

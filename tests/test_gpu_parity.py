@@ -13,9 +13,20 @@ from oracle import cases, proposed
 
 pytestmark = pytest.mark.gpu
 
-TIE = 1e-5          # oracle score margin below which an index flip is a documented near-tie
-Y_TOL_F32 = 2e-5    # max |y - y_ref| for the fp32 path when all indices agree (|y| <= ~0.15)
-PRECISIONS = ["f32"]
+# Arithmetic plans (multimodal_vqvae_compression_audio_tactile_b200/_lib.py PLANS):
+#   f32: FP32 FFMA everywhere.  tc: tcgen05, bf16 hi/lo split x3 (>= 16 mantissa bits) upstream of the
+#   quantizer, single-pass bf16 in the decoder.
+# TIE: oracle top-1/top-2 score margin below which an index flip is a documented floating-point near-tie
+#   (scores are O(1); fp32 summation-order noise is ~1e-6, the bf16x3 contractions add ~1e-5 relative).
+# Y_TOL: max |y - y_ref| when all indices agree (|y| <= ~0.15).  PSNR_MIN: reconstruction PSNR vs the oracle.
+PLANS = ["f32", "tc"]
+TIE = {"f32": 1e-5, "tc": 5e-5}
+Y_TOL = {"f32": 2e-5, "tc": 4e-3}
+Z_TOL = {"f32": 1e-4, "tc": 1e-3}
+PSNR_MIN = {"f32": 80.0, "tc": 40.0}
+ENC_TOL = {"f32": 2e-5, "tc": 3e-4}
+DEC_TOL = {"f32": 1e-5, "tc": 4e-3}
+PRED_TOL = {"f32": 5e-5, "tc": 2e-4}
 
 
 @pytest.fixture(scope="module")
@@ -25,7 +36,7 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def gpu_model(ref, case, precision="f32"):
+def gpu_model(ref, case, precision="tc"):
     net = pkg.build_proposed(case["books"], case["K"])
     net.load_state_dict(ref.state_dict())
     for m in (net, net.A_ENC, net.T_ENC, net.T_DEC, net.A_QUANT, net.predict, net.vq):
@@ -33,12 +44,12 @@ def gpu_model(ref, case, precision="f32"):
     return net
 
 
-def first_mismatch_is_near_tie(idx, gold, margin):
+def first_mismatch_is_near_tie(idx, gold, margin, tie):
     bad = idx != gold
     if not bad.any():
         return True, 0
     first = (bad.int().cumsum(dim=1) == 1) & bad
-    return bool((margin[first] < TIE).all()), int(bad.sum())
+    return bool((margin[first] < tie).all()), int(bad.sum())
 
 
 def psnr(y, ref):
@@ -47,12 +58,13 @@ def psnr(y, ref):
     return 10 * np.log10(peak * peak / max(mse, 1e-30))
 
 
+@pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("name", list(cases.CODEC_CASES))
-def test_codec_against_golden(name, dev, golden_dir, oracle_models):
+def test_codec_against_golden(name, plan, dev, golden_dir, oracle_models):
     case = cases.CODEC_CASES[name]
     g = np.load(os.path.join(golden_dir, f"codec_{name}.npz"))
     ref = oracle_models(name)
-    net = gpu_model(ref, case)
+    net = gpu_model(ref, case, plan)
     a, t = cases.codec_inputs(case)
     y = net.forward_eval(a.to(dev), t.to(dev), case.get("books_use")).cpu()
     idx = net.last_indices.cpu().long()
@@ -66,30 +78,33 @@ def test_codec_against_golden(name, dev, golden_dir, oracle_models):
     n_bad = int((idx != gold_idx).sum())
     if n_bad == 0 and n_code_bad == 0:
         err = float((y - torch.from_numpy(g["y"])).abs().max())
-        assert err < Y_TOL_F32, err
+        assert err < Y_TOL[plan], err
+        assert psnr(y, torch.from_numpy(g["y"])) > PSNR_MIN[plan]
         z = net.encode_latents(a.to(dev), t.to(dev), case.get("books_use")).cpu()
-        assert float((z - torch.from_numpy(g["z_run"])).abs().max()) < 1e-4
+        assert float((z - torch.from_numpy(g["z_run"])).abs().max()) < Z_TOL[plan]
     else:   # near-tie flips: rebuild the margins with the oracle and check each first flip is a near-tie
         tr = {}
         ref.forward_eval(a, t, case.get("books_use"), trace=tr)
-        ok, n = first_mismatch_is_near_tie(idx, tr["idx"], tr["margin"])
+        ok, n = first_mismatch_is_near_tie(idx, tr["idx"], tr["margin"], TIE[plan])
         assert ok or n_code_bad > 0, f"{n} index mismatches that are not near-ties"
+        assert n <= idx.numel() // 50, f"{n} of {idx.numel()} indices differ"
         assert psnr(y, torch.from_numpy(g["y"])) > 30.0
 
 
-def test_stages_teacher_forced(dev, oracle_models):
+@pytest.mark.parametrize("plan", PLANS)
+def test_stages_teacher_forced(plan, dev, oracle_models):
     """Every module of the boundary on its own, fed the oracle's intermediate tensors."""
     name = "cal_b4k256_use3_short"
     case = cases.CODEC_CASES[name]
     ref = oracle_models(name)
-    net = gpu_model(ref, case)
+    net = gpu_model(ref, case, plan)
     a, t = cases.codec_inputs(case)
     tr = {}
     y_ref = ref.forward_eval(a, t, case["books_use"], trace=tr)
     za = net.A_ENC(a.to(dev)).cpu()
-    assert float((za - tr["za"]).abs().max()) < 2e-5          # |za| ~ 0.1..1
+    assert float((za - tr["za"]).abs().max()) < ENC_TOL[plan]          # |za| ~ 0.1..1
     zt = net.T_ENC(t.to(dev)).cpu()
-    assert float((zt - tr["zt"]).abs().max()) < 2e-5
+    assert float((zt - tr["zt"]).abs().max()) < ENC_TOL[plan]
     qa, codes, *_ = net.A_QUANT(tr["za"].to(dev))
     bad = codes.cpu() != tr["a_codes"]
     assert int(bad.sum()) <= bad.numel() // 1000
@@ -100,13 +115,13 @@ def test_stages_teacher_forced(dev, oracle_models):
     assert tuple(codes8.shape) == tuple(q_ref8[1].shape)
     assert int((codes8.cpu() != q_ref8[1]).sum()) <= 2
     y = net.T_DEC(tr["z_run"].to(dev)).cpu()
-    assert float((y - y_ref).abs().max()) < 1e-5
+    assert float((y - y_ref).abs().max()) < DEC_TOL[plan]
     zp, zk = cases.predictor_inputs()
     out = net.predict(zp.to(dev), zk.to(dev)).cpu()
-    assert float((out - ref.predict(zp, zk)).abs().max()) < 5e-5
+    assert float((out - ref.predict(zp, zk).detach()).abs().max()) < PRED_TOL[plan]
     q_ref = ref.vq(tr["rD"], case["books_use"])
     q, i = net.vq(tr["rD"].to(dev), case["books_use"], return_indices=True)
-    ok, n = first_mismatch_is_near_tie(i.cpu(), ref.vq.last_indices, ref.vq.last_margins)
+    ok, n = first_mismatch_is_near_tie(i.cpu(), ref.vq.last_indices, ref.vq.last_margins, TIE[plan])
     assert ok
     if n == 0:
         assert torch.equal(q.cpu(), q_ref), "residual VQ output must be bit-exact when indices agree"
@@ -116,10 +131,10 @@ def test_nearest_code_golden(dev, golden_dir):
     g = np.load(os.path.join(golden_dir, "nearest.npz"))
     for name, (n, d, k) in cases.SEARCH_CASES.items():
         x, emb = cases.search_inputs(n, d, k)
-        for prec in PRECISIONS:
+        for prec in ["f32"]:
             idx = pkg.nearest_code(x.to(dev), emb.to(dev), precision=prec).cpu().numpy()
             bad = idx != g[f"{name}_idx"]
-            assert (g[f"{name}_margin"][bad] < TIE).all(), (name, prec, int(bad.sum()))
+            assert (g[f"{name}_margin"][bad] < TIE["f32"]).all(), (name, prec, int(bad.sum()))
         assert idx.min() >= 0 and idx.max() < k
 
 
@@ -137,12 +152,13 @@ def test_nearest_code_edges(dev):
     assert int(one.abs().sum()) == 0
 
 
-def test_batch_invariance_and_ragged_micro_batches(dev, oracle_models):
+@pytest.mark.parametrize("plan", PLANS)
+def test_batch_invariance_and_ragged_micro_batches(plan, dev, oracle_models):
     """Size-independent properties at a batch the oracle would not finish quickly: a frame's result
     does not depend on its neighbours, on the micro-batch split, or on the run."""
     name = "cal_b8k512"
     case = cases.CODEC_CASES[name]
-    net = gpu_model(oracle_models(name), case)
+    net = gpu_model(oracle_models(name), case, plan)
     big = dict(case, B=21)
     a, t = cases.codec_inputs(big)
     a, t = a.to(dev), t.to(dev)
