@@ -148,7 +148,13 @@ int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv, b2c_ref o
 int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N, int row_mode,
                  int B, int Tl, int chunk);
 /* ResidualVQEMA._nearest_l2 (:417-419) with caller tensors: x [N, D], emb [K, D] -> idx int32 [N].
- * scratch: K floats (receives 0.5*|e_k|^2). */
+ * scratch: b2c_nearest_scratch_bytes(N, D, K, precision) bytes.
+ *   B2C_PREC_F32: FFMA scores, 32 rows per CTA.  B2C_PREC_BF16X3 / BF16: tcgen05 score GEMM (bf16 hi/lo split,
+ *   3 MMAs, fp32 accumulate in TMEM) with the arg-max in the epilogue -- the [N, K] score matrix never exists
+ *   in memory -- then the candidates within the contraction's error bound of the maximum are re-scored with
+ *   the FP32 kernel's arithmetic, so both precisions return the same indices. */
+size_t b2c_nearest_scratch_bytes(int N, int D, int K, int precision);
+int b2c_nearest_tc_eligible(int N, int D, int K);
 int b2c_prog_nearest(b2c_prog* p, b2c_ref x, b2c_ref emb, b2c_ref scratch, b2c_ref idx, int N, int D, int K,
                      int precision);
 /* dac ResidualVectorQuantize.forward (eval), z [B*Tl, c] -> zq [B*Tl, c], codes int32 [B, n_q, Tl]. */

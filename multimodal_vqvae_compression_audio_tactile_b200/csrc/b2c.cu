@@ -497,11 +497,24 @@ extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x
   return B2C_OK;
 }
 
+extern "C" size_t b2c_nearest_scratch_bytes(int N, int D, int K, int precision) {
+  if (N <= 0 || D <= 0 || K <= 0) return 0;
+  if (precision == B2C_PREC_F32) return (size_t)K * sizeof(float);
+  return tc_nearest_scratch_bytes(N, D, K);
+}
+extern "C" int b2c_nearest_tc_eligible(int N, int D, int K) {
+  TcNearestDims d;
+  return tc_nearest_dims(N, D, K, &d) ? 1 : 0;
+}
+
 extern "C" int b2c_prog_nearest(b2c_prog* p, b2c_ref x, b2c_ref emb, b2c_ref scratch, b2c_ref idx, int N, int D,
                                 int K, int precision) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_nearest: NULL program");
   if (N <= 0 || D <= 0 || K <= 0) return fail(B2C_ERR_ARG, "b2c_prog_nearest: empty input (N=%d D=%d K=%d)", N, D, K);
   if (D > 256) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_nearest: D=%d > 256", D);
+  if (precision != B2C_PREC_F32 && !b2c_nearest_tc_eligible(N, D, K))
+    return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_nearest: N=%d D=%d K=%d is not eligible for the tcgen05 search "
+                "(D must be a multiple of 8); use B2C_PREC_F32", N, D, K);
   Op op;
   op.type = OP_NEAREST;
   blank_refs(op);
@@ -716,12 +729,14 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           r.idx = R.get<int>(op.r[3]);
           r.qsum = nullptr;
           if (R.bad || !scratch || !r.books) return fail(B2C_ERR_WORKSPACE, "op %zu (nearest): unresolved buffer", oi);
-          half_sqnorm_f32<<<(r.K + 127) / 128, 128, 0, st>>>(r.books, scratch, r.K, r.D);
+          if (op.precision == B2C_PREC_F32) half_sqnorm_f32<<<(r.K + 127) / 128, 128, 0, st>>>(r.books, scratch, r.K, r.D);
           r.half_n = scratch;
           if (op.precision != B2C_PREC_F32) {
-            int rc = tc_nearest_launch(r, op.precision, ctx->sm_count, st);
+            if (R.bad || !r.x || !r.idx) return fail(B2C_ERR_WORKSPACE, "op %zu (nearest): unresolved buffer", oi);
+            int rc = tc_nearest_launch(r.x, r.books, scratch, r.idx, r.N, r.D, r.K, ctx->sm_count, st);
             if (rc == 0) break;
-            if (rc < 0) return fail(B2C_ERR_CUDA, "op %zu (nearest, tcgen05): launch failed (%d)", oi, rc);
+            return fail(rc < 0 ? B2C_ERR_CUDA : B2C_ERR_UNSUPPORTED,
+                        "op %zu (nearest, tcgen05): %s (%d)", oi, rc < 0 ? "launch failed" : "shape not eligible", rc);
           }
         }
         if (R.bad || !r.x || (!r.idx && r.books_use > 0)) return fail(B2C_ERR_WORKSPACE, "op %zu (rvq): unresolved buffer", oi);

@@ -128,6 +128,32 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (low word, shared constant high word): the issue loop then only does 32-bit adds
+__device__ __forceinline__ void umma_bf16_w32(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+      : "memory");
+}
+// KS K-steps (16 elements = 32 bytes = 2 descriptor units each) of one operand pair, fully unrolled
+template <int X3, int KS>
+__device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_plane, uint32_t b_plane,
+                                            uint32_t desc_hi, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    umma_bf16_w32(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, k == 0 ? acc_first : 1u);
+    if (X3) {
+      umma_bf16_w32(d_tmem, a_lo + 2 * k, b_lo + b_plane + 2 * k, desc_hi, idesc, 1u);
+      umma_bf16_w32(d_tmem, a_lo + a_plane + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+    }
+  }
+}
 __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -178,6 +204,11 @@ struct TcConvParams {
   int BN, BK, n_kblk, stages, tiles_j, n_ntiles, total_tiles;
   int tmem_cols, acc_stride;
   uint32_t a_bytes, b_bytes, sbo, layout_type;
+  // nearest-code search epilogue (EPI = 1): scores = acc - half_norm[code]; per (row, code tile) the best
+  // code, its score and the runner-up score go to cand[row * n_ntiles + nt] = {best, idx, second, -}
+  const float* half_norm;
+  float4* cand;
+  int n_rows, n_codes;
   // slab kernel (conv_tc2_kernel): MT m-tiles per work item share one activation slab and every weight tile
   int MT, groups_j, slab_rows, box_rows, n_aloads, SA, SB;
   uint32_t row_bytes, a_plane_bytes;
@@ -278,7 +309,57 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
   }
 }
 
-template <int X3>
+// Nearest-code epilogue of one 128-row x BN-code score tile (16 warps: 4 TMEM lane quadrants x 4 column
+// quarters; thread = row).  Each thread scans its quarter of the codes keeping (best, first index of best,
+// runner-up); the four quarters of a row are merged through shared memory.  The [N, K] score matrix never
+// leaves TMEM.
+__device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float* stg, uint32_t tcount, uint32_t t_acc,
+                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
+  const int quad = warp & 3;
+  const int part = (warp - 2) >> 2;
+  const int et = threadIdx.x - 64;
+  const int row = quad * 32 + lane;
+  const int cpp = p.BN >> 2;                       // codes per quarter (multiple of 16)
+  const int col0 = nt * p.BN + part * cpp;
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + part * cpp;
+  float best = -INFINITY, second = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int c = 0; c < cpp; c += 16) {
+    float v[16];
+    tmem_ld16(t_src + c, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = col0 + c + i;
+      if (col < p.n_codes) {
+        const float sc = __fsub_rn(v[i], __ldg(p.half_norm + col));
+        if (sc > best) { second = best; best = sc; bidx = col; }
+        else if (sc > second) second = sc;
+      }
+    }
+  }
+  float4* sm = reinterpret_cast<float4*>(stg) + (tcount & 1u) * (4 * TC_BM);
+  sm[part * TC_BM + row] = make_float4(best, __int_as_float(bidx), second, 0.f);
+  tc_fence_before();
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  if (et == 0) mbar_arrive(tempty_bar);
+  if (part == 0) {
+    const int grow = jt * TC_BM + row;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float4 o = sm[q * TC_BM + row];
+      const int oi = __float_as_int(o.y);
+      if (o.x > best || (o.x == best && oi < bidx)) {
+        second = fmaxf(best, o.z);
+        best = o.x; bidx = oi;
+      } else {
+        second = fmaxf(second, o.x);
+      }
+    }
+    if (grow < p.n_rows) p.cand[(size_t)grow * p.n_ntiles + nt] = make_float4(best, __int_as_float(bidx), second, 0.f);
+  }
+}
+
+template <int X3, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -356,13 +437,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp runs the (warp-uniform) loop so that descriptors and addresses live in uniform
-    // registers; only lane 0 issues tcgen05.mma / tcgen05.commit.
+    // The whole warp runs the (warp-uniform) loop; elect.sync inside the MMA / commit wrappers picks the lane
+    // that issues.  K-steps are unrolled at compile time and descriptors advance by 32-bit adds, so the issue
+    // loop costs a few instructions per tcgen05.mma (it was the bottleneck of the narrow layers).
     {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
       const int ksteps = p.BK / 16;
-      const uint64_t dbase = umma_desc_base(p.sbo, p.layout_type);
-      const uint32_t a_lo_off = p.a_bytes >> 4, b_lo_off = p.b_bytes >> 4;
+      const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
+      const uint32_t a_plane = p.a_bytes >> 4, b_plane = p.b_bytes >> 4;
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
@@ -374,16 +456,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(smem_u32(&bar_full[s]), par, 3);
           tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes;
-          const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
-          uint64_t da = dbase | (uint64_t)((sa & 0x3FFFFu) >> 4);
-          uint64_t db = dbase | (uint64_t)((sb & 0x3FFFFu) >> 4);
-          for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
-            umma_bf16_w(d_tmem, da, db, idesc, (ki | k) != 0);
-            if (X3) {
-              umma_bf16_w(d_tmem, da, db + b_lo_off, idesc, 1);
-              umma_bf16_w(d_tmem, da + a_lo_off, db, idesc, 1);
-            }
-          }
+          const uint32_t a_lo = (sa & 0x3FFFFu) >> 4;
+          const uint32_t b_lo = ((sa + p.a_bytes * (X3 ? 2u : 1u)) & 0x3FFFFu) >> 4;
+          const uint32_t first = ki != 0;
+          if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+          else if (ksteps == 2) umma_ksteps<X3, 2>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+          else umma_ksteps<X3, 1>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
           umma_commit_w(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
         }
         umma_commit_w(smem_u32(&bar_tfull[acc]));   // accumulator complete -> epilogue
@@ -407,8 +485,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
       mbar_wait(smem_u32(&bar_tfull[acc]), apar, 4);
       tc_fence_after();
-      tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]), warp,
-                       lane);
+      if (EPI == 0)
+        tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
+                         warp, lane);
+      else
+        tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, jt, nt, smem_u32(&bar_tempty[acc]), warp, lane);
     }
   }
   tc_fence_before();
@@ -526,12 +607,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, lane 0 issues) =====================
+    // ===================== MMA issuer (warp-uniform loop, elect.sync issues) =====================
     {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
       const int ksteps = p.BK / 16;
-      const uint64_t dbase = umma_desc_base(p.sbo, p.layout_type);
-      const uint32_t a_lo_off = p.a_plane_bytes >> 4, b_lo_off = p.b_bytes >> 4;
+      const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
+      const uint32_t a_plane = p.a_plane_bytes >> 4, b_plane = p.b_bytes >> 4;
       const uint32_t tap_step = ((uint32_t)p.dil * p.row_bytes) >> 4;        // descriptor units per tap
       const uint32_t mtile_step = ((uint32_t)TC_BM * p.row_bytes) >> 4;      // descriptor units per m-tile
       uint32_t ia = 0, ib = 0, tcount = 0;
@@ -546,23 +627,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           const uint32_t sa = ia % p.SA, apr = (ia / p.SA) & 1u;
           mbar_wait(smem_u32(&bar_afull[sa]), apr, 4);
           tc_fence_after();
-          const uint64_t da_slab = dbase | (uint64_t)(((smem0 + sa * a_slot) & 0x3FFFFu) >> 4);
-          for (int tap = 0; tap < p.KT; ++tap, ++ib) {
+          uint32_t a_tap = ((smem0 + sa * a_slot) & 0x3FFFFu) >> 4;
+          for (int tap = 0; tap < p.KT; ++tap, ++ib, a_tap += tap_step) {
             const uint32_t sb = ib % p.SB, bpr = (ib / p.SB) & 1u;
             mbar_wait(smem_u32(&bar_bfull[sb]), bpr, 5);
             tc_fence_after();
-            const uint64_t db0 = dbase | (uint64_t)(((smemB + sb * b_slot) & 0x3FFFFu) >> 4);
-            uint64_t da_m = da_slab + (uint64_t)(tap * tap_step);
-            for (int m = 0; m < n_m; ++m, da_m += mtile_step) {
-              const uint32_t d_tmem = d_set + m * p.acc_stride;
-              uint64_t da = da_m, db = db0;
-              for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
-                umma_bf16_w(d_tmem, da, db, idesc, (cb | tap | k) != 0);
-                if (X3) {
-                  umma_bf16_w(d_tmem, da, db + b_lo_off, idesc, 1);
-                  umma_bf16_w(d_tmem, da + a_lo_off, db, idesc, 1);
-                }
-              }
+            const uint32_t b_lo = ((smemB + sb * b_slot) & 0x3FFFFu) >> 4;
+            const uint32_t first = (cb | tap) != 0;
+            uint32_t a_lo = a_tap, d_tmem = d_set;
+            for (int m = 0; m < n_m; ++m, a_lo += mtile_step, d_tmem += p.acc_stride) {
+              if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+              else if (ksteps == 2) umma_ksteps<X3, 2>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+              else umma_ksteps<X3, 1>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
             }
             umma_commit_w(smem_u32(&bar_bempty[sb]));
           }
@@ -913,17 +989,210 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
     return 0;
   }
   if (plan.x3) {
-    e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    e = cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_tc_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    conv_tc_kernel<1, 0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
   } else {
-    e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    e = cudaFuncSetAttribute(conv_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_tc_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    conv_tc_kernel<0, 0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
   }
   return 0;
 }
 
-inline int tc_nearest_launch(const RvqArgs&, int, int, cudaStream_t) { return 1; }
+
+// ---------------------------------------------------------------------------------------------
+// Nearest-code search on tensor cores: prep (bf16 hi/lo planes, norms) -> score GEMM with the argmax
+// epilogue above -> exact fp32 finalisation of the candidates.
+// ---------------------------------------------------------------------------------------------
+// rows [n, d] fp32 -> bf16 planes; optional 0.5*|row|^2 (fmaf chain, the FP32 kernel's arithmetic), |row|^2
+// and the running maximum of |row|^2 (as ordered int bits; the values are non-negative).
+__global__ void nearest_prep(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             float* __restrict__ half_norm, float* __restrict__ norm2, int* __restrict__ max_norm2_bits,
+                             int n, int d) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float s = 0.f;
+  for (int i = 0; i < d; ++i) {
+    const float v = __ldg(x + (size_t)r * d + i);
+    s = fmaf(v, v, s);
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[(size_t)r * d + i] = h;
+    lo[(size_t)r * d + i] = l;
+  }
+  if (half_norm) half_norm[r] = 0.5f * s;
+  if (norm2) norm2[r] = s;
+  if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_int(s));
+}
+
+__device__ __forceinline__ float exact_score(const float* __restrict__ xr, const float* __restrict__ e,
+                                             const float* __restrict__ hn, int k, int D) {
+  const float* ek = e + (size_t)k * D;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) acc = fmaf(__ldg(xr + d), __ldg(ek + d), acc);
+  return __fsub_rn(acc, __ldg(hn + k));
+}
+
+// One warp per row.  A code can only be the fp32 arg-max if its tensor-core score is within tol = 2 * (error
+// bound of the bf16x3 contraction) of the tensor-core maximum; those few candidates are re-scored with the FP32
+// kernel's exact arithmetic (sequential fmaf over d, minus 0.5|e|^2) and the first maximum wins -- so the result
+// equals the FP32 kernel's bit for bit.  A tile whose top two tensor-core scores are closer than tol is
+// re-scanned completely.
+__global__ void __launch_bounds__(256) nearest_finalize(const float4* __restrict__ cand, int n_tiles, int BN,
+                                                        const float* __restrict__ x, const float* __restrict__ emb,
+                                                        const float* __restrict__ hn, const float* __restrict__ xnorm2,
+                                                        const int* __restrict__ emax2_bits, int N, int D, int K,
+                                                        int* __restrict__ idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= N) return;
+  const float4* cr = cand + (size_t)row * n_tiles;
+  const float* xr = x + (size_t)row * D;
+  float M = -INFINITY;
+  for (int t = lane; t < n_tiles; t += 32) M = fmaxf(M, cr[t].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  const float tol = 1.220703125e-4f * sqrtf(__ldg(xnorm2 + row) * __int_as_float(__ldg(emax2_bits))) + 1e-30f;
+  float ebest = -INFINITY;
+  int eidx = 0x7fffffff;
+  for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+    const int t = t0 + lane;
+    bool rescan = false;
+    if (t < n_tiles) {
+      const float4 c = cr[t];
+      if (c.x >= M - tol) {
+        if (c.x - c.z >= tol) {
+          const int k = __float_as_int(c.y);
+          const float sc = exact_score(xr, emb, hn, k, D);
+          if (sc > ebest || (sc == ebest && k < eidx)) { ebest = sc; eidx = k; }
+        } else {
+          rescan = true;
+        }
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, rescan);
+    while (m) {
+      const int tt = t0 + __ffs(m) - 1;
+      m &= m - 1;
+      const int k1 = min(K, (tt + 1) * BN);
+      for (int k = tt * BN + lane; k < k1; k += 32) {
+        const float sc = exact_score(xr, emb, hn, k, D);
+        if (sc > ebest || (sc == ebest && k < eidx)) { ebest = sc; eidx = k; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, ebest, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, eidx, o);
+    if (os > ebest || (os == ebest && oi < eidx)) { ebest = os; eidx = oi; }
+  }
+  if (lane == 0) idx[row] = eidx < K ? eidx : 0;
+}
+
+inline CUtensorMapSwizzle tc_swizzle_of(int bk) {
+  return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct TcNearestDims {
+  int BN, BK, n_kblk, stages, tiles_j, n_ntiles;
+  size_t smem;
+};
+inline bool tc_nearest_dims(int N, int D, int K, TcNearestDims* o) {
+  if (D % 8 != 0 || D < 8 || D > 256 || K < 1 || N < 1) return false;
+  o->BK = D % 64 == 0 ? 64 : (D % 32 == 0 ? 32 : 16);
+  o->n_kblk = (D + o->BK - 1) / o->BK;
+  o->BN = K >= 256 ? 256 : (K + 63) / 64 * 64;
+  uint32_t stage = 0;
+  int stages = 0;
+  for (;; o->BN >>= 1) {   // narrower code tiles until three pipeline stages fit (D = 256: BN = 128)
+    stage = (uint32_t)(TC_BM + o->BN) * o->BK * 2 * 2;
+    stages = (232448 - 2048 - TC_STG_BYTES - 1024) / (int)stage;
+    if (stages >= 3 || o->BN <= 64) break;
+  }
+  o->tiles_j = (N + TC_BM - 1) / TC_BM;
+  o->n_ntiles = (K + o->BN - 1) / o->BN;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) return false;
+  o->stages = stages;
+  o->smem = (size_t)stages * stage + TC_STG_BYTES + 1024;
+  return (long)o->tiles_j * o->n_ntiles < 0x7fffffffL;
+}
+// scratch layout (bytes, 256-aligned pieces): x planes | emb planes | half_norm[K] | xnorm2[N] | emax2 | cand
+inline size_t tc_nearest_scratch_bytes(int N, int D, int K) {
+  TcNearestDims d;
+  if (!tc_nearest_dims(N, D, K, &d)) return (size_t)K * 4;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  return al((size_t)N * D * 4) + al((size_t)K * D * 4) + al((size_t)K * 4) + al((size_t)N * 4) + 256 +
+         al((size_t)N * d.n_ntiles * 16);
+}
+
+// returns 0 = launched; 1 = shape not eligible (caller uses the FP32 kernel); < 0 = error
+inline int tc_nearest_launch(const float* x, const float* emb, void* scratch, int* idx, int N, int D, int K,
+                             int sm_count, cudaStream_t st) {
+  TcNearestDims d;
+  if (!tc_nearest_dims(N, D, K, &d)) return 1;
+  if (!tc_encode_fn()) return -10;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  char* s = reinterpret_cast<char*>(scratch);
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(s);
+  __nv_bfloat16* xl = xh + (size_t)N * D;
+  s += al((size_t)N * D * 4);
+  __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(s);
+  __nv_bfloat16* el = eh + (size_t)K * D;
+  s += al((size_t)K * D * 4);
+  float* hn = reinterpret_cast<float*>(s);
+  s += al((size_t)K * 4);
+  float* xn2 = reinterpret_cast<float*>(s);
+  s += al((size_t)N * 4);
+  int* emax = reinterpret_cast<int*>(s);
+  s += 256;
+  float4* cand = reinterpret_cast<float4*>(s);
+  if (cudaMemsetAsync(emax, 0, 4, st) != cudaSuccess) return -3;
+  nearest_prep<<<(N + 127) / 128, 128, 0, st>>>(x, xh, xl, nullptr, xn2, nullptr, N, D);
+  nearest_prep<<<(K + 127) / 128, 128, 0, st>>>(emb, eh, el, hn, nullptr, emax, K, D);
+
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = 1; p.Lin = N; p.Cin = D; p.Cout = K; p.KT = 1; p.in_step = 1; p.dil = 1; p.n_phase = 1;
+  p.Lj = N; p.out_step = 1; p.Lout = N;
+  p.BN = d.BN; p.BK = d.BK; p.n_kblk = d.n_kblk; p.stages = d.stages; p.tiles_j = d.tiles_j; p.n_ntiles = d.n_ntiles;
+  p.total_tiles = d.tiles_j * d.n_ntiles;
+  p.acc_stride = d.BN <= 64 ? 64 : (d.BN <= 128 ? 128 : 256);
+  p.tmem_cols = 2 * p.acc_stride;
+  p.a_bytes = TC_BM * d.BK * 2; p.b_bytes = d.BN * d.BK * 2;
+  p.sbo = 8 * d.BK * 2;
+  p.layout_type = d.BK == 64 ? 2u : (d.BK == 32 ? 4u : 6u);
+  p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  cuuint32_t es[3] = {1, 1, 1};
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, 1};
+    cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+    cuuint32_t box[3] = {(cuuint32_t)d.BK, TC_BM, 1};
+    for (int pl = 0; pl < 2; ++pl)
+      if (tc_encode_fn()(pl ? &mA_lo : &mA_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pl ? (void*)xl : (void*)xh, dims, str,
+                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_of(d.BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -11;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)K};
+    cuuint64_t str[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d.BK, (cuuint32_t)d.BN};
+    for (int pl = 0; pl < 2; ++pl)
+      if (tc_encode_fn()(pl ? &mB_lo : &mB_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl ? (void*)el : (void*)eh, dims, str,
+                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_of(d.BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -12;
+  }
+  if (cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem) != cudaSuccess)
+    return -2;
+  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  conv_tc_kernel<1, 1><<<grid, TC_THREADS, d.smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  nearest_finalize<<<(N + 7) / 8, 256, 0, st>>>(cand, d.n_ntiles, d.BN, x, emb, hn, xn2, emax, N, D, K, idx);
+  return 0;
+}
 
 }  // namespace b2c

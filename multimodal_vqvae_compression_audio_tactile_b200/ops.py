@@ -18,7 +18,7 @@ def _engine(device: torch.device) -> Engine:
 
 
 @torch.no_grad()
-def nearest_code(x: torch.Tensor, emb: torch.Tensor, precision: str = "f32") -> torch.Tensor:
+def nearest_code(x: torch.Tensor, emb: torch.Tensor, precision: str = "tc") -> torch.Tensor:
     """ResidualVQEMA._nearest_l2 (Evaluation/dac_vcpwq_proposed6_latency.py:417-419):
     argmax_k (x @ emb.T - 0.5 * |emb_k|^2), first maximum wins.  x [N, D], emb [K, D] CUDA tensors
     -> int64 [N].  The [N, K] score matrix is never written to memory."""
@@ -33,12 +33,14 @@ def nearest_code(x: torch.Tensor, emb: torch.Tensor, precision: str = "f32") -> 
     if n == 0:
         return torch.empty(0, dtype=torch.int64, device=x.device)
     eng = _engine(x.device)
-    prec = L.PRECISIONS[precision]
+    prec = L.PRECISIONS[{"tc": "bf16x3"}.get(precision, precision)]
+    if prec != L.PREC_F32 and not eng.lib.b2c_nearest_tc_eligible(n, d, k):
+        prec = L.PREC_F32      # D not a multiple of 8: the FP32 CUDA kernel (same indices by construction)
     key = ("nearest", n, d, k, prec)
     prog = eng.programs.get(key)
     if prog is None:
         em = Emitter(eng)
-        scratch = em.new(k)
+        scratch = em.arena.alloc(int(eng.lib.b2c_nearest_scratch_bytes(n, d, k, prec)))
         ii = em.new(n)
         em.nearest(em.ext(1), em.ext(2), scratch, ii, n, d, k, prec)
         em.widen(ii, em.ext(3), n)

@@ -131,10 +131,14 @@ def test_nearest_code_golden(dev, golden_dir):
     g = np.load(os.path.join(golden_dir, "nearest.npz"))
     for name, (n, d, k) in cases.SEARCH_CASES.items():
         x, emb = cases.search_inputs(n, d, k)
-        for prec in ["f32"]:
+        got = {}
+        for prec in ["f32", "tc"]:
             idx = pkg.nearest_code(x.to(dev), emb.to(dev), precision=prec).cpu().numpy()
             bad = idx != g[f"{name}_idx"]
             assert (g[f"{name}_margin"][bad] < TIE["f32"]).all(), (name, prec, int(bad.sum()))
+            got[prec] = idx
+        # the tcgen05 search re-scores its candidates with the FP32 kernel's arithmetic: same indices, bit for bit
+        assert (got["f32"] == got["tc"]).all(), name
         assert idx.min() >= 0 and idx.max() < k
 
 
@@ -142,9 +146,14 @@ def test_nearest_code_edges(dev):
     x, emb = cases.search_inputs(5, 96, 128)
     # duplicated codeword: the FIRST maximum must win (torch.argmax semantics)
     emb2 = torch.cat([emb, emb[:3]], 0)
-    i1 = pkg.nearest_code(x.to(dev), emb.to(dev)).cpu()
-    i2 = pkg.nearest_code(x.to(dev), emb2.to(dev)).cpu()
-    assert torch.equal(i1, i2)
+    for prec in ("f32", "tc"):
+        i1 = pkg.nearest_code(x.to(dev), emb.to(dev), precision=prec).cpu()
+        i2 = pkg.nearest_code(x.to(dev), emb2.to(dev), precision=prec).cpu()
+        assert torch.equal(i1, i2), prec
+    # D not a multiple of 8 is outside the tcgen05 search: the FP32 kernel serves it, same call
+    x7, e7 = cases.search_inputs(9, 7, 40)
+    ref7 = (x7 @ e7.t() - 0.5 * (e7 * e7).sum(1)).argmax(1)
+    assert torch.equal(pkg.nearest_code(x7.to(dev), e7.to(dev)).cpu(), ref7)
     assert pkg.nearest_code(torch.empty(0, 96, device=dev), emb.to(dev)).numel() == 0
     with pytest.raises(ValueError):
         pkg.nearest_code(x.to(dev), emb[:, :5].to(dev))
