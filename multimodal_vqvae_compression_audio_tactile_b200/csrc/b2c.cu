@@ -216,16 +216,18 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
   if (d != 8) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: codebook_dim must be 8 (got %d)", d);
   if (c % 32 != 0 || c > 1024) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: latent dim %d (need multiple of 32, <= 1024)", c);
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const long stride = 8L * c + 8 + 8L * K + K + 8L * K + 8L * c + c;
+  if (K % 4 != 0) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: codebook size %d must be a multiple of 4", K);
+  // per stage: Win[8][c] | bin[8] | cbnT[8][K] | c2[K] | WoutT[8][c] | bout[c]  (staged in smem) | cb[K][8]
+  const long stride = 8L * c + 8 + 8L * K + K + 8L * c + c + 8L * K;
   std::vector<float> blob((size_t)stride * n_q, 0.f), tmp;
   for (int s = 0; s < n_q; ++s) {
     float* Win = &blob[(size_t)s * stride];
     float* bin = Win + 8L * c;
-    float* cbn = bin + 8;
-    float* c2 = cbn + 8L * K;
-    float* cb = c2 + K;
-    float* Wout = cb + 8L * K;
-    float* bout = Wout + 8L * c;
+    float* cbnT = bin + 8;
+    float* c2 = cbnT + 8L * K;
+    float* WoutT = c2 + K;
+    float* bout = WoutT + 8L * c;
+    float* cb = bout + c;
     fold_weight_norm(in_v[s], in_g ? in_g[s] : nullptr, 8, c, tmp);  // [d][c]
     memcpy(Win, tmp.data(), 8L * c * sizeof(float));
     if (in_b && in_b[s]) memcpy(bin, in_b[s], 8 * sizeof(float));
@@ -237,14 +239,15 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
       float cc = 0.f;
       for (int j = 0; j < 8; ++j) {
         float v = e[j] / den;
-        cbn[8L * k + j] = v;
+        cbnT[(long)j * K + k] = v;
         cb[8L * k + j] = e[j];
         cc += v * v;
       }
       c2[k] = cc;
     }
     fold_weight_norm(out_v[s], out_g ? out_g[s] : nullptr, c, 8, tmp);  // [c][d]
-    memcpy(Wout, tmp.data(), 8L * c * sizeof(float));
+    for (int ch = 0; ch < c; ++ch)
+      for (int j = 0; j < 8; ++j) WoutT[(long)j * c + ch] = tmp[8L * ch + j];
     if (out_b && out_b[s]) memcpy(bout, out_b[s], c * sizeof(float));
   }
   Weight w;
@@ -651,8 +654,15 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         int B = op.i[0], L = op.i[1];
         dim3 grid((L + 63) / 64, B);
         size_t sm = (64 + 8 + 7 * w.cout) * sizeof(float);
-        stem_k7_f32<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, o_act, alpha, L, w.cout, op.i[2], op.act_fmt,
-                                           (size_t)B * L * w.cout);
+        if (op.act_fmt != B2C_FMT_F32 && op.i[2] == ACT_SNAKE && w.cout % 4 == 0 && o_act) {
+          __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(o_act);
+          stem_k7_planes<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, hi,
+                                                op.act_fmt == B2C_FMT_BF16X2 ? hi + (size_t)B * L * w.cout : nullptr, alpha,
+                                                ctx->w[op.wid2].aux, L, w.cout);
+        } else {
+          stem_k7_f32<<<grid, 256, sm, st>>>(x, w.dev, w.bias, o_raw, o_act, alpha, L, w.cout, op.i[2], op.act_fmt,
+                                             (size_t)B * L * w.cout);
+        }
         break;
       }
       case OP_CONV:
@@ -685,9 +695,27 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         float* y = R.get<float>(op.r[1]);
         if (R.bad || !x || !y) return fail(B2C_ERR_WORKSPACE, "op %zu (head): unresolved buffer", oi);
         int B = op.i[0], L = op.i[1];
-        dim3 grid((L + 63) / 64, B);
-        head_k7_tanh_f32<<<grid, 256, 7 * w.cin * sizeof(float), st>>>(x, w.dev, w.bias, y, L, w.cin, op.x_fmt,
-                                                                       (size_t)B * L * w.cin);
+        const size_t tiled_sm = ((size_t)(128 + 6) * (w.cin + 4) + 7 * w.cin) * sizeof(float);
+        if (op.x_fmt != B2C_FMT_F32 && w.cin % 8 == 0 && tiled_sm <= 100 * 1024) {
+          // tensor-core plans: tiled head (each input element read once); the f32 plan keeps the
+          // one-warp-per-output kernel and its summation order
+          dim3 grid((L + 127) / 128, B);
+          const size_t xn = (size_t)B * L * w.cin;
+          cudaError_t e;
+          if (op.x_fmt == B2C_FMT_BF16X2) {
+            e = cudaFuncSetAttribute(head_k7_tanh_tiled<FMT_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_sm);
+            if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "head smem: %s", cudaGetErrorString(e));
+            head_k7_tanh_tiled<FMT_PLANES><<<grid, 128, tiled_sm, st>>>(x, w.dev, w.bias, y, L, w.cin, xn);
+          } else {
+            e = cudaFuncSetAttribute(head_k7_tanh_tiled<FMT_HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_sm);
+            if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "head smem: %s", cudaGetErrorString(e));
+            head_k7_tanh_tiled<FMT_HI><<<grid, 128, tiled_sm, st>>>(x, w.dev, w.bias, y, L, w.cin, xn);
+          }
+        } else {
+          dim3 grid((L + 63) / 64, B);
+          head_k7_tanh_f32<<<grid, 256, 7 * w.cin * sizeof(float), st>>>(x, w.dev, w.bias, y, L, w.cin, op.x_fmt,
+                                                                         (size_t)B * L * w.cin);
+        }
         break;
       }
       case OP_LN: {
@@ -741,12 +769,15 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         }
         if (R.bad || !r.x || (!r.idx && r.books_use > 0)) return fail(B2C_ERR_WORKSPACE, "op %zu (rvq): unresolved buffer", oi);
         if (r.books_use > 0) {
-          size_t sm = ((size_t)64 * r.D + 64 * (r.D + 1)) * sizeof(float);
-          if (sm > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(rvq_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
-          }
-          rvq_f32<<<(r.N + 31) / 32, 256, sm, st>>>(r);
+          // 32 tokens per CTA when that still gives every SM two CTAs, else 8 (one per warp)
+          const bool wide = (long)r.N >= 64L * ctx->sm_count;
+          const int tok = wide ? 32 : 8;
+          size_t sm = ((size_t)2 * tok * r.D + 64 * (r.D + 1)) * sizeof(float);
+          cudaError_t e = wide ? cudaFuncSetAttribute(rvq_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                               : cudaFuncSetAttribute(rvq_f32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
+          if (wide) rvq_f32<4><<<(r.N + tok - 1) / tok, 256, sm, st>>>(r);
+          else rvq_f32<1><<<(r.N + tok - 1) / tok, 256, sm, st>>>(r);
         } else if (r.qsum) {
           cudaError_t e = cudaMemsetAsync(r.qsum, 0, (size_t)r.N * r.D * sizeof(float), st);
           if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq memset: %s", cudaGetErrorString(e));
@@ -761,14 +792,23 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         d.w = ctx->w[op.wid].dev;
         if (R.bad || !d.z || !d.zq || !d.codes) return fail(B2C_ERR_WORKSPACE, "op %zu (dac rvq): unresolved buffer", oi);
         int blocks = (d.N + 7) / 8;
+        const size_t sm = 2 * (size_t)(17 * d.C + 9 * d.K + 8) * sizeof(float);
+        if (sm > 227 * 1024) return fail(B2C_ERR_UNSUPPORTED, "dac rvq: C=%d K=%d needs %zu bytes of shared memory", d.C, d.K, sm);
+#define B2C_DACRVQ(CPL)                                                                                         \
+  {                                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(dac_rvq_f32<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "dac rvq smem: %s", cudaGetErrorString(e));                 \
+    dac_rvq_f32<CPL><<<blocks, 256, sm, st>>>(d);                                                               \
+  }
         switch (d.C / 32) {
-          case 32: dac_rvq_f32<32><<<blocks, 256, 0, st>>>(d); break;
-          case 16: dac_rvq_f32<16><<<blocks, 256, 0, st>>>(d); break;
-          case 8: dac_rvq_f32<8><<<blocks, 256, 0, st>>>(d); break;
-          case 4: dac_rvq_f32<4><<<blocks, 256, 0, st>>>(d); break;
-          case 2: dac_rvq_f32<2><<<blocks, 256, 0, st>>>(d); break;
+          case 32: B2C_DACRVQ(32) break;
+          case 16: B2C_DACRVQ(16) break;
+          case 8: B2C_DACRVQ(8) break;
+          case 4: B2C_DACRVQ(4) break;
+          case 2: B2C_DACRVQ(2) break;
           default: return fail(B2C_ERR_UNSUPPORTED, "dac rvq: latent dim %d not in {64,128,256,512,1024}", d.C);
         }
+#undef B2C_DACRVQ
         break;
       }
       case OP_SCATTER: {

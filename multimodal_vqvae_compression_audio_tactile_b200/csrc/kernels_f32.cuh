@@ -287,6 +287,125 @@ __global__ void __launch_bounds__(256) stem_k7_f32(const float* __restrict__ x, 
   }
 }
 
+// Same stem for the tensor-core plans: 4 channels per thread, float4 raw stores, bf16x2-packed plane stores,
+// polynomial snake.  Cout % 4 == 0.
+__global__ void __launch_bounds__(256) stem_k7_planes(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out_raw,
+                                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                       const float* __restrict__ alpha, const float* __restrict__ inv_alpha,
+                                                       int L, int Cout) {
+  constexpr int TP = 64;
+  extern __shared__ float sm[];
+  float* xs = sm;             // TP + 6
+  float* ws = sm + TP + 8;    // 7 * Cout
+  const int b = blockIdx.y, l0 = blockIdx.x * TP;
+  for (int i = threadIdx.x; i < TP + 6; i += blockDim.x) {
+    int l = l0 + i - 3;
+    xs[i] = (l >= 0 && l < L) ? __ldg(x + (size_t)b * L + l) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 7 * Cout; i += blockDim.x) ws[i] = __ldg(w + i);
+  __syncthreads();
+  const int ng = Cout >> 2;
+  for (int idx = threadIdx.x; idx < TP * ng; idx += blockDim.x) {
+    const int pp = idx / ng, co = (idx - pp * ng) * 4;
+    const int l = l0 + pp;
+    if (l >= L) break;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const float xv = xs[pp + t];
+      const float4 wv = *reinterpret_cast<const float4*>(ws + t * Cout + co);
+      a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y); a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
+    }
+    if (bias) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co));
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+    }
+    const size_t o = ((size_t)b * L + l) * Cout + co;
+    if (out_raw) *reinterpret_cast<float4*>(out_raw + o) = a;
+    if (out_hi) {
+      const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + co));
+      const float4 ia = __ldg(reinterpret_cast<const float4*>(inv_alpha + co));
+      float4 v;
+      v.x = snake_fast(a.x, al.x, ia.x); v.y = snake_fast(a.y, al.y, ia.y);
+      v.z = snake_fast(a.z, al.z, ia.z); v.w = snake_fast(a.w, al.w, ia.w);
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(out_hi + o) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      if (out_lo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        *reinterpret_cast<uint2*>(out_lo + o) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+  }
+}
+
+// Decoder head, tiled: a CTA stages 128 + 6 rows of the channel-last input (contiguous in memory) in shared
+// memory as fp32 with a padded row (Cin + 4 words: conflict-free float4 reads), thread t computes position t.
+// Cin % 8 == 0.  Reads each input element once from HBM.
+template <int FMT>
+__global__ void __launch_bounds__(128) head_k7_tanh_tiled(const void* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y, int L,
+                                                           int Cin, size_t x_n) {
+  constexpr int TP = 128;
+  extern __shared__ __align__(16) float hsm[];
+  const int ld = Cin + 4;
+  float* xs = hsm;                    // [TP + 6][ld]
+  float* ws = hsm + (TP + 6) * ld;    // [7][Cin]
+  const int b = blockIdx.y, l0 = blockIdx.x * TP;
+  for (int i = threadIdx.x; i < 7 * Cin; i += blockDim.x) ws[i] = __ldg(w + i);
+  const int vec_per_row = Cin >> 3;
+  for (int v = threadIdx.x; v < (TP + 6) * vec_per_row; v += blockDim.x) {
+    const int r = v / vec_per_row, c = (v - r * vec_per_row) * 8;
+    const int l = l0 + r - 3;
+    float f[8];
+    if (l >= 0 && l < L) {
+      const size_t e = ((size_t)b * L + l) * Cin + c;
+      if (FMT == FMT_F32) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e + 4));
+        f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
+      } else {
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(xb + e));
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(hp[q]); f[2 * q] = t2.x; f[2 * q + 1] = t2.y; }
+        if (FMT == FMT_PLANES) {
+          const uint4 lo = __ldg(reinterpret_cast<const uint4*>(xb + x_n + e));
+          const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&lo);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(lp[q]); f[2 * q] += t2.x; f[2 * q + 1] += t2.y; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = 0.f;
+    }
+    *reinterpret_cast<float4*>(xs + r * ld + c) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(xs + r * ld + c + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __syncthreads();
+  const int l = l0 + threadIdx.x;
+  if (l >= L) return;
+  // same summation order as the one-warp-per-output kernel is not required: the head is downstream of the
+  // quantizer; four partial sums keep the FMA chains short
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int r = 0; r < 7; ++r) {
+    const float* xr = xs + (threadIdx.x + r) * ld;
+    const float* wr = ws + r * Cin;
+    for (int c = 0; c < Cin; c += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const float4 wv = *reinterpret_cast<const float4*>(wr + c);
+      a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+  }
+  y[(size_t)b * L + l] = tanhf(__fadd_rn((a0 + a1) + (a2 + a3), bias ? __ldg(bias) : 0.f));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Decoder head: Conv1d(Cin, 1, k=7, p=3) + tanh.  In channel-last layout the 7*Cin window of one
 // output is CONTIGUOUS, so y[l] = tanh(b + <w_flat, x_flat[(l-3)*Cin ...]>): one warp per output,
@@ -472,16 +591,18 @@ struct RvqArgs {
   int idx_flat;         // 1: idx[n] (nearest op)
 };
 
+// TPW tokens per warp (8 * TPW per CTA): 4 for large N, 1 when that would leave most SMs idle.
+template <int TPW>
 __global__ void __launch_bounds__(256) rvq_f32(const RvqArgs p) {
-  constexpr int TPW = 4, CH = 64;
+  constexpr int CH = 64, TOK = 8 * TPW;
   extern __shared__ float sm[];
   const int D = p.D, DP = D + 1;
-  float* xs = sm;                   // [32][D]  residual
-  float* qs = xs + 32 * D;          // [32][D]  q_sum
-  float* es = qs + 32 * D;          // [CH][D+1]
+  float* xs = sm;                   // [TOK][D]  residual
+  float* qs = xs + TOK * D;         // [TOK][D]  q_sum
+  float* es = qs + TOK * D;         // [CH][D+1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < 32 * D; i += 256) {
+  const int n0 = blockIdx.x * TOK;
+  for (int i = threadIdx.x; i < TOK * D; i += 256) {
     int t = i / D;
     int n = n0 + t;
     xs[i] = n < p.N ? __ldg(p.x + (long)n0 * D + i) : 0.f;
@@ -568,7 +689,7 @@ __global__ void __launch_bounds__(256) rvq_f32(const RvqArgs p) {
   }
   __syncthreads();
   if (p.qsum)
-    for (int i = threadIdx.x; i < 32 * D; i += 256)
+    for (int i = threadIdx.x; i < TOK * D; i += 256)
       if (n0 + i / D < p.N) p.qsum[(long)n0 * D + i] = qs[i];
 }
 
@@ -582,9 +703,13 @@ __global__ void half_sqnorm_f32(const float* __restrict__ emb, float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// dac ResidualVectorQuantize (eval): all stages fused, one warp per token, residual and the
-// running z_q in registers (C = 32 * CPL channels, codebook dim 8).
-// Packed stage layout (floats): Win[8][C] | bin[8] | cbn[K][8] | c2[K] | cb[K][8] | Wout[C][8] | bout[C]
+// dac ResidualVectorQuantize (eval): all stages fused.  One warp per token (8 tokens per CTA), the residual
+// and the running z_q in registers (C = 32 * CPL channels, codebook dim 8).  The weights of a stage are
+// staged ONCE per CTA in shared memory (cp.async, double buffered: stage s+1 streams in while stage s is
+// computed) in layouts that make every warp access conflict-free:
+//   Win[8][C] | bin[8] | cbnT[8][K] | c2[K] | WoutT[8][C] | bout[C]        (staged, 17C + 9K + 8 floats)
+//   cb[K][8]                                                                 (global: one row gathered per token)
+// cbnT = L2-normalised codebook, transposed; c2 = |cbn_k|^2; WoutT = out_proj weight, transposed.
 // ---------------------------------------------------------------------------------------------
 struct DacRvqArgs {
   const float* z;   // [N, C]
@@ -595,103 +720,116 @@ struct DacRvqArgs {
   long stage_stride;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+
 template <int CPL>
-__global__ void __launch_bounds__(256) dac_rvq_f32(const DacRvqArgs p) {
+__global__ void __launch_bounds__(256, 1) dac_rvq_f32(const DacRvqArgs p) {
+  extern __shared__ __align__(16) float wsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
-  if (n >= p.N) return;
+  const bool live = n < p.N;
   const int C = p.C, K = p.K;
+  const int staged = 17 * C + 9 * K + 8;
   float r[CPL], zq[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
-    r[i] = __ldg(p.z + (long)n * C + lane + 32 * i);
+    r[i] = live ? __ldg(p.z + (long)n * C + lane + 32 * i) : 0.f;
     zq[i] = 0.f;
   }
-  const int b = n / p.Tl, t = n - b * p.Tl;
+  const int b = live ? n / p.Tl : 0, t = live ? n - b * p.Tl : 0;
+  auto prefetch = [&](int st, int buf) {
+    const float4* src = reinterpret_cast<const float4*>(p.w + (long)st * p.stage_stride);
+    float4* dst = reinterpret_cast<float4*>(wsm + (long)buf * staged);
+    for (int i = threadIdx.x; i < staged / 4; i += 256) cp_async16(dst + i, src + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
   for (int st = 0; st < p.n_q; ++st) {
-    const float* Win = p.w + st * p.stage_stride;
+    if (st + 1 < p.n_q) {
+      prefetch(st + 1, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* Win = wsm + (long)(st & 1) * staged;
     const float* bin = Win + 8 * C;
-    const float* cbn = bin + 8;
-    const float* c2 = cbn + (long)K * 8;
-    const float* cb = c2 + K;
-    const float* Wout = cb + (long)K * 8;
-    const float* bout = Wout + (long)C * 8;
-    // in_proj (1x1 conv C -> 8)
-    float ze[8];
+    const float* cbnT = bin + 8;
+    const float* c2 = cbnT + 8 * K;
+    const float* WoutT = c2 + K;
+    const float* bout = WoutT + 8 * C;
+    const float* cb = p.w + (long)st * p.stage_stride + staged;
+    if (live) {
+      // in_proj (1x1 conv C -> 8)
+      float ze[8];
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      float s = 0.f;
+      for (int d = 0; d < 8; ++d) {
+        float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) s = fmaf(__ldg(Win + (long)d * C + lane + 32 * i), r[i], s);
+        for (int i = 0; i < CPL; ++i) s = fmaf(Win[d * C + lane + 32 * i], r[i], s);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      ze[d] = __fadd_rn(s, __ldg(bin + d));
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        ze[d] = __fadd_rn(s, bin[d]);
+      }
+      // F.normalize(encodings): x / max(|x|, 1e-12)
+      float nn = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) nn = fmaf(ze[d], ze[d], nn);
+      const float den = fmaxf(sqrtf(nn), 1e-12f);
+      float en[8];
+      float e2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { en[d] = __fdiv_rn(ze[d], den); }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) e2 = __fadd_rn(e2, __fmul_rn(en[d], en[d]));
+      // dist = |enc|^2 - 2 enc.cb + |cb|^2 ; first minimum of dist (== first maximum of -dist)
+      float best = INFINITY;
+      int bi = 0x7fffffff;
+      for (int k = lane; k < K; k += 32) {
+        float dot = (2.f * en[0]) * cbnT[k];
+#pragma unroll
+        for (int d = 1; d < 8; ++d) dot = fmaf(2.f * en[d], cbnT[d * K + k], dot);
+        float dist = __fadd_rn(__fsub_rn(e2, dot), c2[k]);
+        if (dist < best) { best = dist; bi = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
+      }
+      if (bi >= K) bi = 0;
+      if (lane == 0) p.codes[((long)b * p.n_q + st) * p.Tl + t] = bi;
+      // straight-through value z_e + (z_q - z_e), then out_proj (1x1 conv 8 -> C)
+      float stv[8];
+      {
+        float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8));
+        float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8 + 4));
+        float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) stv[d] = __fadd_rn(ze[d], __fsub_rn(qv[d], ze[d]));
+      }
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = lane + 32 * i;
+        float o = WoutT[c] * stv[0];
+#pragma unroll
+        for (int d = 1; d < 8; ++d) o = fmaf(WoutT[d * C + c], stv[d], o);
+        o = __fadd_rn(o, bout[c]);
+        zq[i] = __fadd_rn(zq[i], o);
+        r[i] = __fsub_rn(r[i], o);
+      }
     }
-    // F.normalize(encodings): x / max(|x|, 1e-12)
-    float nn = 0.f;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) nn = fmaf(ze[d], ze[d], nn);
-    const float den = fmaxf(sqrtf(nn), 1e-12f);
-    float en[8];
-    float e2 = 0.f;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) { en[d] = __fdiv_rn(ze[d], den); }
-#pragma unroll
-    for (int d = 0; d < 8; ++d) e2 = __fadd_rn(e2, __fmul_rn(en[d], en[d]));
-    // dist = |enc|^2 - 2 enc.cb + |cb|^2 ; first minimum of dist (== first maximum of -dist)
-    float best = INFINITY;
-    int bi = 0x7fffffff;
-    for (int k = lane; k < K; k += 32) {
-      float4 c0 = __ldg(reinterpret_cast<const float4*>(cbn + (long)k * 8));
-      float4 c1 = __ldg(reinterpret_cast<const float4*>(cbn + (long)k * 8 + 4));
-      float dot = (2.f * en[0]) * c0.x;
-      dot = fmaf(2.f * en[1], c0.y, dot);
-      dot = fmaf(2.f * en[2], c0.z, dot);
-      dot = fmaf(2.f * en[3], c0.w, dot);
-      dot = fmaf(2.f * en[4], c1.x, dot);
-      dot = fmaf(2.f * en[5], c1.y, dot);
-      dot = fmaf(2.f * en[6], c1.z, dot);
-      dot = fmaf(2.f * en[7], c1.w, dot);
-      float dist = __fadd_rn(__fsub_rn(e2, dot), __ldg(c2 + k));
-      if (dist < best) { best = dist; bi = k; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float os = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
-    }
-    if (bi >= K) bi = 0;
-    if (lane == 0) p.codes[((long)b * p.n_q + st) * p.Tl + t] = bi;
-    // straight-through value z_e + (z_q - z_e), then out_proj (1x1 conv 8 -> C)
-    float stv[8];
-    {
-      float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8));
-      float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8 + 4));
-      float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-      for (int d = 0; d < 8; ++d) stv[d] = __fadd_rn(ze[d], __fsub_rn(qv[d], ze[d]));
-    }
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      int c = lane + 32 * i;
-      float4 w0 = __ldg(reinterpret_cast<const float4*>(Wout + (long)c * 8));
-      float4 w1 = __ldg(reinterpret_cast<const float4*>(Wout + (long)c * 8 + 4));
-      float o = w0.x * stv[0];
-      o = fmaf(w0.y, stv[1], o);
-      o = fmaf(w0.z, stv[2], o);
-      o = fmaf(w0.w, stv[3], o);
-      o = fmaf(w1.x, stv[4], o);
-      o = fmaf(w1.y, stv[5], o);
-      o = fmaf(w1.z, stv[6], o);
-      o = fmaf(w1.w, stv[7], o);
-      o = __fadd_rn(o, __ldg(bout + c));
-      zq[i] = __fadd_rn(zq[i], o);
-      r[i] = __fsub_rn(r[i], o);
-    }
+    __syncthreads();   // this buffer is refilled by the prefetch issued at the top of iteration st + 1
   }
+  if (live) {
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) p.zq[(long)n * C + lane + 32 * i] = zq[i];
+    for (int i = 0; i < CPL; ++i) p.zq[(long)n * C + lane + 32 * i] = zq[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

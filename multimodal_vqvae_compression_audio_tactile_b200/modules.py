@@ -470,6 +470,9 @@ class ProposedEval(_Top):
         self.vq = ResidualVQEMA(dim=CODE_DIM, n_books=rvq_books, n_embed=rvq_embed)
         self.last_indices = None
         self.last_audio_codes = None
+        #: replay the per-shape program as a CUDA graph (one graph launch instead of ~125 kernel launches):
+        #: what the batch-1 streaming path (measure_proposed_latency, :489-525) wants
+        self.use_cuda_graph = False
 
     # -- packing ------------------------------------------------------------------------
     def _pack(self, eng):
@@ -542,6 +545,8 @@ class ProposedEval(_Top):
         c, n_q = pk["pp"].c, pk["n_q"]
         Lout = pk["t_dec"].out_len(Tl)
         a, t = _as_f32(a_1T), _as_f32(t_1T)
+        if self.use_cuda_graph and B <= self.micro_batch:
+            return self._run_graph(eng, pk, a, t, use, decode, want_latents)
         y = torch.empty(B, 1, Lout, device=dev, dtype=torch.float32) if decode else None
         idx = torch.empty(B, use, Tl, device=dev, dtype=torch.int32)
         codes = torch.empty(B, n_q, Tl, device=dev, dtype=torch.int32)
@@ -554,6 +559,40 @@ class ProposedEval(_Top):
                            idx[b0:].data_ptr(), codes[b0:].data_ptr(), z[b0:].data_ptr() if want_latents else 0])
         self.last_indices, self.last_audio_codes = idx, codes
         return y, z
+
+    def _run_graph(self, eng, pk, a, t, use, decode, want_latents):
+        """One CUDA-graph replay of the whole program on static buffers (inputs are copied in, outputs are
+        views of the static buffers, valid until the next call of the same shape)."""
+        B, T = a.shape[0], a.shape[-1]
+        dev = a.device
+        prog = self.program(eng, pk, B, T, use, decode=decode, latents_cm=want_latents)
+        key = ("graph", id(prog))
+        rec = eng.programs.get(key)
+        if rec is None:
+            c, n_q, Tl, Lout = pk["pp"].c, pk["n_q"], prog.info["Tl"], prog.info["Lout"]
+            st = dict(a=torch.empty(B, 1, T, device=dev), t=torch.empty(B, 1, T, device=dev),
+                      y=torch.empty(B, 1, Lout, device=dev) if decode else None,
+                      idx=torch.empty(B, use, Tl, device=dev, dtype=torch.int32),
+                      codes=torch.empty(B, n_q, Tl, device=dev, dtype=torch.int32),
+                      z=torch.empty(B, c, Tl, device=dev) if want_latents else None)
+            ext = [st["a"].data_ptr(), st["t"].data_ptr(), st["y"].data_ptr() if decode else 0, st["idx"].data_ptr(),
+                   st["codes"].data_ptr(), st["z"].data_ptr() if want_latents else 0]
+            st["a"].copy_(a); st["t"].copy_(t)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                eng.run(prog, ext)          # warm-up: tensor maps encoded, function attributes set
+                eng.run(prog, ext)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                eng.run(prog, ext)
+            rec = eng.programs[key] = dict(graph=graph, st=st, ws=eng.workspace(prog.ws_bytes))   # keeps the workspace alive
+        st = rec["st"]
+        st["a"].copy_(a); st["t"].copy_(t)
+        rec["graph"].replay()
+        self.last_indices, self.last_audio_codes = st["idx"], st["codes"]
+        return st["y"], st["z"]
 
     @torch.no_grad()
     def encode_latents(self, a_1T, t_1T, books_use=None):   # :451-478
