@@ -791,14 +791,14 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         d.codes = R.get<int>(op.r[2]);
         d.w = ctx->w[op.wid].dev;
         if (R.bad || !d.z || !d.zq || !d.codes) return fail(B2C_ERR_WORKSPACE, "op %zu (dac rvq): unresolved buffer", oi);
-        int blocks = (d.N + 7) / 8;
+        int blocks = (d.N + DACRVQ_WARPS - 1) / DACRVQ_WARPS;
         const size_t sm = 2 * (size_t)(17 * d.C + 9 * d.K + 8) * sizeof(float);
         if (sm > 227 * 1024) return fail(B2C_ERR_UNSUPPORTED, "dac rvq: C=%d K=%d needs %zu bytes of shared memory", d.C, d.K, sm);
 #define B2C_DACRVQ(CPL)                                                                                         \
   {                                                                                                             \
     cudaError_t e = cudaFuncSetAttribute(dac_rvq_f32<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
     if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "dac rvq smem: %s", cudaGetErrorString(e));                 \
-    dac_rvq_f32<CPL><<<blocks, 256, sm, st>>>(d);                                                               \
+    dac_rvq_f32<CPL><<<blocks, 32 * DACRVQ_WARPS, sm, st>>>(d);                                                 \
   }
         switch (d.C / 32) {
           case 32: B2C_DACRVQ(32) break;

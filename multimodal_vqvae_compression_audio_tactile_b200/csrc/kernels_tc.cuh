@@ -58,6 +58,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   printf("b2c conv_tc: mbarrier timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x);
   __trap();
 }
+// position in a ring of n mbarrier-guarded slots: slot index + phase parity, advanced without integer division
+// (two runtime divisions per pipeline step cost more than the MMAs of a narrow layer)
+struct Ring {
+  uint32_t s = 0, par = 0;
+  __device__ __forceinline__ void next(uint32_t n) {
+    if (++s == n) { s = 0; par ^= 1u; }
+  }
+};
+
+// one lane polls, the rest of the warp waits at __syncwarp (32 lanes polling the same mbarrier slow every
+// other mbarrier operation of the CTA down)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag, int lane) {
+  (void)lane;
+  mbar_wait(bar, parity, tag);   // measured: every lane polling is slightly FASTER than one lane + __syncwarp
+}
+// one thread of the 16 epilogue warps polls, the other 511 sleep in a hardware named barrier
+__device__ __forceinline__ void mbar_wait_epilogue(uint32_t bar, uint32_t parity, int tag) {
+  mbar_wait(bar, parity, tag);   // measured: all 512 threads polling beats one poller + a named barrier
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -211,6 +230,8 @@ struct TcConvParams {
   int n_rows, n_codes;
   // slab kernel (conv_tc2_kernel): MT m-tiles per work item share one activation slab and every weight tile
   int MT, groups_j, slab_rows, box_rows, n_aloads, SA, SB;
+  int dbg;        // B2C_TC_DEBUG bit mask (timing experiments only): 1 skip epilogue work, 2 no TMA, 4 no MMA
+  int stg_bufs;   // epilogue staging tiles: 2 (one barrier per chunk) or 1 (two barriers, frees 18 KB for the rings)
   uint32_t row_bytes, a_plane_bytes;
 };
 
@@ -249,7 +270,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
   }
   const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
   for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-    float* sb = stg + (chunk_ctr & 1u) * (TC_BM * TC_STG_LD);
+    float* sb = stg + (p.stg_bufs == 2 ? (chunk_ctr & 1u) * (TC_BM * TC_STG_LD) : 0u);
     const int co = nt * p.BN + c * 32 + cq * 4;
     float4 rr[2];
 #pragma unroll
@@ -306,6 +327,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
         }
       }
     }
+    if (p.stg_bufs != 2) asm volatile("bar.sync 1, 512;" ::: "memory");   // the single tile is rewritten next chunk
   }
 }
 
@@ -399,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      Ring rg;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
         int mt = tile / p.n_ntiles;
@@ -410,10 +432,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int j0 = jt * TC_BM;
         for (int tap = 0; tap < p.KT; ++tap) {
           const int brow = (ph * p.KT + tap) * p.Cout + nt * p.BN;
-          for (int cb = 0; cb < p.n_kblk; ++cb, ++it) {
-            const uint32_t s = it % p.stages, par = (it / p.stages) & 1u;
+          for (int cb = 0; cb < p.n_kblk; ++cb, rg.next(p.stages)) {
+            const uint32_t s = rg.s, par = rg.par;
             mbar_wait(smem_u32(&bar_empty[s]), par ^ 1u, 1);
             const uint32_t full = smem_u32(&bar_full[s]);
+            if (p.dbg & 2) { mbar_arrive(full); continue; }
             mbar_expect_tx(full, stage_bytes);
             const uint32_t sa = smem0 + s * stage_bytes;
             const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
@@ -445,24 +468,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ksteps = p.BK / 16;
       const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
       const uint32_t a_plane = p.a_bytes >> 4, b_plane = p.b_bytes >> 4;
-      uint32_t it = 0, tcount = 0;
+      uint32_t tcount = 0;
+      Ring rg;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-        mbar_wait(smem_u32(&bar_tempty[acc]), apar ^ 1u, 2);
+        mbar_wait_warp(smem_u32(&bar_tempty[acc]), apar ^ 1u, 2, lane);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        for (int ki = 0; ki < n_kiter; ++ki, ++it) {
-          const uint32_t s = it % p.stages, par = (it / p.stages) & 1u;
-          mbar_wait(smem_u32(&bar_full[s]), par, 3);
-          tc_fence_after();
+        for (int ki = 0; ki < n_kiter; ++ki, rg.next(p.stages)) {
+          const uint32_t s = rg.s, par = rg.par;
+          mbar_wait_warp(smem_u32(&bar_full[s]), par, 3, lane);
+          if (!(p.dbg & 16)) tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes;
           const uint32_t a_lo = (sa & 0x3FFFFu) >> 4;
           const uint32_t b_lo = ((sa + p.a_bytes * (X3 ? 2u : 1u)) & 0x3FFFFu) >> 4;
           const uint32_t first = ki != 0;
-          if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+          if (p.dbg & 4) {}
+          else if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
           else if (ksteps == 2) umma_ksteps<X3, 2>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
           else umma_ksteps<X3, 1>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
-          umma_commit_w(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
+          if (p.dbg & 8) { if (lane == 0) mbar_arrive(smem_u32(&bar_empty[s])); __syncwarp(); }
+          else umma_commit_w(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
         }
         umma_commit_w(smem_u32(&bar_tfull[acc]));   // accumulator complete -> epilogue
       }
@@ -483,9 +509,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ph = mt % p.n_phase;
       const int b = mt / p.n_phase;
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-      mbar_wait(smem_u32(&bar_tfull[acc]), apar, 4);
+      mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 4);
       tc_fence_after();
-      if (EPI == 0)
+      if (p.dbg & 1) {
+        tc_fence_before();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 64) mbar_arrive(smem_u32(&bar_tempty[acc]));
+      } else if (EPI == 0)
         tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
                          warp, lane);
       else
@@ -565,7 +595,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // tiles of step s, so the (large, possibly DRAM-resident) activation slab has a whole step of lead time
     // instead of the few weight tiles the B ring would otherwise allow.
     if (lane == 0) {
-      uint32_t ia = 0, ib = 0;
+      Ring ra, rb;
       auto issue_slab = [&](int item, int cb) {
         int r = item / p.n_ntiles;
         const int jg = r % p.groups_j;
@@ -573,7 +603,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int ph = r % p.n_phase;
         const int b = r / p.n_phase;
         const int row0 = jg * p.MT * TC_BM + p.in_off[ph];
-        const uint32_t sa = ia % p.SA, par = (ia / p.SA) & 1u;
+        const uint32_t sa = ra.s, par = ra.par;
         mbar_wait(smem_u32(&bar_aempty[sa]), par ^ 1u, 1);
         const uint32_t full = smem_u32(&bar_afull[sa]);
         mbar_expect_tx(full, a_slot);
@@ -583,7 +613,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tma_load_3d(dst + off, &tmA_hi, full, cb * p.BK, row0 + ld * p.box_rows, b);
           if (X3) tma_load_3d(dst + p.a_plane_bytes + off, &tmA_lo, full, cb * p.BK, row0 + ld * p.box_rows, b);
         }
-        ++ia;
+        ra.next(p.SA);
       };
       if ((int)blockIdx.x < p.total_tiles) issue_slab(blockIdx.x, 0);
       for (int item = blockIdx.x; item < p.total_tiles; item += gridDim.x) {
@@ -593,8 +623,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (cb + 1 < p.n_kblk) issue_slab(item, cb + 1);
           else if (item + (int)gridDim.x < p.total_tiles) issue_slab(item + gridDim.x, 0);
           const int c0 = cb * p.BK;
-          for (int tap = 0; tap < p.KT; ++tap, ++ib) {
-            const uint32_t sb = ib % p.SB, par = (ib / p.SB) & 1u;
+          for (int tap = 0; tap < p.KT; ++tap, rb.next(p.SB)) {
+            const uint32_t sb = rb.s, par = rb.par;
             mbar_wait(smem_u32(&bar_bempty[sb]), par ^ 1u, 2);
             const uint32_t full = smem_u32(&bar_bfull[sb]);
             mbar_expect_tx(full, b_slot);
@@ -615,22 +645,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t a_plane = p.a_plane_bytes >> 4, b_plane = p.b_bytes >> 4;
       const uint32_t tap_step = ((uint32_t)p.dil * p.row_bytes) >> 4;        // descriptor units per tap
       const uint32_t mtile_step = ((uint32_t)TC_BM * p.row_bytes) >> 4;      // descriptor units per m-tile
-      uint32_t ia = 0, ib = 0, tcount = 0;
+      uint32_t tcount = 0;
+      Ring ra, rb;
       for (int item = blockIdx.x; item < p.total_tiles; item += gridDim.x, ++tcount) {
         const int jg = (item / p.n_ntiles) % p.groups_j;
         const int n_m = min(p.MT, p.tiles_j - jg * p.MT);
         const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-        mbar_wait(smem_u32(&bar_tempty[acc]), apar ^ 1u, 3);
+        mbar_wait_warp(smem_u32(&bar_tempty[acc]), apar ^ 1u, 3, lane);
         tc_fence_after();
         const uint32_t d_set = tmem_base + acc * set_cols;
-        for (int cb = 0; cb < p.n_kblk; ++cb, ++ia) {
-          const uint32_t sa = ia % p.SA, apr = (ia / p.SA) & 1u;
-          mbar_wait(smem_u32(&bar_afull[sa]), apr, 4);
+        for (int cb = 0; cb < p.n_kblk; ++cb, ra.next(p.SA)) {
+          const uint32_t sa = ra.s, apr = ra.par;
+          mbar_wait_warp(smem_u32(&bar_afull[sa]), apr, 4, lane);
           tc_fence_after();
           uint32_t a_tap = ((smem0 + sa * a_slot) & 0x3FFFFu) >> 4;
-          for (int tap = 0; tap < p.KT; ++tap, ++ib, a_tap += tap_step) {
-            const uint32_t sb = ib % p.SB, bpr = (ib / p.SB) & 1u;
-            mbar_wait(smem_u32(&bar_bfull[sb]), bpr, 5);
+          for (int tap = 0; tap < p.KT; ++tap, rb.next(p.SB), a_tap += tap_step) {
+            const uint32_t sb = rb.s, bpr = rb.par;
+            mbar_wait_warp(smem_u32(&bar_bfull[sb]), bpr, 5, lane);
             tc_fence_after();
             const uint32_t b_lo = ((smemB + sb * b_slot) & 0x3FFFFu) >> 4;
             const uint32_t first = (cb | tap) != 0;
@@ -661,7 +692,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int b = r / p.n_phase;
       const int n_m = min(p.MT, p.tiles_j - jg * p.MT);
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-      mbar_wait(smem_u32(&bar_tfull[acc]), apar, 6);
+      mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 6);
       tc_fence_after();
       for (int m = 0; m < n_m; ++m)
         tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * set_cols + m * p.acc_stride, b, ph, jg * p.MT + m, nt,
@@ -827,8 +858,13 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   if (!w.hi) return 1;
   if (a.Cin % 32 != 0) return 2;
   if (a.in_step > 1 && (a.dil != 1 || a.Lin % a.in_step != 0)) return 3;
-  const int bn = largest_bn(a.Cout);
+  int bn = largest_bn(a.Cout);
   if (!bn) return 4;
+  // small problems (batch-1 streaming): narrower channel blocks so that more SMs get a tile
+  {
+    const long mtiles = (long)a.B * a.n_phase * ((a.Lj + TC_BM - 1) / TC_BM);
+    while (bn > 64 && (bn / 2) % 32 == 0 && a.Cout % (bn / 2) == 0 && mtiles * (a.Cout / bn) * 2 <= sm_count) bn /= 2;
+  }
   if (!tc_encode_fn()) return -10;
   TcConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -838,20 +874,29 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   p.n_phase = a.n_phase; p.Lj = a.Lj; p.out_step = a.out_step; p.Lout = a.Lout;
   for (int i = 0; i < 8; ++i) { p.in_off[i] = a.in_off[i]; p.out_off[i] = a.out_off[i]; }
   p.act = a.act; p.res_mode = a.res_mode; p.Tl = a.Tl; p.chunk = a.chunk; p.out_fmt = out_fmt;
+  {
+    const char* e = getenv("B2C_TC_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.act_plane_elems = (long)a.B * a.Lout * a.Cout;
   p.BN = bn;
   // shared memory: pipeline stages + the epilogue's two staging tiles + 1 KB of alignment slack, under the
   // 227 KB per-CTA limit (the kernel's static shared memory is ~1.3 KB).  Prefer 128-byte K slices (BK = 64)
   // when at least 3 stages fit, else 64-byte slices (BK = 32).
-  const int budget = 232448 - 2048 - TC_STG_BYTES - 1024;
+  const int budget = 232448 - 2048 - TC_STG_BYTES - 1024;        // with two staging tiles
+  const int budget1 = budget + TC_STG_BYTES / 2;                  // with one
   uint32_t stage = 0;
   int stages = 0;
+  p.stg_bufs = 2;
   for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= 32; bk -= 32) {
     p.BK = bk;
     p.a_bytes = TC_BM * bk * 2;
     p.b_bytes = bn * bk * 2;
     stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
     stages = budget / (int)stage;
+    // the pipeline is TMA-latency bound with < 4 stages of ~48 KB: give up the second staging tile for one more
+    if (stages < 4 && budget1 / (int)stage > stages) { stages = budget1 / (int)stage; p.stg_bufs = 1; }
+    else p.stg_bufs = 2;
     if (stages >= 3 || bk == 32) break;
   }
   p.n_kblk = a.Cin / p.BK;
@@ -868,7 +913,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   p.acc_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
   p.tmem_cols = 2 * p.acc_stride;
   plan->grid = (int)(total < sm_count ? total : sm_count);
-  plan->smem = (size_t)stages * stage + TC_STG_BYTES + 1024;
+  plan->smem = (size_t)stages * stage + (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
   plan->cached_x = nullptr;
   plan->b_ready = false;
   plan->slab = 0;
@@ -913,7 +958,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
         p.acc_stride = stride2;
         p.MT = mt; p.groups_j = (p.tiles_j + mt - 1) / mt;
         p.slab_rows = rows; p.box_rows = box_rows; p.n_aloads = n_loads; p.SA = SA; p.SB = SB;
-        p.row_bytes = bk * 2; p.a_plane_bytes = a_plane;
+        p.row_bytes = bk * 2; p.a_plane_bytes = a_plane; p.stg_bufs = 2;
         p.tmem_cols = 2 * mt * stride2;
         if (p.tmem_cols < 32) p.tmem_cols = 32;
         long items = (long)a.B * a.n_phase * p.groups_j * p.n_ntiles;
@@ -1164,7 +1209,7 @@ inline int tc_nearest_launch(const float* x, const float* emb, void* scratch, in
   p.a_bytes = TC_BM * d.BK * 2; p.b_bytes = d.BN * d.BK * 2;
   p.sbo = 8 * d.BK * 2;
   p.layout_type = d.BK == 64 ? 2u : (d.BK == 32 ? 4u : 6u);
-  p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K;
+  p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K; p.stg_bufs = 2;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   cuuint32_t es[3] = {1, 1, 1};
   {
