@@ -230,6 +230,7 @@ struct TcConvParams {
   int n_rows, n_codes;
   // slab kernel (conv_tc2_kernel): MT m-tiles per work item share one activation slab and every weight tile
   int MT, groups_j, slab_rows, box_rows, n_aloads, SA, SB;
+  int kgroup;     // K blocks per pipeline stage of the generic kernel (one mbarrier hand-off per kgroup blocks)
   int dbg;        // B2C_TC_DEBUG bit mask (timing experiments only): 1 skip epilogue work, 2 no TMA, 4 no MMA
   int stg_bufs;   // epilogue staging tiles: 2 (one barrier per chunk) or 1 (two barriers, frees 18 KB for the rings)
   uint32_t row_bytes, a_plane_bytes;
@@ -395,7 +396,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (p.a_bytes + p.b_bytes) * (X3 ? 2u : 1u);
+  const uint32_t sub_bytes = (p.a_bytes + p.b_bytes) * (X3 ? 2u : 1u);   // one K block: A (+lo) | B (+lo)
+  const uint32_t stage_bytes = sub_bytes * (uint32_t)p.kgroup;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -430,17 +432,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ph = mt % p.n_phase;
         const int b = mt / p.n_phase;
         const int j0 = jt * TC_BM;
-        for (int tap = 0; tap < p.KT; ++tap) {
-          const int brow = (ph * p.KT + tap) * p.Cout + nt * p.BN;
-          for (int cb = 0; cb < p.n_kblk; ++cb, rg.next(p.stages)) {
-            const uint32_t s = rg.s, par = rg.par;
-            mbar_wait(smem_u32(&bar_empty[s]), par ^ 1u, 1);
-            const uint32_t full = smem_u32(&bar_full[s]);
-            if (p.dbg & 2) { mbar_arrive(full); continue; }
-            mbar_expect_tx(full, stage_bytes);
-            const uint32_t sa = smem0 + s * stage_bytes;
+        int tap = 0, cb = 0;
+        for (int k0 = 0; k0 < n_kiter; k0 += p.kgroup, rg.next(p.stages)) {
+          const int cnt = min(p.kgroup, n_kiter - k0);
+          const uint32_t s = rg.s, par = rg.par;
+          mbar_wait(smem_u32(&bar_empty[s]), par ^ 1u, 1);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          if (p.dbg & 2) { mbar_arrive(full); continue; }
+          mbar_expect_tx(full, sub_bytes * (uint32_t)cnt);
+          for (int g = 0; g < cnt; ++g) {
+            const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
             const uint32_t sb = sa + p.a_bytes * (X3 ? 2u : 1u);
             const int c0 = cb * p.BK;
+            const int brow = (ph * p.KT + tap) * p.Cout + nt * p.BN;
             if (p.in_step == 1) {
               const int row = j0 + tap * p.dil + p.in_off[ph];
               tma_load_3d(sa, &tmA_hi, full, c0, row, b);
@@ -454,6 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             tma_load_2d(sb, &tmB_hi, full, c0, brow);
             if (X3) tma_load_2d(sb + p.b_bytes, &tmB_lo, full, c0, brow);
+            if (++cb == p.n_kblk) { cb = 0; ++tap; }
           }
         }
       }
@@ -475,18 +480,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait_warp(smem_u32(&bar_tempty[acc]), apar ^ 1u, 2, lane);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        for (int ki = 0; ki < n_kiter; ++ki, rg.next(p.stages)) {
+        for (int k0 = 0; k0 < n_kiter; k0 += p.kgroup, rg.next(p.stages)) {
+          const int cnt = min(p.kgroup, n_kiter - k0);
           const uint32_t s = rg.s, par = rg.par;
           mbar_wait_warp(smem_u32(&bar_full[s]), par, 3, lane);
           if (!(p.dbg & 16)) tc_fence_after();
-          const uint32_t sa = smem0 + s * stage_bytes;
-          const uint32_t a_lo = (sa & 0x3FFFFu) >> 4;
-          const uint32_t b_lo = ((sa + p.a_bytes * (X3 ? 2u : 1u)) & 0x3FFFFu) >> 4;
-          const uint32_t first = ki != 0;
-          if (p.dbg & 4) {}
-          else if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
-          else if (ksteps == 2) umma_ksteps<X3, 2>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
-          else umma_ksteps<X3, 1>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+          for (int g = 0; g < cnt; ++g) {
+            const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
+            const uint32_t a_lo = (sa & 0x3FFFFu) >> 4;
+            const uint32_t b_lo = ((sa + p.a_bytes * (X3 ? 2u : 1u)) & 0x3FFFFu) >> 4;
+            const uint32_t first = (k0 + g) != 0;
+            if (p.dbg & 4) {}
+            else if (ksteps == 4) umma_ksteps<X3, 4>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+            else if (ksteps == 2) umma_ksteps<X3, 2>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+            else umma_ksteps<X3, 1>(d_tmem, a_lo, b_lo, a_plane, b_plane, desc_hi, idesc, first);
+          }
           if (p.dbg & 8) { if (lane == 0) mbar_arrive(smem_u32(&bar_empty[s])); __syncwarp(); }
           else umma_commit_w(smem_u32(&bar_empty[s]));   // frees the smem stage when these MMAs retire
         }
@@ -894,10 +902,28 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
     p.b_bytes = bn * bk * 2;
     stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
     stages = budget / (int)stage;
-    // the pipeline is TMA-latency bound with < 4 stages of ~48 KB: give up the second staging tile for one more
+    // give up the second staging tile when that buys one more K block in flight
     if (stages < 4 && budget1 / (int)stage > stages) { stages = budget1 / (int)stage; p.stg_bufs = 1; }
     else p.stg_bufs = 2;
     if (stages >= 3 || bk == 32) break;
+  }
+  // K blocks per stage: every mbarrier hand-off costs ~400 cycles on both the TMA and the MMA warp (measured
+  // with the MMAs and copies switched off).  K blocks whose MMAs take less than ~512 tensor-pipe cycles are
+  // grouped under one hand-off while at least two stages remain; longer blocks lose more from the shallower
+  // ring than they gain (measured: grouping helps 64..384-channel layers, hurts 256-wide bf16x3 and 768 bf16).
+  p.kgroup = 1;
+  {
+    const int cyc = (p.BK / 16) * (plan->x3 ? 3 : 1) * (bn / 2);   // tensor-pipe cycles of one K block (M = 128)
+    int want = (512 + cyc - 1) / cyc;
+    const char* e = getenv("B2C_TC_KGROUP");
+    if (e) want = atoi(e);
+    if (want < 1) want = 1;
+    if (want > 8) want = 8;
+    while (want > 1 && stages / want < 2) --want;
+    while (want > 1 && a.KT * (a.Cin / p.BK) < 2 * want) --want;
+    p.kgroup = want;
+    stages /= want;
+    stage *= want;
   }
   p.n_kblk = a.Cin / p.BK;
   p.sbo = 8 * p.BK * 2;
@@ -920,7 +946,10 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   // Measured on B200 (tools/tc_selftest.py, batch 32): the slab kernel wins where the generic kernel's MMA is
   // narrow (N <= 128) and the contraction is long enough to amortise the slab (k = 7 at 96 / 128 channels);
   // wider layers are MMA-issue bound and prefer the generic kernel's N = 192 / 256 instructions.
-  const bool slab_pays = a.KT >= 3 && (a.Cout == 96 || a.Cout == 128);
+  // ... that was before K blocks were grouped per hand-off in the generic kernel; with grouping the generic
+  // kernel is as fast or faster on every layer of this model (96 ch: 0.240 vs 0.263 ms, 128 ch: 0.258 vs 0.256),
+  // so the slab kernel is kept for experiments (B2C_TC_SLAB=2) and not selected by default.
+  const bool slab_pays = false;
   if (a.in_step == 1 && tc_slab_enabled() && (slab_pays || tc_slab_forced())) {
     // slab kernel: narrower channel blocks, several m-tiles per work item
     const int bn2 = a.Cout % 128 == 0 ? 128 : (a.Cout % 96 == 0 ? 96 : (a.Cout % 64 == 0 ? 64 : bn));
@@ -1209,7 +1238,7 @@ inline int tc_nearest_launch(const float* x, const float* emb, void* scratch, in
   p.a_bytes = TC_BM * d.BK * 2; p.b_bytes = d.BN * d.BK * 2;
   p.sbo = 8 * d.BK * 2;
   p.layout_type = d.BK == 64 ? 2u : (d.BK == 32 ? 4u : 6u);
-  p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K; p.stg_bufs = 2;
+  p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K; p.stg_bufs = 2; p.kgroup = 1;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   cuuint32_t es[3] = {1, 1, 1};
   {
