@@ -130,6 +130,14 @@ int b2c_prog_conv(b2c_prog* p, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw,
 /* ConvTranspose1d (k = 2*stride, padding = ceil(stride/2)), x [B, Lin, cin] -> [B, Lout, cout]. */
 int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b2c_ref out_act, int act, int alpha_wid, int B,
                    int Lin, int precision, int x_fmt, int act_fmt);
+/* One fused launch for a dac ResidualUnit (snake -> Conv1d k=7 dilated -> snake -> Conv1d k=1 -> + x):
+ *   x_act = snake1(x) as bf16 plane(s) (precision BF16X3: two planes, BF16: one), x_raw = x (fp32 residual),
+ *   out_raw = y (fp32, may be B2C_NULL_REF), out_act = snake_next(y) stored as act_fmt (bf16 plane(s)).
+ * The intermediate h = snake2(conv7(.)) stays in shared memory.  b2c_ru_tc_eligible(): 1 when the weight pair is
+ * a k=7 / k=1 pair of equal width C in {64, 96, 128, 192} with 'same' padding. */
+int b2c_ru_tc_eligible(const b2c_ctx* ctx, int wid7, int wid1, int precision);
+int b2c_prog_ru(b2c_prog* p, int wid7, int alpha2_wid, int wid1, b2c_ref x_act, b2c_ref x_raw, b2c_ref out_raw,
+                b2c_ref out_act, int alpha_next_wid, int B, int L, int dilation, int precision, int act_fmt);
 /* dac Decoder head: Conv1d(cin, 1, k=7, p=3) + tanh on x [B, L, cin] -> y [B, L]. */
 int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int x_fmt);
 /* LayerNorm over C of rows gathered by a_mode from a (minus sub, plus pe row), optional scale*tanh.

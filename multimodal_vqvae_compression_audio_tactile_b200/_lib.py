@@ -71,6 +71,8 @@ SIGNATURES = {
     "b2c_prog_stem": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_conv": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "b2c_prog_convT": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i]),
+    "b2c_ru_tc_eligible": (_i, [C.c_void_p, _i, _i, _i]),
+    "b2c_prog_ru": (_i, [C.c_void_p, _i, _i, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i]),
     "b2c_prog_head": (_i, [C.c_void_p, _i, _ref, _ref, _i, _i, _i]),
     "b2c_prog_layernorm": (_i, [C.c_void_p, _i, _i, _ref, _i, _ref, _i, _i, _i, C.c_float, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_convert": (_i, [C.c_void_p, _ref, _i, _ref, _i, C.c_size_t]),

@@ -12,6 +12,7 @@
 
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_ru.cuh"
 
 using namespace b2c;
 
@@ -262,7 +263,7 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
 // programs
 // ------------------------------------------------------------------------------------------
 enum OpType { OP_STEM, OP_CONV, OP_HEAD, OP_LN, OP_ATTN, OP_RVQ, OP_NEAREST, OP_DACRVQ, OP_SCATTER, OP_TRANSPOSE,
-              OP_WIDEN, OP_CONV_TC, OP_CONVERT };
+              OP_WIDEN, OP_CONV_TC, OP_CONVERT, OP_RU_TC };
 
 struct Op {
   OpType type;
@@ -274,6 +275,7 @@ struct Op {
   RvqArgs rvq;
   DacRvqArgs dac;
   TcConvPlan tc;
+  TcRuPlan ru;
   int i[8] = {0};
   size_t n = 0;
   int precision = 0;
@@ -413,6 +415,48 @@ extern "C" int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, 
   }
   return add_conv(p, "b2c_prog_convT", wid, x, B2C_NULL_REF, out_raw, out_act, act, alpha_wid, B, Lin, 1, 1, 0, 0, 0,
                   0, precision, x_fmt, act_fmt);
+}
+
+static int ru_weights_ok(const b2c_ctx* ctx, int wid7, int wid1, int precision) {
+  if (!ctx || wid7 < 0 || wid1 < 0 || wid7 >= (int)ctx->w.size() || wid1 >= (int)ctx->w.size()) return 0;
+  const Weight& a = ctx->w[wid7];
+  const Weight& b = ctx->w[wid1];
+  if (a.kind != W_CONV || b.kind != W_CONV || a.transposed || b.transposed) return 0;
+  if (a.k != 7 || b.k != 1 || a.cin != a.cout || b.cin != b.cout || a.cin != b.cin || a.stride != 1 || b.stride != 1) return 0;
+  const int C = a.cin;
+  if (!(C == 64 || C == 96 || C == 128 || C == 192)) return 0;
+  if (!(a.tc.hi && b.tc.hi && tc_ru_enabled())) return 0;
+  if (precision != B2C_PREC_BF16X3 && precision != B2C_PREC_BF16) return 0;
+  TcRuPlan probe;   // shared-memory feasibility depends on the precision (two planes of h for bf16x3)
+  return tc_ru_plan(1, 128, C, 1, a.tc, b.tc, precision, FMT_HI, ctx->sm_count, &probe) == 0 ? 1 : 0;
+}
+
+extern "C" int b2c_ru_tc_eligible(const b2c_ctx* ctx, int wid7, int wid1, int precision) {
+  return ru_weights_ok(ctx, wid7, wid1, precision);
+}
+
+extern "C" int b2c_prog_ru(b2c_prog* p, int wid7, int alpha2_wid, int wid1, b2c_ref x_act, b2c_ref x_raw, b2c_ref out_raw,
+                           b2c_ref out_act, int alpha_next_wid, int B, int L, int dilation, int precision, int act_fmt) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_ru: NULL program");
+  if (!ru_weights_ok(p->ctx, wid7, wid1, precision))
+    return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_ru: weights %d / %d are not a fusable ResidualUnit (ask b2c_ru_tc_eligible)", wid7, wid1);
+  if (precision != B2C_PREC_BF16X3 && precision != B2C_PREC_BF16) return fail(B2C_ERR_ARG, "b2c_prog_ru: tensor-core precisions only");
+  if (!get_w(p, alpha2_wid, W_VEC, "b2c_prog_ru(alpha2)") || !get_w(p, alpha_next_wid, W_VEC, "b2c_prog_ru(alpha_next)")) return B2C_ERR_ARG;
+  if (B <= 0 || L <= 0 || dilation < 1) return fail(B2C_ERR_ARG, "b2c_prog_ru: bad sizes");
+  if (act_fmt != B2C_FMT_BF16X2 && act_fmt != B2C_FMT_BF16) return fail(B2C_ERR_ARG, "b2c_prog_ru: out_act is stored as bf16 plane(s)");
+  const Weight& w7 = p->ctx->w[wid7];
+  if (w7.padding != 3 * dilation) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_ru: 'same' padding (3*dilation) only");
+  Op op;
+  op.type = OP_RU_TC;
+  blank_refs(op);
+  op.r[0] = x_act; op.r[1] = x_raw; op.r[2] = out_raw; op.r[3] = out_act;
+  op.wid = wid7; op.wid2 = alpha2_wid; op.wid3 = wid1;
+  op.i[0] = alpha_next_wid; op.i[1] = B; op.i[2] = L; op.i[3] = dilation;
+  op.precision = precision; op.act_fmt = act_fmt;
+  int rc = tc_ru_plan(B, L, w7.cin, dilation, w7.tc, p->ctx->w[wid1].tc, precision, act_fmt, p->ctx->sm_count, &op.ru);
+  if (rc) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_ru: plan failed (%d)", rc);
+  p->ops.push_back(op);
+  return B2C_OK;
 }
 
 extern "C" int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int x_fmt) {
@@ -689,6 +733,23 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         }
         break;
       }
+      case OP_RU_TC: {
+        const Weight& w7 = ctx->w[op.wid];
+        const Weight& w1 = ctx->w[op.wid3];
+        const Weight& a2 = ctx->w[op.wid2];
+        const Weight& an = ctx->w[op.i[0]];
+        TcRuArgs ra;
+        ra.x_planes = R.get<const char>(op.r[0]);
+        ra.x_raw = R.get<const float>(op.r[1]);
+        ra.out_raw = R.get<float>(op.r[2]);
+        ra.out_act = R.get<char>(op.r[3]);
+        ra.bias7 = w7.bias; ra.alpha2 = a2.dev; ra.inv_alpha2 = a2.aux;
+        ra.bias1 = w1.bias; ra.alpha_next = an.dev; ra.inv_alpha_next = an.aux;
+        if (R.bad || !ra.x_planes || !ra.x_raw || !ra.out_act) return fail(B2C_ERR_WORKSPACE, "op %zu (residual unit): unresolved buffer", oi);
+        int rc = tc_ru_launch(op.ru, ra, w7.tc, w1.tc, st);
+        if (rc) return fail(B2C_ERR_CUDA, "op %zu (residual unit, tcgen05): launch failed (%d)", oi, rc);
+        break;
+      }
       case OP_HEAD: {
         const Weight& w = ctx->w[op.wid];
         const void* x = R.get<const char>(op.r[0]);
@@ -869,6 +930,14 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
       *flops = 2.0 * rows * a.Cout * a.Cin * a.KT;
       double outs = (op.r[2] != B2C_NULL_REF ? 1 : 0) + (op.r[3] != B2C_NULL_REF ? 1 : 0) + (op.r[1] != B2C_NULL_REF ? 1 : 0);
       *bytes = 4.0 * ((double)a.B * a.Lin * a.Cin + rows * a.Cout * outs + (double)a.n_phase * a.KT * a.Cin * a.Cout);
+      break;
+    }
+    case OP_RU_TC: {
+      const Weight& w = ctx->w[op.wid];
+      double rows = (double)op.i[1] * op.i[2], C = w.cin;
+      *kind = B2C_KIND_CONV_TC;
+      *flops = 2.0 * rows * C * C * 8.0;                       // k = 7 conv + k = 1 conv
+      *bytes = 4.0 * (rows * C * (3.0 + (op.r[2] != B2C_NULL_REF ? 1 : 0)) + 8.0 * C * C);   // x_act, x_raw, out_act (+ out_raw)
       break;
     }
     case OP_STEM: {

@@ -1,0 +1,411 @@
+// Fused dac ResidualUnit on tcgen05:   y = x + conv1( snake2( conv7_dilated( snake1(x) ) ) ),   out_act = snake_next(y)
+// (dac ResidualUnit; call sites Evaluation/dac_vcpwq_proposed6_latency.py:457,459,486).
+//
+// One CTA owns 128 positions x all C channels (C = 64 / 96 / 128 / 192: the long, narrow, HBM-bound layers):
+//   GEMM 1  acc1[128 x C] = sum over (tap, channel block) A(tap) . W7        (activation tiles by TMA, as conv_tc_kernel)
+//   epilogue A   h = snake2(acc1 + b7) -> bf16 hi/lo, written by the epilogue warps straight into shared memory in
+//                the K-major swizzled layout UMMA reads (never to HBM)
+//   GEMM 2  acc2[128 x C] = h . W1                                            (W1 tiles through the same TMA ring)
+//   epilogue B   y = acc2 + b1 + x_raw -> out_raw (fp32) and snake_next(y) -> out_act (bf16 planes)
+// Against the two separate kernels this removes one write and one read of h (2 of 6 activation passes per unit) and
+// one launch.  Warp roles as conv_tc_kernel.  With 4*S <= 512 TMEM columns (C <= 128) acc1 and acc2 are double
+// buffered and GEMM 1 of tile i+1 is issued BEFORE GEMM 2 of tile i, so the tensor pipe works while the epilogue
+// warps produce h(i).
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace b2c {
+
+struct TcRuParams {
+  TcConvParams e;            // geometry + epilogue B (bias1, res = x_raw, out_raw, out_act, alpha_next)
+  const float* bias7;
+  const float* alpha2;
+  const float* inv_alpha2;
+  int nk;                    // channel blocks (C / BK) of either GEMM
+  int nbuf;                  // TMEM accumulator buffers per GEMM (2 or 1)
+  uint32_t h_plane_bytes;    // 128 * C * 2
+  uint32_t h_block_bytes;    // 128 * BK * 2
+};
+
+// epilogue A of one tile: TMEM acc1 -> staging -> (+b7, snake2, bf16 split) -> swizzled K-major h in shared memory
+template <int X3>
+__device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
+                                              uint8_t* hbuf, int warp, int lane) {
+  const TcConvParams& p = q.e;
+  const int ew = warp - 2;
+  const int quad = warp & 3;
+  const int cg8 = ew >> 2;
+  const int et = threadIdx.x - 64;
+  const int cq = et & 7;
+  const int r0 = et >> 3;
+  const int nchunks = p.BN >> 5;
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
+  const uint32_t row_bytes = (uint32_t)p.BK * 2;
+  for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+    float* sb = stg + (p.stg_bufs == 2 ? (chunk_ctr & 1u) * (TC_BM * TC_STG_LD) : 0u);
+    const int co = c * 32 + cq * 4;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q.bias7) bb = __ldg(reinterpret_cast<const float4*>(q.bias7 + co));
+    const float4 al = __ldg(reinterpret_cast<const float4*>(q.alpha2 + co));
+    const float4 ia = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + co));
+    {
+      float v[8];
+      tmem_ld8(t_src + c * 32, v);
+      float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int kb = co / p.BK, cin = co - kb * p.BK;
+    const uint32_t chunk16 = (uint32_t)cin >> 3, within = ((uint32_t)cin & 7u) * 2u;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + 64 * i;
+      float4 a = *reinterpret_cast<const float4*>(sb + r * TC_STG_LD + cq * 4);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      float4 w;
+      w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
+      w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+      // K-major swizzled position of (row r, channel co): 16-byte chunk index XOR the row bits the TMA/UMMA swizzle
+      // uses (128B: r & 7; 64B: (r >> 1) & 3)
+      const uint32_t sw = p.BK == 64 ? ((uint32_t)r & 7u) : (((uint32_t)r >> 1) & 3u);
+      uint8_t* dst = hbuf + (uint32_t)kb * q.h_block_bytes + (uint32_t)r * row_bytes + ((chunk16 ^ sw) << 4) + within;
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      if (X3) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
+        *reinterpret_cast<uint2*>(dst + q.h_plane_bytes) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+    if (p.stg_bufs != 2) asm volatile("bar.sync 1, 512;" ::: "memory");
+  }
+}
+
+template <int X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB7_hi, const __grid_constant__ CUtensorMap tmB7_lo,
+               const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+               const TcRuParams q) {
+  const TcConvParams& p = q.e;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_t1full[2];
+  __shared__ __align__(8) uint64_t bar_t1empty[2];
+  __shared__ __align__(8) uint64_t bar_t2full[2];
+  __shared__ __align__(8) uint64_t bar_t2empty[2];
+  __shared__ __align__(8) uint64_t bar_hfull;
+  __shared__ __align__(8) uint64_t bar_hempty;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t planes = X3 ? 2u : 1u;
+  const uint32_t sub_bytes = (p.a_bytes + p.b_bytes) * planes;
+  const uint32_t stage_bytes = sub_bytes * (uint32_t)p.kgroup;
+  const uint32_t ring_bytes = stage_bytes * (uint32_t)p.stages;
+  const uint32_t hbuf_u32 = smem0 + ring_bytes;                       // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint8_t* hbuf = smem_raw + (smem0 - smem_u32(smem_raw)) + ring_bytes;
+  const uint32_t h_total = q.h_plane_bytes * planes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB7_hi); tma_prefetch_desc(&tmB1_hi);
+    if (X3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB7_lo); tma_prefetch_desc(&tmB1_lo); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_t1full[i]), 1); mbar_init(smem_u32(&bar_t1empty[i]), 1);
+      mbar_init(smem_u32(&bar_t2full[i]), 1); mbar_init(smem_u32(&bar_t2empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bar_hfull), 1); mbar_init(smem_u32(&bar_hempty), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int n7 = p.KT * q.nk;                          // K blocks of GEMM 1
+  const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int la = q.nbuf - 1;                           // GEMM-1 lookahead in tiles
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      Ring rg;
+      auto produce_conv7 = [&](int i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+        const int j0 = jt * TC_BM + p.in_off[0];
+        int tap = 0, cb = 0;
+        for (int k0 = 0; k0 < n7; k0 += p.kgroup, rg.next(p.stages)) {
+          const int cnt = min(p.kgroup, n7 - k0);
+          const uint32_t s = rg.s;
+          mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 1);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          mbar_expect_tx(full, sub_bytes * (uint32_t)cnt);
+          for (int g = 0; g < cnt; ++g) {
+            const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
+            const uint32_t sb = sa + p.a_bytes * planes;
+            const int c0 = cb * p.BK, row = j0 + tap * p.dil;
+            tma_load_3d(sa, &tmA_hi, full, c0, row, b);
+            if (X3) tma_load_3d(sa + p.a_bytes, &tmA_lo, full, c0, row, b);
+            tma_load_2d(sb, &tmB7_hi, full, c0, tap * p.Cout);
+            if (X3) tma_load_2d(sb + p.b_bytes, &tmB7_lo, full, c0, tap * p.Cout);
+            if (++cb == q.nk) { cb = 0; ++tap; }
+          }
+        }
+      };
+      auto produce_w1 = [&]() {
+        for (int k0 = 0; k0 < q.nk; k0 += p.kgroup, rg.next(p.stages)) {
+          const int cnt = min(p.kgroup, q.nk - k0);
+          const uint32_t s = rg.s;
+          mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 2);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          mbar_expect_tx(full, p.b_bytes * planes * (uint32_t)cnt);
+          for (int g = 0; g < cnt; ++g) {
+            const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + p.a_bytes * planes;
+            tma_load_2d(sb, &tmB1_hi, full, (k0 + g) * p.BK, 0);
+            if (X3) tma_load_2d(sb + p.b_bytes, &tmB1_lo, full, (k0 + g) * p.BK, 0);
+          }
+        }
+      };
+      for (int i = 0; i < la && i < my_tiles; ++i) produce_conv7(i);
+      for (int i = 0; i < my_tiles; ++i) {
+        if (i + la < my_tiles) produce_conv7(i + la);
+        produce_w1();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp; elect.sync issues) =====================
+    const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+    const int ksteps = p.BK / 16;
+    const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
+    const uint32_t a_plane = p.a_bytes >> 4, b_plane = p.b_bytes >> 4, h_plane = q.h_plane_bytes >> 4;
+    Ring rg;
+    auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t apl, uint32_t first) {
+      if (ksteps == 4) umma_ksteps<X3, 4>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
+      else if (ksteps == 2) umma_ksteps<X3, 2>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
+      else umma_ksteps<X3, 1>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
+    };
+    auto gemm1 = [&](int i) {
+      const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+      mbar_wait(smem_u32(&bar_t1empty[buf]), par ^ 1u, 3);
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * p.acc_stride;
+      for (int k0 = 0; k0 < n7; k0 += p.kgroup, rg.next(p.stages)) {
+        const int cnt = min(p.kgroup, n7 - k0);
+        const uint32_t s = rg.s;
+        mbar_wait(smem_u32(&bar_full[s]), rg.par, 4);
+        tc_fence_after();
+        for (int g = 0; g < cnt; ++g) {
+          const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
+          issue(d, (sa & 0x3FFFFu) >> 4, ((sa + p.a_bytes * planes) & 0x3FFFFu) >> 4, a_plane, (k0 + g) != 0);
+        }
+        umma_commit_w(smem_u32(&bar_empty[s]));
+      }
+      umma_commit_w(smem_u32(&bar_t1full[buf]));
+    };
+    auto gemm2 = [&](int i) {
+      const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+      mbar_wait(smem_u32(&bar_hfull), (uint32_t)i & 1u, 5);           // h(i) is in shared memory
+      mbar_wait(smem_u32(&bar_t2empty[buf]), par ^ 1u, 6);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (q.nbuf + buf) * p.acc_stride;
+      for (int k0 = 0; k0 < q.nk; k0 += p.kgroup, rg.next(p.stages)) {
+        const int cnt = min(p.kgroup, q.nk - k0);
+        const uint32_t s = rg.s;
+        mbar_wait(smem_u32(&bar_full[s]), rg.par, 7);
+        tc_fence_after();
+        for (int g = 0; g < cnt; ++g) {
+          const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + p.a_bytes * planes;
+          const uint32_t ha = hbuf_u32 + (uint32_t)(k0 + g) * q.h_block_bytes;
+          issue(d, (ha & 0x3FFFFu) >> 4, (sb & 0x3FFFFu) >> 4, h_plane, (k0 + g) != 0);
+        }
+        umma_commit_w(smem_u32(&bar_empty[s]));
+      }
+      umma_commit_w(smem_u32(&bar_hempty));          // h may be overwritten once these MMAs retire
+      umma_commit_w(smem_u32(&bar_t2full[buf]));
+    };
+    for (int i = 0; i < la && i < my_tiles; ++i) gemm1(i);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i + la < my_tiles) gemm1(i + la);
+      gemm2(i);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    float* stg = reinterpret_cast<float*>(hbuf + h_total);
+    uint32_t chunk_ctr = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+      const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+      // ---- A: acc1 -> h
+      mbar_wait(smem_u32(&bar_t1full[buf]), par, 8);
+      mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);       // GEMM 2 of tile i-1 has read h
+      tc_fence_after();
+      ru_epilogue_h<X3>(q, stg, chunk_ctr, tmem_base + buf * p.acc_stride, hbuf, warp, lane);
+      tc_fence_before();
+      fence_proxy_async();                                                // generic-proxy smem writes -> async proxy (UMMA)
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (threadIdx.x == 64) {
+        mbar_arrive(smem_u32(&bar_t1empty[buf]));
+        mbar_arrive(smem_u32(&bar_hfull));
+      }
+      // ---- B: acc2 -> y
+      mbar_wait(smem_u32(&bar_t2full[buf]), par, 10);
+      tc_fence_after();
+      tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + (q.nbuf + buf) * p.acc_stride, b, 0, jt, 0,
+                       smem_u32(&bar_t2empty[buf]), warp, lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TcRuPlan {
+  TcRuParams q;
+  int x3 = 0, grid = 0;
+  size_t smem = 0;
+  const void* cached_x = nullptr;
+  CUtensorMap mA_hi, mA_lo, mB7_hi, mB7_lo, mB1_hi, mB1_lo;
+  bool b_ready = false;
+};
+
+inline bool tc_ru_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_TC_RU");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// 0 = planned; > 0 = not eligible
+inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const TcWeight& w1, int precision, int out_fmt,
+                      int sm_count, TcRuPlan* plan) {
+  if (!tc_ru_enabled()) return 9;
+  if (!w7.hi || !w1.hi) return 1;
+  if (!(C == 64 || C == 96 || C == 128 || C == 192)) return 2;
+  if (!tc_encode_fn()) return 3;
+  TcRuParams& q = plan->q;
+  memset(&q, 0, sizeof(q));
+  TcConvParams& p = q.e;
+  plan->x3 = precision == 1 ? 1 : 0;
+  const int planes = plan->x3 ? 2 : 1;
+  p.B = B; p.Lin = L; p.Cin = C; p.Cout = C; p.KT = 7; p.in_step = 1; p.dil = dil; p.n_phase = 1;
+  p.Lj = L; p.out_step = 1; p.Lout = L;
+  p.in_off[0] = -3 * dil; p.out_off[0] = 0;
+  p.act = ACT_SNAKE; p.res_mode = 0; p.Tl = 1; p.chunk = 1; p.out_fmt = out_fmt;
+  p.act_plane_elems = (long)B * L * C;
+  p.BN = C;
+  p.BK = (C % 64 == 0) ? 64 : 32;
+  q.nk = C / p.BK;
+  p.n_kblk = q.nk;
+  p.a_bytes = TC_BM * p.BK * 2;
+  p.b_bytes = C * p.BK * 2;
+  p.sbo = 8 * p.BK * 2;
+  p.layout_type = p.BK == 64 ? 2u : 4u;
+  p.acc_stride = C <= 64 ? 64 : (C <= 128 ? 128 : 256);
+  q.nbuf = 4 * p.acc_stride <= 512 ? 2 : 1;
+  p.tmem_cols = 2 * q.nbuf * p.acc_stride;
+  q.h_plane_bytes = TC_BM * C * 2;
+  q.h_block_bytes = TC_BM * p.BK * 2;
+  const uint32_t sub = (p.a_bytes + p.b_bytes) * planes;
+  const int h_total = (int)q.h_plane_bytes * planes;
+  const int avail2 = 232448 - 2048 - 1024 - h_total - TC_STG_BYTES;
+  const int avail1 = avail2 + TC_STG_BYTES / 2;
+  int subs = avail2 / (int)sub;
+  p.stg_bufs = 2;
+  if (subs < 4 && avail1 / (int)sub > subs) { subs = avail1 / (int)sub; p.stg_bufs = 1; }
+  if (subs < 2) return 4;
+  const int cyc = (p.BK / 16) * (plan->x3 ? 3 : 1) * (C / 2);
+  int g = (512 + cyc - 1) / cyc;
+  if (g > 8) g = 8;
+  while (g > 1 && subs / g < 2) --g;
+  p.kgroup = g;
+  p.stages = subs / g;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  p.tiles_j = (L + TC_BM - 1) / TC_BM;
+  p.n_ntiles = 1;
+  long total = (long)B * p.tiles_j;
+  if (total > 0x7fffffffL) return 5;
+  p.total_tiles = (int)total;
+  plan->grid = (int)(total < sm_count ? total : sm_count);
+  plan->smem = (size_t)p.stages * g * sub + h_total + (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
+  plan->cached_x = nullptr;
+  plan->b_ready = false;
+  return 0;
+}
+
+struct TcRuArgs {
+  const void* x_planes;      // snake1(x) as bf16 planes [B, L, C]
+  const float* x_raw;        // x, fp32 (the residual)
+  const float* bias7; const float* alpha2; const float* inv_alpha2;
+  const float* bias1; const float* alpha_next; const float* inv_alpha_next;
+  float* out_raw;            // y fp32 or null
+  void* out_act;             // snake_next(y) planes
+};
+
+inline int tc_ru_launch(TcRuPlan& plan, const TcRuArgs& a, const TcWeight& w7, const TcWeight& w1, cudaStream_t st) {
+  TcRuParams q = plan.q;
+  TcConvParams& p = q.e;
+  q.bias7 = a.bias7; q.alpha2 = a.alpha2; q.inv_alpha2 = a.inv_alpha2;
+  p.bias = a.bias1; p.res = a.x_raw; p.out_raw = a.out_raw; p.out_act = a.out_act; p.alpha = a.alpha_next;
+  p.inv_alpha = a.inv_alpha_next;
+  if (plan.cached_x != a.x_planes) {
+    const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(a.x_planes);
+    const __nv_bfloat16* xl = xh + (size_t)p.B * p.Lin * p.Cin;
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Lin, (cuuint64_t)p.B};
+    cuuint64_t str[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.BK, TC_BM, 1};
+    int rc = tc_encode(&plan.mA_hi, xh, 3, dims, str, box, p.BK);
+    if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 3, dims, str, box, p.BK);
+    if (rc) return rc;
+    plan.cached_x = a.x_planes;
+  }
+  if (!plan.b_ready) {
+    cuuint64_t str[1] = {(cuuint64_t)p.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
+    cuuint64_t d7[2] = {(cuuint64_t)p.Cin, (cuuint64_t)w7.rows};
+    cuuint64_t d1[2] = {(cuuint64_t)p.Cin, (cuuint64_t)w1.rows};
+    int rc = tc_encode(&plan.mB7_hi, w7.hi, 2, d7, str, box, p.BK);
+    if (!rc) rc = tc_encode(&plan.mB7_lo, w7.lo, 2, d7, str, box, p.BK);
+    if (!rc) rc = tc_encode(&plan.mB1_hi, w1.hi, 2, d1, str, box, p.BK);
+    if (!rc) rc = tc_encode(&plan.mB1_lo, w1.lo, 2, d1, str, box, p.BK);
+    if (rc) return rc;
+    plan.b_ready = true;
+  }
+  cudaError_t e;
+  if (plan.x3) {
+    e = cudaFuncSetAttribute(conv_ru_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return -2;
+    conv_ru_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
+                                                                plan.mB1_hi, plan.mB1_lo, q);
+  } else {
+    e = cudaFuncSetAttribute(conv_ru_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return -2;
+    conv_ru_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
+                                                                plan.mB1_hi, plan.mB1_lo, q);
+  }
+  return 0;
+}
+
+}  // namespace b2c

@@ -402,6 +402,14 @@ def _emit_ru(em: Emitter, ru: PackedRU, x_raw, x_act, B, Lx, next_alpha, need_ra
     Returns (y_raw or None, y_act = snake_next(y))."""
     C_ = ru.c7.cout
     f = L.FMT_OF_PREC[prec]
+    if prec != L.PREC_F32 and em.lib.b2c_ru_tc_eligible(em.eng.ctx, ru.c7.wid, ru.c1.wid, prec) == 1:
+        # one fused tcgen05 launch: h = snake2(conv7(x_act)) never leaves shared memory
+        y_raw = em.new(B * Lx * C_) if need_raw else None
+        y_act = em.new(B * Lx * C_)
+        L.check(em.lib.b2c_prog_ru(em.h, ru.c7.wid, ru.a2, ru.c1.wid, em._r(x_act), em._r(x_raw), em._r(y_raw),
+                                   em._r(y_act), next_alpha, B, Lx, ru.c7.dilation, prec, f), "b2c_prog_ru")
+        em.drop(x_act, x_raw)
+        return y_raw, y_act
     h_act = em.new(B * Lx * C_)
     em.conv(ru.c7, x_act, B, Lx, out_act=h_act, alpha=ru.a2, prec=prec, x_fmt=f, act_fmt=f)
     em.drop(x_act)
