@@ -249,6 +249,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int tile = blockIdx.x + i * gridDim.x;
       const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
       const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+      if (i == 0) tc_prefetch_res(p, b, 0, jt, 0);
+      if (i + 1 < my_tiles) {                       // residual rows of the next tile -> L2, a whole tile ahead
+        const int t2 = tile + gridDim.x;
+        const int b2 = t2 / p.tiles_j;
+        tc_prefetch_res(p, b2, 0, t2 - b2 * p.tiles_j, 0);
+      }
       // ---- A: acc1 -> h
       mbar_wait(smem_u32(&bar_t1full[buf]), par, 8);
       mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);       // GEMM 2 of tile i-1 has read h

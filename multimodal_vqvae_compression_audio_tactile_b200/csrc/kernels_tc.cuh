@@ -244,6 +244,23 @@ constexpr int TC_STG_LD = 36;                        // floats per staging row: 
 constexpr int TC_STG_BYTES = 2 * TC_BM * TC_STG_LD * 4;
 
 
+// L2 prefetch of the residual rows of one output tile (issued one tile ahead by the 512 epilogue threads): the
+// epilogue's residual loads are latency-bound otherwise -- only one 32-column chunk (16 KB per SM) is in flight.
+__device__ __forceinline__ void tc_prefetch_res(const TcConvParams& p, int b, int ph, int jt, int nt) {
+  if (!p.res || p.res_mode == 1) return;
+  const int et = threadIdx.x - 64;
+  const int lines_per_row = p.BN >> 5;                       // 128-byte lines of one tile row
+  for (int idx = et; idx < TC_BM * lines_per_row; idx += 32 * TC_EPI_WARPS) {
+    const int row = idx / lines_per_row, seg = idx - row * lines_per_row;
+    const int j = jt * TC_BM + row;
+    const int lo = j * p.out_step + p.out_off[ph];
+    if (j < p.Lj && lo >= 0 && lo < p.Lout) {
+      const float* a = p.res + ((size_t)b * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+}
+
 // Epilogue of one 128 x BN accumulator (16 warps).  Per 32-column chunk: (1) every warp copies its TMEM
 // quadrant (thread = row, 8 columns) into a padded fp32 staging tile in shared memory; (2) after a named
 // barrier the 512 threads re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the
@@ -517,6 +534,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ph = mt % p.n_phase;
       const int b = mt / p.n_phase;
       const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+      if (tcount == 0) tc_prefetch_res(p, b, ph, jt, nt);
+      {
+        const int nx = tile + gridDim.x;
+        if (nx < p.total_tiles) {
+          const int nt2 = nx % p.n_ntiles;
+          int m2 = nx / p.n_ntiles;
+          const int jt2 = m2 % p.tiles_j;
+          m2 /= p.tiles_j;
+          tc_prefetch_res(p, m2 / p.n_phase, m2 % p.n_phase, jt2, nt2);
+        }
+      }
       mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 4);
       tc_fence_after();
       if (p.dbg & 1) {
