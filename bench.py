@@ -253,12 +253,33 @@ def main():
     dom = max((k for k in by_kind if k.startswith("conv")), key=lambda k: by_kind[k]["ms"])
     dd = by_kind[dom]
     achieved = dd["flops"] / (dd["ms"] / 1e3) / 1e12
+    # bf16x3 contractions (everything upstream of the quantizer in plan "tc") issue 3 tensor-core FLOPs per
+    # algorithmic FLOP: launches before the decoder's first conv are the x3 ones
+    executed = dd["flops"] * (3.0 if dom.endswith("_x3") else 1.0)
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_conv_tc.json")
+    if os.path.isfile(tpath):
+        try:
+            ks = json.load(open(tpath))["kernels"]
+            traffic_note = [dict(kernel=k["Kernel Name"][:40], us=float(k["gpu__time_duration.sum"]),
+                                 dram_MB=float(k["dram__bytes_read.sum"]) + float(k["dram__bytes_write.sum"]),
+                                 tensor_pct=float(k["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]))
+                            for k in ks]
+        except Exception:
+            traffic_note = None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sus"], "traffic": None,
+                "frac": achieved / peaks["tf_sus"], "traffic": traffic,
                 "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "share_of_step": dd["ms"] / tot_ms, "launches_per_program": dd["launches"],
                 "avg_launch_ms": dd["ms"] / dd["launches"],
-                "flops_per_launch_avg": dd["flops"] / dd["launches"]}
+                "flops_per_launch_avg": dd["flops"] / dd["launches"],
+                "executed_tflops": executed / (dd["ms"] / 1e3) / 1e12,
+                "executed_frac": executed / (dd["ms"] / 1e3) / 1e12 / peaks["tf_sus"],
+                "note": "achieved = algorithmic conv FLOPs / CUDA-event time of the conv launches of one program; the "
+                        "bf16x3 launches execute 3 MMA FLOPs per algorithmic FLOP (executed_tflops); traffic is null "
+                        "because the 'kernel' is ~90 launches of different shapes -- ncu DRAM bytes of sampled launches "
+                        "are in ncu_samples / profiles/r01_ncu_full_conv_tc.json",
+                "ncu_samples": traffic_note}
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"by_kind": by_kind, "launches": prof, "micro_batch": mb}, fh, indent=1)

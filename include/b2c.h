@@ -194,6 +194,7 @@ int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_by
 #define B2C_KIND_NEAREST 8
 #define B2C_KIND_DAC_RVQ 9
 #define B2C_KIND_MOVE 10
+#define B2C_KIND_CONV_TC_X3 11 /* tcgen05 contraction in bf16x3: 3 MMA FLOPs per algorithmic FLOP */
 int b2c_prog_profile(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext,
                      float* ms, int* kind, double* flops, double* bytes, int cap);
 

@@ -18,7 +18,7 @@ ROWS_DENSE, ROWS_HEAD, ROWS_HEAD_PREV, ROWS_ZERO = 0, 1, 2, 3
 PE_NONE, PE_CHUNK_POS, PE_ROW0, PE_ROW_N = 0, 1, 2, 3
 
 KIND_NAMES = {1: "conv_f32", 2: "conv_tc", 3: "stem", 4: "head", 5: "layernorm", 6: "attention", 7: "rvq",
-              8: "nearest", 9: "dac_rvq", 10: "move"}
+              8: "nearest", 9: "dac_rvq", 10: "move", 11: "conv_tc_x3"}
 
 PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 #: activation storage a contraction of this precision reads

@@ -926,7 +926,7 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
     case OP_CONV_TC: {
       const ConvArgs& a = op.conv;
       double rows = (double)a.B * a.Lout;
-      *kind = op.type == OP_CONV ? B2C_KIND_CONV_F32 : B2C_KIND_CONV_TC;
+      *kind = op.type == OP_CONV ? B2C_KIND_CONV_F32 : (op.precision == B2C_PREC_BF16X3 ? B2C_KIND_CONV_TC_X3 : B2C_KIND_CONV_TC);
       *flops = 2.0 * rows * a.Cout * a.Cin * a.KT;
       double outs = (op.r[2] != B2C_NULL_REF ? 1 : 0) + (op.r[3] != B2C_NULL_REF ? 1 : 0) + (op.r[1] != B2C_NULL_REF ? 1 : 0);
       *bytes = 4.0 * ((double)a.B * a.Lin * a.Cin + rows * a.Cout * outs + (double)a.n_phase * a.KT * a.Cin * a.Cout);
@@ -935,7 +935,7 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
     case OP_RU_TC: {
       const Weight& w = ctx->w[op.wid];
       double rows = (double)op.i[1] * op.i[2], C = w.cin;
-      *kind = B2C_KIND_CONV_TC;
+      *kind = op.precision == B2C_PREC_BF16X3 ? B2C_KIND_CONV_TC_X3 : B2C_KIND_CONV_TC;
       *flops = 2.0 * rows * C * C * 8.0;                       // k = 7 conv + k = 1 conv
       *bytes = 4.0 * (rows * C * (3.0 + (op.r[2] != B2C_NULL_REF ? 1 : 0)) + 8.0 * C * C);   // x_act, x_raw, out_act (+ out_raw)
       break;

@@ -203,3 +203,81 @@ def test_errors(dev):
         net.forward_eval(torch.zeros(1, 1, 100, device=dev), torch.zeros(1, 1, 100, device=dev))
     with pytest.raises(ValueError):
         net.T_DEC(torch.zeros(1, 7, 4, device=dev))
+
+
+def test_cuda_graph_replay_equals_eager(dev, oracle_models):
+    """The batch-1 streaming path (tools/latency.py) replays the program as one CUDA graph: same bits."""
+    name = "zeros_b1k128"
+    case = cases.CODEC_CASES[name]
+    net = gpu_model(oracle_models(name), case)
+    a, t = cases.codec_inputs(dict(case, kind="uniform"))
+    a, t = a.to(dev), t.to(dev)
+    y0 = net.forward_eval(a, t).clone()
+    i0 = net.last_indices.clone()
+    z0 = net.encode_latents(a, t).clone()
+    net.use_cuda_graph = True
+    for _ in range(2):          # first call captures, second replays
+        y1 = net.forward_eval(a, t)
+        assert torch.equal(y1, y0) and torch.equal(net.last_indices, i0)
+        assert torch.equal(net.encode_latents(a, t), z0)
+
+
+def test_odd_frame_length_uses_fp32_kernel_for_ineligible_layers(dev, oracle_models):
+    """T = 9607 makes the stride-2 conv's input length odd: the tcgen05 kernel's 4-D tensor map does not apply,
+    the engine routes that layer through the FP32 kernel (with format conversions) -- results must agree with the
+    all-FP32 plan within the tc tolerance, and with the oracle."""
+    name = "c3_b10k128"
+    case = dict(cases.CODEC_CASES[name], T=9607, B=2)
+    ref = oracle_models(name)
+    a, t = cases.codec_inputs(case)
+    tr = {}
+    y_ref = ref.forward_eval(a, t, None, trace=tr)
+    out = {}
+    for plan in PLANS:
+        net = gpu_model(ref, case, plan)
+        out[plan] = (net.forward_eval(a.to(dev), t.to(dev)).cpu(), net.last_indices.cpu().long())
+        assert tuple(out[plan][0].shape) == tuple(y_ref.shape)
+        ok, n = first_mismatch_is_near_tie(out[plan][1], tr["idx"], tr["margin"], TIE[plan])
+        assert ok, (plan, n)
+        if n == 0:
+            assert float((out[plan][0] - y_ref).abs().max()) < Y_TOL[plan]
+
+
+def test_fused_residual_unit_matches_separate_launches(dev):
+    """b2c_prog_ru (one launch, h in shared memory) against conv k7 + conv k1 launches of the same precision."""
+    from multimodal_vqvae_compression_audio_tactile_b200 import _lib as L
+    from multimodal_vqvae_compression_audio_tactile_b200.engine import Emitter, Engine, _pack_ru
+    torch.manual_seed(3)
+    net = pkg.build_proposed(1, 128)
+    eng = Engine(dev)
+    for mod, Lx, prec in ((net.T_ENC.block[1].block[1], 1000, "bf16x3"), (net.T_ENC.block[2].block[2], 515, "bf16x3"),
+                          (net.T_DEC.model[4].block[3], 777, "bf16"), (net.T_DEC.model[3].block[4], 300, "bf16")):
+        ru = _pack_ru(eng, mod)
+        C_, B = ru.c7.cout, 3
+        pr = L.PRECISIONS[prec]
+        f = L.FMT_OF_PREC[pr]
+        assert eng.lib.b2c_ru_tc_eligible(eng.ctx, ru.c7.wid, ru.c1.wid, pr) == 1
+        n = B * Lx * C_
+        x = (torch.rand(B, Lx, C_, device=dev) * 2 - 1)
+        a_next = eng.pack_vec(torch.rand(C_) + 0.5)
+        res = {}
+        for fused in (True, False):
+            em = Emitter(eng)
+            xa, ya = em.new(n), em.new(n)
+            em.convert(em.ext(1), L.FMT_F32, xa, f, n)
+            if fused:
+                L.check(eng.lib.b2c_prog_ru(em.h, ru.c7.wid, ru.a2, ru.c1.wid, em._r(xa), em._r(em.ext(1)), em._r(em.ext(2)),
+                                            em._r(ya), a_next, B, Lx, ru.c7.dilation, pr, f), "b2c_prog_ru")
+            else:
+                h = em.new(n)
+                em.conv(ru.c7, xa, B, Lx, out_act=h, alpha=ru.a2, prec=pr, x_fmt=f, act_fmt=f)
+                em.conv(ru.c1, h, B, Lx, res=em.ext(1), out_raw=em.ext(2), out_act=ya, alpha=a_next, prec=pr, x_fmt=f, act_fmt=f)
+            em.convert(ya, f, em.ext(3), L.FMT_F32, n)
+            prog = em.finish(3)
+            raw, act = torch.empty(B, Lx, C_, device=dev), torch.empty(B, Lx, C_, device=dev)
+            eng.run(prog, [x.data_ptr(), raw.data_ptr(), act.data_ptr()])
+            torch.cuda.synchronize()
+            res[fused] = (raw.cpu(), act.cpu())
+        # same arithmetic (same MMAs, same epilogue math): only the accumulation grouping of h's bf16 split can differ
+        assert float((res[True][0] - res[False][0]).abs().max()) < 1e-5, (C_, prec)
+        assert float((res[True][1] - res[False][1]).abs().max()) < (2e-2 if prec == "bf16" else 1e-4), (C_, prec)
