@@ -208,6 +208,14 @@ typedef struct {
 int b2c_prog_run_host(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext,
                       const b2c_hostcopy* h2d, int n_h2d, const b2c_hostcopy* d2h, int n_d2h);
 
+/* The same for n_micro equal micro-batches with copies and compute overlapped: ext_sets holds TWO sets of n_ext
+ * device pointers (double-buffered staging, [2][n_ext]); host pointers of h2d / d2h advance by their `bytes` per
+ * micro-batch.  H2D of micro-batch k+1 and D2H of k-1 run on a copy stream owned by the context while the program
+ * of micro-batch k runs on `stream`.  Synchronises both streams before returning. */
+int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext_sets,
+                                int n_ext, const b2c_hostcopy* h2d, int n_h2d, const b2c_hostcopy* d2h, int n_d2h,
+                                int n_micro);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,8 @@ SIGNATURES = {
     "b2c_prog_profile": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                              C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
                              _i]),
+    "b2c_prog_run_host_pipelined": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
+                                         C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i, _i]),
     "b2c_prog_run_host": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                                C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i]),
 }

@@ -61,6 +61,9 @@ struct b2c_ctx {
   std::vector<Weight> w;
   size_t bytes = 0;
   int sm_count = 148;
+  // copy engine side of b2c_prog_run_host_pipelined (created on first use)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 static int upload(b2c_ctx* ctx, const float* host, size_t n, float** dev) {
@@ -91,6 +94,12 @@ extern "C" int b2c_ctx_create(int device, b2c_ctx** out) {
 extern "C" int b2c_ctx_destroy(b2c_ctx* ctx) {
   if (!ctx) return B2C_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
   for (auto& w : ctx->w) {
     if (w.dev) cudaFree(w.dev);
     if (w.bias) cudaFree(w.bias);
@@ -1027,5 +1036,51 @@ extern "C" int b2c_prog_run_host(b2c_prog* p, void* stream, void* workspace, siz
     CUDA_TRY(cudaMemcpyAsync(d2h[i].host, ext[d2h[i].slot - 1], d2h[i].bytes, cudaMemcpyDeviceToHost, st));
   }
   CUDA_TRY(cudaStreamSynchronize(st));
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes,
+                                           void* const* ext_sets, int n_ext, const b2c_hostcopy* h2d, int n_h2d,
+                                           const b2c_hostcopy* d2h, int n_d2h, int n_micro) {
+  if (!p || !ext_sets || n_micro <= 0) return fail(B2C_ERR_ARG, "b2c_prog_run_host_pipelined: bad argument");
+  b2c_ctx* ctx = p->ctx;
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  if (!ctx->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t xs = ctx->copy_stream;
+  for (int i = 0; i < n_h2d; ++i)
+    if (h2d[i].slot < 1 || h2d[i].slot > n_ext || !h2d[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host_pipelined: bad h2d[%d]", i);
+  for (int i = 0; i < n_d2h; ++i)
+    if (d2h[i].slot < 1 || d2h[i].slot > n_ext || !d2h[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host_pipelined: bad d2h[%d]", i);
+  for (int k = 0; k < n_micro; ++k) {
+    const int set = k & 1;
+    void* const* ext = ext_sets + (size_t)set * n_ext;
+    // copy stream: inputs of micro-batch k (the compute stream finished reading this set two micro-batches ago)
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(xs, ctx->ev_done[set], 0));
+    for (int i = 0; i < n_h2d; ++i)
+      CUDA_TRY(cudaMemcpyAsync(ext[h2d[i].slot - 1], (const char*)h2d[i].host + (size_t)k * h2d[i].bytes, h2d[i].bytes,
+                               cudaMemcpyHostToDevice, xs));
+    CUDA_TRY(cudaEventRecord(ctx->ev_in[set], xs));
+    // compute stream: wait for the inputs, and for the D2H that last read this set's outputs
+    CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev_in[set], 0));
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev_out[set], 0));
+    int rc = b2c_prog_run(p, stream, workspace, workspace_bytes, ext, n_ext);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_done[set], cs));
+    // copy stream: results of micro-batch k
+    CUDA_TRY(cudaStreamWaitEvent(xs, ctx->ev_done[set], 0));
+    for (int i = 0; i < n_d2h; ++i)
+      CUDA_TRY(cudaMemcpyAsync((char*)d2h[i].host + (size_t)k * d2h[i].bytes, ext[d2h[i].slot - 1], d2h[i].bytes,
+                               cudaMemcpyDeviceToHost, xs));
+    CUDA_TRY(cudaEventRecord(ctx->ev_out[set], xs));
+  }
+  CUDA_TRY(cudaStreamSynchronize(xs));
+  CUDA_TRY(cudaStreamSynchronize(cs));
   return B2C_OK;
 }

@@ -230,6 +230,7 @@ struct TcConvParams {
   int n_rows, n_codes;
   // slab kernel (conv_tc2_kernel): MT m-tiles per work item share one activation slab and every weight tile
   int MT, groups_j, slab_rows, box_rows, n_aloads, SA, SB;
+  int epi_groups; // 2: the 16 epilogue warps work as two independent groups of 8, one per TMEM accumulator buffer
   int kgroup;     // K blocks per pipeline stage of the generic kernel (one mbarrier hand-off per kgroup blocks)
   int dbg;        // B2C_TC_DEBUG bit mask (timing experiments only): 1 skip epilogue work, 2 no TMA, 4 no MMA
   int stg_bufs;   // epilogue staging tiles: 2 (one barrier per chunk) or 1 (two barriers, frees 18 KB for the rings)
@@ -346,6 +347,114 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
       }
     }
     if (p.stg_bufs != 2) asm volatile("bar.sync 1, 512;" ::: "memory");   // the single tile is rewritten next chunk
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-group epilogue.  The 16 epilogue warps form two groups of 8 (256 threads); group g owns the tiles whose
+// accumulator is TMEM buffer g, its own staging tile and its own named barrier (id 1 + g), so one group can be
+// in its TMEM-load / barrier phase while the other computes and stores: with all 16 warps in lock step
+// (tc_epilogue_tile) nothing overlapped the latency of either phase.
+// Mapping inside a group: TMEM -> staging: warp = (lane quadrant, 16-column half); row-major phase: thread =
+// (float4 column group cq, row r0 + 32 i, i < 4).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_group_sync(int g) {
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+}
+__device__ __forceinline__ void tc_prefetch_res_g(const TcConvParams& p, int b, int ph, int jt, int nt) {
+  if (!p.res || p.res_mode == 1) return;
+  const int et = (threadIdx.x - 64) & 255;
+  const int lines_per_row = p.BN >> 5;
+  for (int idx = et; idx < TC_BM * lines_per_row; idx += 256) {
+    const int row = idx / lines_per_row, seg = idx - row * lines_per_row;
+    const int j = jt * TC_BM + row;
+    const int lo = j * p.out_step + p.out_off[ph];
+    if (j < p.Lj && lo >= 0 && lo < p.Lout) {
+      const float* a = p.res + ((size_t)b * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float* stg_g, int g, uint32_t t_acc, int b, int ph,
+                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
+  const int wg = (warp - 2) & 7;
+  const int quad = warp & 3;
+  const int half = wg >> 2;
+  const int et = (threadIdx.x - 64) & 255;
+  const int cq = et & 7;
+  const int r0 = et >> 3;               // rows r0 + 32 i
+  const int nchunks = p.BN >> 5;
+  bool valid[4];
+  size_t orow[4], rrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = jt * TC_BM + r0 + 32 * i;
+    const int lo = j * p.out_step + p.out_off[ph];
+    valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+    const int los = valid[i] ? lo : 0;
+    orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
+    rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
+  }
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + half * 16;
+  for (int c = 0; c < nchunks; ++c) {
+    const int co = nt * p.BN + c * 32 + cq * 4;
+    float4 rr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      rr[i] = (p.res && valid[i]) ? __ldg(reinterpret_cast<const float4*>(p.res + rrow[i] + co))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
+    if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+    if (p.out_act && p.act == ACT_SNAKE) {
+      al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
+      ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+    }
+    {
+      float v[16];
+      tmem_ld16(t_src + c * 32, v);
+      float* dst = stg_g + (quad * 32 + lane) * TC_STG_LD + half * 16;
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+    }
+    const bool last = (c == nchunks - 1) && tempty_bar != 0;
+    if (last) tc_fence_before();
+    epi_group_sync(g);
+    if (last && et == 0) mbar_arrive(tempty_bar);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!valid[i]) continue;
+      float4 a = *reinterpret_cast<const float4*>(stg_g + (r0 + 32 * i) * TC_STG_LD + cq * 4);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
+      if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
+      if (p.out_act) {
+        float4 w;
+        if (p.act == ACT_SNAKE) {
+          w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
+          w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+        } else {
+          w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
+          w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
+        }
+        if (p.out_fmt == FMT_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + orow[i] + co) = w;
+        } else {
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
+          __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_act) + orow[i] + co;
+          *reinterpret_cast<uint2*>(oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
+                                                     *reinterpret_cast<const uint32_t*>(&h23));
+          if (p.out_fmt == FMT_PLANES) {
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
+            *reinterpret_cast<uint2*>(oh + p.act_plane_elems) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          }
+        }
+      }
+    }
+    epi_group_sync(g);   // the group's staging tile is rewritten by the next chunk
   }
 }
 
@@ -525,37 +634,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the bias / residual loads
     // and the raw / activated stores are coalesced.  Two staging tiles alternate: one barrier per chunk.
     float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
-    uint32_t tcount = 0, chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const int nt = tile % p.n_ntiles;
-      int mt = tile / p.n_ntiles;
-      const int jt = mt % p.tiles_j;
-      mt /= p.tiles_j;
-      const int ph = mt % p.n_phase;
-      const int b = mt / p.n_phase;
-      const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
-      if (tcount == 0) tc_prefetch_res(p, b, ph, jt, nt);
-      {
-        const int nx = tile + gridDim.x;
-        if (nx < p.total_tiles) {
-          const int nt2 = nx % p.n_ntiles;
-          int m2 = nx / p.n_ntiles;
-          const int jt2 = m2 % p.tiles_j;
-          m2 /= p.tiles_j;
-          tc_prefetch_res(p, m2 / p.n_phase, m2 % p.n_phase, jt2, nt2);
+    if (EPI == 0 && p.epi_groups == 2) {
+      // two independent groups of 8 warps: group g drains TMEM buffer g (tiles g, g + 2, ... of this CTA)
+      const int g = (warp - 2) >> 3;
+      float* stg_g = stg + g * (TC_BM * TC_STG_LD);
+      auto coords = [&](int tile, int& b, int& ph, int& jt, int& nt) {
+        nt = tile % p.n_ntiles;
+        int mt = tile / p.n_ntiles;
+        jt = mt % p.tiles_j;
+        mt /= p.tiles_j;
+        ph = mt % p.n_phase;
+        b = mt / p.n_phase;
+      };
+      uint32_t use = 0;   // how many times this group's TMEM buffer has been used
+      for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, ++use) {
+        int b, ph, jt, nt;
+        coords(tile, b, ph, jt, nt);
+        if (use == 0) tc_prefetch_res_g(p, b, ph, jt, nt);
+        if (tile + 2 * (int)gridDim.x < p.total_tiles) {
+          int b2, ph2, jt2, nt2;
+          coords(tile + 2 * gridDim.x, b2, ph2, jt2, nt2);
+          tc_prefetch_res_g(p, b2, ph2, jt2, nt2);
+        }
+        mbar_wait(smem_u32(&bar_tfull[g]), use & 1u, 4);
+        tc_fence_after();
+        if (p.dbg & 1) {
+          tc_fence_before();
+          epi_group_sync(g);
+          if (((threadIdx.x - 64) & 255) == 0) mbar_arrive(smem_u32(&bar_tempty[g]));
+        } else {
+          tc_epilogue_tile_g(p, stg_g, g, tmem_base + g * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[g]), warp, lane);
         }
       }
-      mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 4);
-      tc_fence_after();
-      if (p.dbg & 1) {
-        tc_fence_before();
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (threadIdx.x == 64) mbar_arrive(smem_u32(&bar_tempty[acc]));
-      } else if (EPI == 0)
-        tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
-                         warp, lane);
-      else
-        tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, jt, nt, smem_u32(&bar_tempty[acc]), warp, lane);
+    } else {
+      uint32_t tcount = 0, chunk_ctr = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const int nt = tile % p.n_ntiles;
+        int mt = tile / p.n_ntiles;
+        const int jt = mt % p.tiles_j;
+        mt /= p.tiles_j;
+        const int ph = mt % p.n_phase;
+        const int b = mt / p.n_phase;
+        const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        if (tcount == 0) tc_prefetch_res(p, b, ph, jt, nt);
+        {
+          const int nx = tile + gridDim.x;
+          if (nx < p.total_tiles) {
+            const int nt2 = nx % p.n_ntiles;
+            int m2 = nx / p.n_ntiles;
+            const int jt2 = m2 % p.tiles_j;
+            m2 /= p.tiles_j;
+            tc_prefetch_res(p, m2 / p.n_phase, m2 % p.n_phase, jt2, nt2);
+          }
+        }
+        mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 4);
+        tc_fence_after();
+        if (p.dbg & 1) {
+          tc_fence_before();
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (threadIdx.x == 64) mbar_arrive(smem_u32(&bar_tempty[acc]));
+        } else if (EPI == 0)
+          tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
+                           warp, lane);
+        else
+          tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, jt, nt, smem_u32(&bar_tempty[acc]), warp, lane);
+      }
     }
   }
   tc_fence_before();
@@ -924,6 +1067,17 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   uint32_t stage = 0;
   int stages = 0;
   p.stg_bufs = 2;
+  {
+    // Two independent epilogue groups (one per TMEM buffer) overlap the load and store phases of consecutive
+    // tiles -- a gain where the epilogue dominates (k = 1 convs, up-convs: -12..-16 %), a loss where a tile's MMAs
+    // are long, because a 256-thread group takes twice as long to release its buffer (128-wide bf16x3 k = 7:
+    // +16 %).  Rule from the B200 A/B run: groups when the MMAs of a tile take <= ~1000 tensor-pipe cycles per
+    // 32-column chunk of epilogue work.
+    const long mma_cyc = (long)a.KT * (a.Cin / 16) * (plan->x3 ? 3 : 1) * (bn / 2);
+    p.epi_groups = mma_cyc <= 1000L * (bn / 32) ? 2 : 1;
+    const char* e = getenv("B2C_TC_EPI2");
+    if (e) p.epi_groups = e[0] == '0' ? 1 : 2;
+  }
   for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= 32; bk -= 32) {
     p.BK = bk;
     p.a_bytes = TC_BM * bk * 2;
@@ -931,7 +1085,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
     stage = (p.a_bytes + p.b_bytes) * (plan->x3 ? 2 : 1);
     stages = budget / (int)stage;
     // give up the second staging tile when that buys one more K block in flight
-    if (stages < 4 && budget1 / (int)stage > stages) { stages = budget1 / (int)stage; p.stg_bufs = 1; }
+    if (p.epi_groups == 1 && stages < 4 && budget1 / (int)stage > stages) { stages = budget1 / (int)stage; p.stg_bufs = 1; }
     else p.stg_bufs = 2;
     if (stages >= 3 || bk == 32) break;
   }

@@ -214,6 +214,20 @@ class Engine:
                                            arr, len(ext_ptrs), hin, len(h2d), hout, len(d2h)), "b2c_prog_run_host")
 
 
+    def run_host_pipelined(self, prog: Program, ext_sets, h2d, d2h, n_micro: int):
+        """n_micro equal micro-batches, copies overlapped with compute (b2c_prog_run_host_pipelined).
+        ext_sets: two lists of device pointers; h2d / d2h: (host_ptr of micro-batch 0, slot, bytes per micro-batch)."""
+        ws = self.workspace(prog.ws_bytes)
+        n_ext = len(ext_sets[0])
+        arr = (C.c_void_p * (2 * n_ext))(*(list(ext_sets[0]) + list(ext_sets[1])))
+        hin = (L.HostCopy * max(len(h2d), 1))(*[L.HostCopy(p, s, n) for p, s, n in h2d])
+        hout = (L.HostCopy * max(len(d2h), 1))(*[L.HostCopy(p, s, n) for p, s, n in d2h])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.b2c_prog_run_host_pipelined(prog.handle, C.c_void_p(stream), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                     arr, n_ext, hin, len(h2d), hout, len(d2h), n_micro),
+                "b2c_prog_run_host_pipelined")
+
+
 class Emitter:
     """Builds one program.  Buffers are workspace offsets (ints) or ('ext', slot, off)."""
 

@@ -631,22 +631,34 @@ class ProposedEval(_Top):
         key = ("hoststage", mb, T, use)
         st = eng.programs.get(key)
         if st is None:
-            st = eng.programs[key] = dict(
+            st = eng.programs[key] = [dict(
                 a=torch.empty(mb, T, device=dev), t=torch.empty(mb, T, device=dev),
                 y=torch.empty(mb, Lout, device=dev), idx=torch.empty(mb, max(use, 1), Tl, device=dev, dtype=torch.int32),
-                codes=torch.empty(mb, n_q, Tl, device=dev, dtype=torch.int32))
+                codes=torch.empty(mb, n_q, Tl, device=dev, dtype=torch.int32)) for _ in range(2)]
+        exts = [[s_["a"].data_ptr(), s_["t"].data_ptr(), s_["y"].data_ptr(), s_["idx"].data_ptr(), s_["codes"].data_ptr(), 0]
+                for s_ in st]
         h2d_b = d2h_b = 0
+
+        def copies(b0, nb):
+            h2d = [(a_host[b0:].data_ptr(), 1, nb * T * 4), (t_host[b0:].data_ptr(), 2, nb * T * 4)]
+            d2h = [(y_out[b0:].data_ptr(), 3, nb * Lout * 4)]
+            if use > 0:
+                d2h.append((idx_out[b0:].data_ptr(), 4, nb * use * Tl * 4))
+            return h2d, d2h
+
         with torch.cuda.device(dev):
-            for b0 in range(0, B, mb):
-                nb = min(mb, B - b0)
+            n_full = B // mb
+            if n_full > 0:          # equal micro-batches: H2D / D2H overlapped with compute on a copy stream
+                prog = self.program(eng, pk, mb, T, use, decode=True, latents_cm=False)
+                h2d, d2h = copies(0, mb)
+                eng.run_host_pipelined(prog, exts, h2d, d2h, n_full)
+                h2d_b += n_full * sum(x[2] for x in h2d)
+                d2h_b += n_full * sum(x[2] for x in d2h)
+            if B - n_full * mb > 0:  # ragged tail
+                nb, b0 = B - n_full * mb, n_full * mb
                 prog = self.program(eng, pk, nb, T, use, decode=True, latents_cm=False)
-                ext = [st["a"].data_ptr(), st["t"].data_ptr(), st["y"].data_ptr(), st["idx"].data_ptr(),
-                       st["codes"].data_ptr(), 0]
-                h2d = [(a_host[b0:].data_ptr(), 1, nb * T * 4), (t_host[b0:].data_ptr(), 2, nb * T * 4)]
-                d2h = [(y_out[b0:].data_ptr(), 3, nb * Lout * 4)]
-                if use > 0:
-                    d2h.append((idx_out[b0:].data_ptr(), 4, nb * use * Tl * 4))
-                eng.run_host(prog, ext, h2d, d2h)
+                h2d, d2h = copies(b0, nb)
+                eng.run_host(prog, exts[0], h2d, d2h)
                 h2d_b += sum(x[2] for x in h2d)
                 d2h_b += sum(x[2] for x in d2h)
         self.last_host_bytes = (h2d_b, d2h_b)
