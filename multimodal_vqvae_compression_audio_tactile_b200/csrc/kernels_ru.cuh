@@ -84,6 +84,60 @@ __device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, float* stg, u
   }
 }
 
+// the same for one 8-warp epilogue group (see tc_epilogue_tile_g): thread = (float4 column group, rows r0 + 32 i)
+template <int X3>
+__device__ __forceinline__ void ru_epilogue_h_g(const TcRuParams& q, float* stg_g, int g, uint32_t t_acc, uint8_t* hbuf,
+                                                int warp, int lane) {
+  const TcConvParams& p = q.e;
+  const int wg = (warp - 2) & 7;
+  const int quad = warp & 3;
+  const int half = wg >> 2;
+  const int et = (threadIdx.x - 64) & 255;
+  const int cq = et & 7;
+  const int r0 = et >> 3;
+  const int nchunks = p.BN >> 5;
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + half * 16;
+  const uint32_t row_bytes = (uint32_t)p.BK * 2;
+  for (int c = 0; c < nchunks; ++c) {
+    const int co = c * 32 + cq * 4;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q.bias7) bb = __ldg(reinterpret_cast<const float4*>(q.bias7 + co));
+    const float4 al = __ldg(reinterpret_cast<const float4*>(q.alpha2 + co));
+    const float4 ia = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + co));
+    {
+      float v[16];
+      tmem_ld16(t_src + c * 32, v);
+      float* dst = stg_g + (quad * 32 + lane) * TC_STG_LD + half * 16;
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+    }
+    epi_group_sync(g);
+    const int kb = co / p.BK, cin = co - kb * p.BK;
+    const uint32_t chunk16 = (uint32_t)cin >> 3, within = ((uint32_t)cin & 7u) * 2u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 32 * i;
+      float4 a = *reinterpret_cast<const float4*>(stg_g + r * TC_STG_LD + cq * 4);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      float4 w;
+      w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
+      w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+      const uint32_t sw = p.BK == 64 ? ((uint32_t)r & 7u) : (((uint32_t)r >> 1) & 3u);
+      uint8_t* dst = hbuf + (uint32_t)kb * q.h_block_bytes + (uint32_t)r * row_bytes + ((chunk16 ^ sw) << 4) + within;
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      if (X3) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
+        *reinterpret_cast<uint2*>(dst + q.h_plane_bytes) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+    epi_group_sync(g);
+  }
+}
+
 template <int X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -245,6 +299,38 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== epilogue warps =====================
     float* stg = reinterpret_cast<float*>(hbuf + h_total);
     uint32_t chunk_ctr = 0;
+    if (q.nbuf == 2 && p.epi_groups == 2) {
+      // two independent 8-warp groups: group g serves this CTA's tiles i = g, g + 2, ... (TMEM buffers acc1[g], acc2[g]);
+      // epilogue B of tile i then overlaps epilogue A of tile i + 1.  The single h buffer is handed over by hfull / hempty.
+      const int g = (warp - 2) >> 3;
+      float* stg_g = stg + g * (TC_BM * TC_STG_LD);
+      const bool leader = ((threadIdx.x - 64) & 255) == 0;
+      for (int i = g; i < my_tiles; i += 2) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        if (i < 2) tc_prefetch_res_g(p, b, 0, jt, 0);
+        if (i + 2 < my_tiles) {
+          const int t2 = tile + 2 * gridDim.x;
+          const int b2 = t2 / p.tiles_j;
+          tc_prefetch_res_g(p, b2, 0, t2 - b2 * p.tiles_j, 0);
+        }
+        mbar_wait(smem_u32(&bar_t1full[g]), par, 8);
+        mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);
+        tc_fence_after();
+        ru_epilogue_h_g<X3>(q, stg_g, g, tmem_base + g * p.acc_stride, hbuf, warp, lane);
+        tc_fence_before();
+        fence_proxy_async();
+        epi_group_sync(g);
+        if (leader) {
+          mbar_arrive(smem_u32(&bar_t1empty[g]));
+          mbar_arrive(smem_u32(&bar_hfull));
+        }
+        mbar_wait(smem_u32(&bar_t2full[g]), par, 10);
+        tc_fence_after();
+        tc_epilogue_tile_g(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
+      }
+    } else
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
@@ -349,6 +435,10 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   p.kgroup = g;
   p.stages = subs / g;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  {
+    const char* e = getenv("B2C_TC_EPI2");
+    p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !(e && e[0] == '0')) ? 2 : 1;
+  }
   p.tiles_j = (L + TC_BM - 1) / TC_BM;
   p.n_ntiles = 1;
   long total = (long)B * p.tiles_j;
