@@ -25,6 +25,11 @@ struct TcRuParams {
   int nbuf;                  // TMEM accumulator buffers per GEMM (2 or 1)
   uint32_t h_plane_bytes;    // 128 * C * 2
   uint32_t h_block_bytes;    // 128 * BK * 2
+  // slab mode (GEMM 1): per channel block ONE activation slab of 128 + 6*dil rows serves the 7 taps (descriptor row
+  // offsets, as conv_tc2_kernel); the TMA ring then carries weight tiles only.  Halves the L2 -> SM traffic that
+  // bounds the 64-channel bf16x3 units (ncu: ~7 TB/s of L2 reads at 20 % tensor activity).
+  int slab;
+  uint32_t slab_plane_bytes; // slab_rows * BK * 2
 };
 
 // epilogue A of one tile: TMEM acc1 -> staging -> (+b7, snake2, bf16 split) -> swizzled K-major h in shared memory
@@ -154,16 +159,22 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_t2empty[2];
   __shared__ __align__(8) uint64_t bar_hfull;
   __shared__ __align__(8) uint64_t bar_hempty;
+  __shared__ __align__(8) uint64_t bar_afull[2];
+  __shared__ __align__(8) uint64_t bar_aempty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t planes = X3 ? 2u : 1u;
-  const uint32_t sub_bytes = (p.a_bytes + p.b_bytes) * planes;
+  const uint32_t a_in_ring = q.slab ? 0u : p.a_bytes * planes;       // bytes of the A part of a ring sub-block
+  const uint32_t sub_bytes = a_in_ring + p.b_bytes * planes;
   const uint32_t stage_bytes = sub_bytes * (uint32_t)p.kgroup;
   const uint32_t ring_bytes = stage_bytes * (uint32_t)p.stages;
-  const uint32_t hbuf_u32 = smem0 + ring_bytes;                       // 1024-aligned (stage sizes are multiples of 1 KB)
-  uint8_t* hbuf = smem_raw + (smem0 - smem_u32(smem_raw)) + ring_bytes;
+  const uint32_t slab_slot = q.slab_plane_bytes * planes;
+  const uint32_t slab_u32 = smem0 + ring_bytes;                       // two slab slots (slab mode), then h, then staging
+  const uint32_t pre_h = ring_bytes + (q.slab ? 2u * slab_slot : 0u);
+  const uint32_t hbuf_u32 = smem0 + pre_h;                            // 1024-aligned (all pieces are multiples of 1 KB)
+  uint8_t* hbuf = smem_raw + (smem0 - smem_u32(smem_raw)) + pre_h;
   const uint32_t h_total = q.h_plane_bytes * planes;
 
   if (warp == 0 && lane == 0) {
@@ -175,6 +186,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(smem_u32(&bar_t2full[i]), 1); mbar_init(smem_u32(&bar_t2empty[i]), 1);
     }
     mbar_init(smem_u32(&bar_hfull), 1); mbar_init(smem_u32(&bar_hempty), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aempty[i]), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -195,8 +207,44 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      Ring rg;
+      Ring rg, ra;
+      // slab mode: steps = (tile, channel block) in order; the slab of step s + 1 is requested before the weight
+      // tiles of step s
+      auto issue_slab = [&](int step) {
+        const int i = step / q.nk, cb = step - i * q.nk;
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+        const uint32_t sa = ra.s;
+        mbar_wait(smem_u32(&bar_aempty[sa]), ra.par ^ 1u, 11);
+        const uint32_t full = smem_u32(&bar_afull[sa]);
+        mbar_expect_tx(full, slab_slot);
+        const uint32_t dst = slab_u32 + sa * slab_slot;
+        tma_load_3d(dst, &tmA_hi, full, cb * p.BK, jt * TC_BM + p.in_off[0], b);
+        if (X3) tma_load_3d(dst + q.slab_plane_bytes, &tmA_lo, full, cb * p.BK, jt * TC_BM + p.in_off[0], b);
+        ra.next(2);
+      };
+      const int total_steps = my_tiles * q.nk;
+      if (q.slab && total_steps > 0) issue_slab(0);
+      auto produce_conv7_slab = [&](int i) {
+        for (int cb = 0; cb < q.nk; ++cb) {
+          const int step = i * q.nk + cb;
+          if (step + 1 < total_steps) issue_slab(step + 1);
+          for (int k0 = 0; k0 < p.KT; k0 += p.kgroup, rg.next(p.stages)) {
+            const int cnt = min(p.kgroup, p.KT - k0);
+            const uint32_t s = rg.s;
+            mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 1);
+            const uint32_t full = smem_u32(&bar_full[s]);
+            mbar_expect_tx(full, sub_bytes * (uint32_t)cnt);
+            for (int g = 0; g < cnt; ++g) {
+              const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes;
+              tma_load_2d(sb, &tmB7_hi, full, cb * p.BK, (k0 + g) * p.Cout);
+              if (X3) tma_load_2d(sb + p.b_bytes, &tmB7_lo, full, cb * p.BK, (k0 + g) * p.Cout);
+            }
+          }
+        }
+      };
       auto produce_conv7 = [&](int i) {
+        if (q.slab) { produce_conv7_slab(i); return; }
         const int tile = blockIdx.x + i * gridDim.x;
         const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
         const int j0 = jt * TC_BM + p.in_off[0];
@@ -227,7 +275,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t full = smem_u32(&bar_full[s]);
           mbar_expect_tx(full, p.b_bytes * planes * (uint32_t)cnt);
           for (int g = 0; g < cnt; ++g) {
-            const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + p.a_bytes * planes;
+            const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + a_in_ring;
             tma_load_2d(sb, &tmB1_hi, full, (k0 + g) * p.BK, 0);
             if (X3) tma_load_2d(sb + p.b_bytes, &tmB1_lo, full, (k0 + g) * p.BK, 0);
           }
@@ -245,7 +293,9 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ksteps = p.BK / 16;
     const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
     const uint32_t a_plane = p.a_bytes >> 4, b_plane = p.b_bytes >> 4, h_plane = q.h_plane_bytes >> 4;
-    Ring rg;
+    Ring rg, ra;
+    const uint32_t slab_plane = q.slab_plane_bytes >> 4;
+    const uint32_t tap_step = ((uint32_t)p.dil * (uint32_t)p.BK * 2u) >> 4;     // descriptor units per tap (slab mode)
     auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t apl, uint32_t first) {
       if (ksteps == 4) umma_ksteps<X3, 4>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else if (ksteps == 2) umma_ksteps<X3, 2>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
@@ -256,6 +306,28 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(smem_u32(&bar_t1empty[buf]), par ^ 1u, 3);
       tc_fence_after();
       const uint32_t d = tmem_base + buf * p.acc_stride;
+      if (q.slab) {
+        for (int cb = 0; cb < q.nk; ++cb, ra.next(2)) {
+          const uint32_t sa = ra.s;
+          mbar_wait(smem_u32(&bar_afull[sa]), ra.par, 12);
+          tc_fence_after();
+          const uint32_t slab_lo = ((slab_u32 + sa * slab_slot) & 0x3FFFFu) >> 4;
+          for (int k0 = 0; k0 < p.KT; k0 += p.kgroup, rg.next(p.stages)) {
+            const int cnt = min(p.kgroup, p.KT - k0);
+            const uint32_t s = rg.s;
+            mbar_wait(smem_u32(&bar_full[s]), rg.par, 4);
+            tc_fence_after();
+            for (int g = 0; g < cnt; ++g) {
+              const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes;
+              issue(d, slab_lo + (uint32_t)(k0 + g) * tap_step, (sb & 0x3FFFFu) >> 4, slab_plane, (cb | (k0 + g)) != 0);
+            }
+            umma_commit_w(smem_u32(&bar_empty[s]));
+          }
+          umma_commit_w(smem_u32(&bar_aempty[sa]));
+        }
+        umma_commit_w(smem_u32(&bar_t1full[buf]));
+        return;
+      }
       for (int k0 = 0; k0 < n7; k0 += p.kgroup, rg.next(p.stages)) {
         const int cnt = min(p.kgroup, n7 - k0);
         const uint32_t s = rg.s;
@@ -281,7 +353,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(smem_u32(&bar_full[s]), rg.par, 7);
         tc_fence_after();
         for (int g = 0; g < cnt; ++g) {
-          const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + p.a_bytes * planes;
+          const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + a_in_ring;
           const uint32_t ha = hbuf_u32 + (uint32_t)(k0 + g) * q.h_block_bytes;
           issue(d, (ha & 0x3FFFFu) >> 4, (sb & 0x3FFFFu) >> 4, h_plane, (k0 + g) != 0);
         }
@@ -408,33 +480,57 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   p.act = ACT_SNAKE; p.res_mode = 0; p.Tl = 1; p.chunk = 1; p.out_fmt = out_fmt;
   p.act_plane_elems = (long)B * L * C;
   p.BN = C;
-  p.BK = (C % 64 == 0) ? 64 : 32;
-  q.nk = C / p.BK;
-  p.n_kblk = q.nk;
-  p.a_bytes = TC_BM * p.BK * 2;
-  p.b_bytes = C * p.BK * 2;
-  p.sbo = 8 * p.BK * 2;
-  p.layout_type = p.BK == 64 ? 2u : 4u;
   p.acc_stride = C <= 64 ? 64 : (C <= 128 ? 128 : 256);
   q.nbuf = 4 * p.acc_stride <= 512 ? 2 : 1;
   p.tmem_cols = 2 * q.nbuf * p.acc_stride;
   q.h_plane_bytes = TC_BM * C * 2;
-  q.h_block_bytes = TC_BM * p.BK * 2;
-  const uint32_t sub = (p.a_bytes + p.b_bytes) * planes;
   const int h_total = (int)q.h_plane_bytes * planes;
-  const int avail2 = 232448 - 2048 - 1024 - h_total - TC_STG_BYTES;
-  const int avail1 = avail2 + TC_STG_BYTES / 2;
-  int subs = avail2 / (int)sub;
-  p.stg_bufs = 2;
-  if (subs < 4 && avail1 / (int)sub > subs) { subs = avail1 / (int)sub; p.stg_bufs = 1; }
-  if (subs < 2) return 4;
-  const int cyc = (p.BK / 16) * (plan->x3 ? 3 : 1) * (C / 2);
-  int g = (512 + cyc - 1) / cyc;
-  if (g > 8) g = 8;
-  while (g > 1 && subs / g < 2) --g;
-  p.kgroup = g;
-  p.stages = subs / g;
-  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  // Slab mode halves the L2 -> SM traffic but measured no faster on B200 (64-ch bf16x3: 0.289 vs 0.289 ms, 128-ch:
+  // 0.398 vs 0.334 ms): these units are bound by per-tile pipeline hand-offs, not by L2 bandwidth.  Off by default
+  // (B2C_RU_SLAB=1 enables it for experiments).
+  bool want_slab = false;
+  {
+    const char* e = getenv("B2C_RU_SLAB");
+    if (e && e[0] == '1') want_slab = true;
+  }
+  bool done = false;
+  for (int slab = want_slab ? 1 : 0; slab >= 0 && !done; --slab) {
+    for (int bk = (C % 64 == 0) ? 64 : 32; bk >= 32 && !done; bk -= 32) {
+      p.BK = bk;
+      q.nk = C / bk;
+      p.n_kblk = q.nk;
+      p.a_bytes = TC_BM * bk * 2;
+      p.b_bytes = C * bk * 2;
+      p.sbo = 8 * bk * 2;
+      p.layout_type = bk == 64 ? 2u : 4u;
+      q.h_block_bytes = TC_BM * bk * 2;
+      int slab_rows = (TC_BM + 6 * dil + 15) / 16 * 16;
+      if (slab && slab_rows > 256) continue;
+      q.slab = slab;
+      q.slab_plane_bytes = slab ? (uint32_t)slab_rows * bk * 2 : 0u;
+      p.slab_rows = slab_rows; p.box_rows = slab ? slab_rows : TC_BM;
+      const uint32_t sub = (slab ? 0u : p.a_bytes * planes) + p.b_bytes * planes;
+      const int fixed = h_total + (slab ? 2 * (int)q.slab_plane_bytes * planes : 0);
+      const int avail2 = 232448 - 2048 - 1024 - fixed - TC_STG_BYTES;
+      const int avail1 = avail2 + TC_STG_BYTES / 2;
+      int subs = avail2 / (int)sub;
+      p.stg_bufs = 2;
+      if (subs < 4 && avail1 > 0 && avail1 / (int)sub > subs) { subs = avail1 / (int)sub; p.stg_bufs = 1; }
+      if (avail2 <= 0 && avail1 <= 0) continue;
+      if (subs < (slab ? 4 : 2)) continue;
+      const int cyc = (bk / 16) * (plan->x3 ? 3 : 1) * (C / 2);
+      int g = (512 + cyc - 1) / cyc;
+      if (g > 8) g = 8;
+      if (slab && g > 7) g = 7;
+      while (g > 1 && subs / g < 2) --g;
+      p.kgroup = g;
+      p.stages = subs / g;
+      if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+      plan->smem = (size_t)p.stages * g * sub + fixed + (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
+      done = true;
+    }
+  }
+  if (!done) return 4;
   {
     const char* e = getenv("B2C_TC_EPI2");
     p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !(e && e[0] == '0')) ? 2 : 1;
@@ -445,7 +541,6 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   if (total > 0x7fffffffL) return 5;
   p.total_tiles = (int)total;
   plan->grid = (int)(total < sm_count ? total : sm_count);
-  plan->smem = (size_t)p.stages * g * sub + h_total + (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
   plan->cached_x = nullptr;
   plan->b_ready = false;
   return 0;
@@ -471,7 +566,7 @@ inline int tc_ru_launch(TcRuPlan& plan, const TcRuArgs& a, const TcWeight& w7, c
     const __nv_bfloat16* xl = xh + (size_t)p.B * p.Lin * p.Cin;
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Lin, (cuuint64_t)p.B};
     cuuint64_t str[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)p.BK, TC_BM, 1};
+    cuuint32_t box[3] = {(cuuint32_t)p.BK, (cuuint32_t)p.box_rows, 1};
     int rc = tc_encode(&plan.mA_hi, xh, 3, dims, str, box, p.BK);
     if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 3, dims, str, box, p.BK);
     if (rc) return rc;
