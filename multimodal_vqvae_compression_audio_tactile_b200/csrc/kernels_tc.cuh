@@ -471,18 +471,35 @@ __device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float*
   const int cpp = p.BN >> 2;                       // codes per quarter (multiple of 16)
   const int col0 = nt * p.BN + part * cpp;
   const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + part * cpp;
+  // 0.5|e|^2 of this tile's codes -> shared memory once (a global load per column stalled every compare: with
+  // ~210 KB of dynamic shared memory the L1 is a few KB and each load went to L2)
+  float* hn_s = stg + 4096 + (tcount & 1u) * 256;      // after the two 8 KB merge tiles
+  if (et < p.BN) {
+    const int col = nt * p.BN + et;
+    hn_s[et] = col < p.n_codes ? __ldg(p.half_norm + col) : 0.f;
+  }
+  asm volatile("bar.sync 1, 512;" ::: "memory");
   float best = -INFINITY, second = -INFINITY;
   int bidx = 0x7fffffff;
+  const int ncol = min(cpp, p.n_codes - col0);           // valid codes of this thread's quarter
   for (int c = 0; c < cpp; c += 16) {
     float v[16];
     tmem_ld16(t_src + c, v);
+    if (c + 16 <= ncol) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int col = col0 + c + i;
-      if (col < p.n_codes) {
-        const float sc = __fsub_rn(v[i], __ldg(p.half_norm + col));
-        if (sc > best) { second = best; best = sc; bidx = col; }
-        else if (sc > second) second = sc;
+      for (int i = 0; i < 16; ++i) {
+        const float sc = __fsub_rn(v[i], hn_s[part * cpp + c + i]);
+        second = fmaxf(second, fminf(best, sc));         // runner-up = max over all but the (first) best
+        if (sc > best) { best = sc; bidx = col0 + c + i; }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (c + i < ncol) {
+          const float sc = __fsub_rn(v[i], hn_s[part * cpp + c + i]);
+          second = fmaxf(second, fminf(best, sc));
+          if (sc > best) { best = sc; bidx = col0 + c + i; }
+        }
       }
     }
   }
@@ -1282,6 +1299,26 @@ __global__ void nearest_prep(const float* __restrict__ x, __nv_bfloat16* __restr
   if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_int(s));
 }
 
+// query rows: one warp per row, coalesced loads and plane stores; |row|^2 only feeds the error bound
+__global__ void __launch_bounds__(256) nearest_prep_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, float* __restrict__ norm2, int n, int d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = __ldg(x + (size_t)r * d + i);
+    s = fmaf(v, v, s);
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[(size_t)r * d + i] = h;
+    lo[(size_t)r * d + i] = l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) norm2[r] = s * 1.0001f;   // a hair above any summation order's result: it scales a tolerance
+}
+
 __device__ __forceinline__ float exact_score(const float* __restrict__ xr, const float* __restrict__ e,
                                              const float* __restrict__ hn, int k, int D) {
   const float* ek = e + (size_t)k * D;
@@ -1347,6 +1384,192 @@ __global__ void __launch_bounds__(256) nearest_finalize(const float4* __restrict
   if (lane == 0) idx[row] = eidx < K ? eidx : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dedicated nearest-code score kernel ("rows resident").  A work item = one block of 128 rows x a contiguous
+// range of code tiles.  The rows' bf16 hi/lo planes (all of D) are loaded ONCE per item and stay in shared memory;
+// the TMA ring then carries one whole code tile (BN codes x D, both planes) per entry, i.e. ONE mbarrier hand-off
+// per 128 x BN score tile instead of one per K block, and only the codebook streams from L2.  MMA / TMEM /
+// arg-max epilogue as in conv_tc_kernel<1, 1>.
+// ---------------------------------------------------------------------------------------------
+struct TcSearchParams {
+  TcConvParams e;             // BN, BK, n_kblk, acc_stride, tmem_cols, sbo, layout_type, half_norm, cand, n_rows, n_codes, n_ntiles
+  int row_blocks, splits, tiles_per_split, n_items;
+  int a_bufs, b_stages;
+  uint32_t a_blk_bytes;       // 128 * BK * 2 (one K block of one plane)
+  uint32_t a_buf_bytes;       // n_kblk * a_blk_bytes * 2 planes
+  uint32_t b_blk_bytes;       // BN * BK * 2
+  uint32_t b_stage_bytes;     // n_kblk * b_blk_bytes * 2 planes
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+nearest_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const TcSearchParams q) {
+  const TcConvParams& p = q.e;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_afull[2];
+  __shared__ __align__(8) uint64_t bar_aempty[2];
+  __shared__ __align__(8) uint64_t bar_bfull[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_bempty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smemB = smem0 + (uint32_t)q.a_bufs * q.a_buf_bytes;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aempty[i]), 1);
+      mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), 1);
+    }
+    for (int i = 0; i < q.b_stages; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t a_plane = (uint32_t)p.n_kblk * q.a_blk_bytes;   // bytes from the hi to the lo plane of the rows
+  const uint32_t b_plane = (uint32_t)p.n_kblk * q.b_blk_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring ra, rb;
+      for (int item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+        const int rbk = item / q.splits, sp = item - rbk * q.splits;
+        const int nt0 = sp * q.tiles_per_split, nt1 = min(p.n_ntiles, nt0 + q.tiles_per_split);
+        {
+          const uint32_t sa = ra.s;
+          mbar_wait(smem_u32(&bar_aempty[sa]), ra.par ^ 1u, 1);
+          const uint32_t full = smem_u32(&bar_afull[sa]);
+          mbar_expect_tx(full, q.a_buf_bytes);
+          const uint32_t dst = smem0 + sa * q.a_buf_bytes;
+          for (int kb = 0; kb < p.n_kblk; ++kb) {
+            tma_load_3d(dst + kb * q.a_blk_bytes, &tmA_hi, full, kb * p.BK, rbk * TC_BM, 0);
+            tma_load_3d(dst + a_plane + kb * q.a_blk_bytes, &tmA_lo, full, kb * p.BK, rbk * TC_BM, 0);
+          }
+          ra.next(q.a_bufs);
+        }
+        for (int nt = nt0; nt < nt1; ++nt, rb.next(q.b_stages)) {
+          const uint32_t sb = rb.s;
+          mbar_wait(smem_u32(&bar_bempty[sb]), rb.par ^ 1u, 2);
+          const uint32_t full = smem_u32(&bar_bfull[sb]);
+          mbar_expect_tx(full, q.b_stage_bytes);
+          const uint32_t dst = smemB + sb * q.b_stage_bytes;
+          for (int kb = 0; kb < p.n_kblk; ++kb) {
+            tma_load_2d(dst + kb * q.b_blk_bytes, &tmB_hi, full, kb * p.BK, nt * p.BN);
+            tma_load_2d(dst + b_plane + kb * q.b_blk_bytes, &tmB_lo, full, kb * p.BK, nt * p.BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+    const int ksteps = p.BK / 16;
+    const uint32_t desc_hi = (uint32_t)(umma_desc_base(p.sbo, p.layout_type) >> 32);
+    Ring ra, rb;
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+      const int rbk = item / q.splits, sp = item - rbk * q.splits;
+      const int nt0 = sp * q.tiles_per_split, nt1 = min(p.n_ntiles, nt0 + q.tiles_per_split);
+      const uint32_t sa = ra.s;
+      mbar_wait(smem_u32(&bar_afull[sa]), ra.par, 3);
+      tc_fence_after();
+      const uint32_t a_base = ((smem0 + sa * q.a_buf_bytes) & 0x3FFFFu) >> 4;
+      for (int nt = nt0; nt < nt1; ++nt, rb.next(q.b_stages), ++tcount) {
+        const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        const uint32_t sb = rb.s;
+        mbar_wait(smem_u32(&bar_bfull[sb]), rb.par, 4);
+        mbar_wait(smem_u32(&bar_tempty[acc]), apar ^ 1u, 5);
+        tc_fence_after();
+        const uint32_t b_base = ((smemB + sb * q.b_stage_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t d = tmem_base + acc * p.acc_stride;
+        for (int kb = 0; kb < p.n_kblk; ++kb) {
+          const uint32_t a_lo = a_base + ((uint32_t)kb * q.a_blk_bytes >> 4), b_lo = b_base + ((uint32_t)kb * q.b_blk_bytes >> 4);
+          if (ksteps == 4) umma_ksteps<1, 4>(d, a_lo, b_lo, a_plane >> 4, b_plane >> 4, desc_hi, idesc, kb != 0);
+          else if (ksteps == 2) umma_ksteps<1, 2>(d, a_lo, b_lo, a_plane >> 4, b_plane >> 4, desc_hi, idesc, kb != 0);
+          else umma_ksteps<1, 1>(d, a_lo, b_lo, a_plane >> 4, b_plane >> 4, desc_hi, idesc, kb != 0);
+        }
+        umma_commit_w(smem_u32(&bar_bempty[sb]));
+        umma_commit_w(smem_u32(&bar_tfull[acc]));
+      }
+      umma_commit_w(smem_u32(&bar_aempty[sa]));
+      ra.next(q.a_bufs);
+    }
+  } else {
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)q.a_bufs * q.a_buf_bytes +
+                                          (size_t)q.b_stages * q.b_stage_bytes);
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+      const int rbk = item / q.splits, sp = item - rbk * q.splits;
+      const int nt0 = sp * q.tiles_per_split, nt1 = min(p.n_ntiles, nt0 + q.tiles_per_split);
+      for (int nt = nt0; nt < nt1; ++nt, ++tcount) {
+        const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        mbar_wait(smem_u32(&bar_tfull[acc]), apar, 6);
+        tc_fence_after();
+        tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, rbk, nt, smem_u32(&bar_tempty[acc]), warp, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// rows-resident plan: returns false when the rows of one block (all of D, both planes) plus two code-tile stages
+// do not fit in shared memory (D = 256): the caller then uses conv_tc_kernel<1, 1>
+inline bool tc_search_plan(int N, int D, int K, int sm_count, TcSearchParams* q, size_t* smem, int* grid) {
+  if (D % 8 != 0 || D < 8 || D > 256 || K < 1 || N < 1) return false;
+  memset(q, 0, sizeof(*q));
+  TcConvParams& p = q->e;
+  p.BK = D % 64 == 0 ? 64 : (D % 32 == 0 ? 32 : 16);
+  p.n_kblk = (D + p.BK - 1) / p.BK;
+  q->a_blk_bytes = TC_BM * p.BK * 2;
+  q->a_buf_bytes = (uint32_t)p.n_kblk * q->a_blk_bytes * 2;
+  const int budget = 232448 - 2048 - 1024 - 20480;    // 20 KB: the arg-max epilogue's two merge tiles + 0.5|e|^2 tiles
+  int bn = K >= 256 ? 256 : (K + 63) / 64 * 64;
+  for (;; bn >>= 1) {
+    q->b_blk_bytes = (uint32_t)bn * p.BK * 2;
+    q->b_stage_bytes = (uint32_t)p.n_kblk * q->b_blk_bytes * 2;
+    const long rest2 = (long)budget - 2L * q->a_buf_bytes, rest1 = (long)budget - (long)q->a_buf_bytes;
+    if (rest2 >= 2L * q->b_stage_bytes) { q->a_bufs = 2; q->b_stages = (int)(rest2 / q->b_stage_bytes); break; }
+    if (rest1 >= 2L * q->b_stage_bytes) { q->a_bufs = 1; q->b_stages = (int)(rest1 / q->b_stage_bytes); break; }
+    if (bn <= 64) return false;
+  }
+  if (q->b_stages > TC_MAX_STAGES) q->b_stages = TC_MAX_STAGES;
+  p.BN = bn;
+  p.n_ntiles = (K + bn - 1) / bn;
+  p.acc_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+  p.tmem_cols = 2 * p.acc_stride;
+  p.sbo = 8 * p.BK * 2;
+  p.layout_type = p.BK == 64 ? 2u : (p.BK == 32 ? 4u : 6u);
+  p.stg_bufs = 2;
+  q->row_blocks = (N + TC_BM - 1) / TC_BM;
+  int splits = (2 * sm_count + q->row_blocks - 1) / q->row_blocks;      // aim at >= 2 items per SM
+  if (splits > p.n_ntiles) splits = p.n_ntiles;
+  if (splits < 1) splits = 1;
+  q->tiles_per_split = (p.n_ntiles + splits - 1) / splits;
+  q->splits = (p.n_ntiles + q->tiles_per_split - 1) / q->tiles_per_split;
+  const long items = (long)q->row_blocks * q->splits;
+  if (items > 0x7fffffffL) return false;
+  q->n_items = (int)items;
+  *grid = (int)(items < sm_count ? items : sm_count);
+  *smem = (size_t)q->a_bufs * q->a_buf_bytes + (size_t)q->b_stages * q->b_stage_bytes + 20480 + 1024;
+  return true;
+}
+
 inline CUtensorMapSwizzle tc_swizzle_of(int bk) {
   return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -1380,8 +1603,9 @@ inline size_t tc_nearest_scratch_bytes(int N, int D, int K) {
   TcNearestDims d;
   if (!tc_nearest_dims(N, D, K, &d)) return (size_t)K * 4;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t max_tiles = (size_t)(K + 63) / 64;   // the narrowest code tile either kernel uses
   return al((size_t)N * D * 4) + al((size_t)K * D * 4) + al((size_t)K * 4) + al((size_t)N * 4) + 256 +
-         al((size_t)N * d.n_ntiles * 16);
+         al((size_t)N * max_tiles * 16);
 }
 
 // returns 0 = launched; 1 = shape not eligible (caller uses the FP32 kernel); < 0 = error
@@ -1406,8 +1630,47 @@ inline int tc_nearest_launch(const float* x, const float* emb, void* scratch, in
   s += 256;
   float4* cand = reinterpret_cast<float4*>(s);
   if (cudaMemsetAsync(emax, 0, 4, st) != cudaSuccess) return -3;
-  nearest_prep<<<(N + 127) / 128, 128, 0, st>>>(x, xh, xl, nullptr, xn2, nullptr, N, D);
+  nearest_prep_rows<<<(N + 7) / 8, 256, 0, st>>>(x, xh, xl, xn2, N, D);
   nearest_prep<<<(K + 127) / 128, 128, 0, st>>>(emb, eh, el, hn, nullptr, emax, K, D);
+
+  {
+    // preferred: rows resident in shared memory, one hand-off per score tile
+    TcSearchParams q;
+    size_t smem = 0;
+    int grid = 0;
+    static int use_rows = -1;
+    if (use_rows < 0) {
+      const char* e = getenv("B2C_SEARCH_ROWS");
+      use_rows = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_rows && tc_search_plan(N, D, K, sm_count, &q, &smem, &grid)) {
+      TcConvParams& p = q.e;
+      p.half_norm = hn; p.cand = cand; p.n_rows = N; p.n_codes = K;
+      CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+      cuuint32_t es[3] = {1, 1, 1};
+      cuuint64_t adims[3] = {(cuuint64_t)D, (cuuint64_t)N, 1};
+      cuuint64_t astr[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+      cuuint32_t abox[3] = {(cuuint32_t)p.BK, TC_BM, 1};
+      cuuint64_t bdims[2] = {(cuuint64_t)D, (cuuint64_t)K};
+      cuuint64_t bstr[1] = {(cuuint64_t)D * 2};
+      cuuint32_t bbox[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
+      for (int pl = 0; pl < 2; ++pl) {
+        if (tc_encode_fn()(pl ? &mA_lo : &mA_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pl ? (void*)xl : (void*)xh, adims, astr,
+                           abox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_of(p.BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return -13;
+        if (tc_encode_fn()(pl ? &mB_lo : &mB_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl ? (void*)el : (void*)eh, bdims, bstr,
+                           bbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_of(p.BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return -14;
+      }
+      if (cudaFuncSetAttribute(nearest_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -2;
+      nearest_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, q);
+      nearest_finalize<<<(N + 7) / 8, 256, 0, st>>>(cand, p.n_ntiles, p.BN, x, emb, hn, xn2, emax, N, D, K, idx);
+      return 0;
+    }
+  }
 
   TcConvParams p;
   memset(&p, 0, sizeof(p));
