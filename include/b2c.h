@@ -109,7 +109,8 @@ int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, const float* co
 /* ---------------- programs ---------------- */
 int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out);
 int b2c_prog_destroy(b2c_prog* prog);
-int b2c_prog_num_launches(const b2c_prog* prog);
+int b2c_prog_num_launches(const b2c_prog* prog); /* kernel launches per run */
+int b2c_prog_num_ops(const b2c_prog* prog);      /* ops (what b2c_prog_profile times) */
 
 /* 1 when the tcgen05 implicit-GEMM kernel takes this layer (precision BF16X3 / BF16), 0 when only the FP32
  * CUDA-core kernel does, negative on a bad argument.  Callers pick activation formats with it. */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "b2c_prog_create": (_i, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2c_prog_destroy": (_i, [C.c_void_p]),
     "b2c_prog_num_launches": (_i, [C.c_void_p]),
+    "b2c_prog_num_ops": (_i, [C.c_void_p]),
     "b2c_conv_tc_eligible": (_i, [C.c_void_p, _i, _i, _i, _i]),
     "b2c_prog_stem": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_conv": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),

@@ -285,6 +285,7 @@ struct Op {
   DacRvqArgs dac;
   TcConvPlan tc;
   TcRuPlan ru;
+  void* scratch = nullptr;   // device memory owned by the op (split residual VQ: residual rows + arg-max keys)
   int i[8] = {0};
   size_t n = 0;
   int precision = 0;
@@ -310,10 +311,26 @@ extern "C" int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out) {
   return B2C_OK;
 }
 extern "C" int b2c_prog_destroy(b2c_prog* p) {
+  if (p) {
+    cudaSetDevice(p->ctx->device);
+    for (auto& op : p->ops)
+      if (op.scratch) cudaFree(op.scratch);
+  }
   delete p;
   return B2C_OK;
 }
-extern "C" int b2c_prog_num_launches(const b2c_prog* p) { return p ? (int)p->ops.size() : 0; }
+// kernel launches one run of the program enqueues (an op can be several launches)
+extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
+  if (!p) return 0;
+  int n = 0;
+  for (const auto& op : p->ops) {
+    if (op.type == OP_RVQ && op.scratch && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
+    else if (op.type == OP_NEAREST) n += op.precision == B2C_PREC_F32 ? 2 : 4;                // prep x2, scores, finalise
+    else n += 1;
+  }
+  return n;
+}
+extern "C" int b2c_prog_num_ops(const b2c_prog* p) { return p ? (int)p->ops.size() : 0; }
 
 static void blank_refs(Op& op) {
   for (auto& r : op.r) r = B2C_NULL_REF;
@@ -549,6 +566,13 @@ extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x
   r.chunk = chunk > 0 ? chunk : 1;
   r.nfix = nfix_of(r.Tl, r.chunk) > 0 ? nfix_of(r.Tl, r.chunk) : 1;
   r.idx_flat = 0;
+  if (books_use > 0) {
+    // split residual VQ: residual [N, D] fp32 + one 64-bit arg-max key per row
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const size_t bytes = ((size_t)N * w->D * 4 + 255) / 256 * 256 + (size_t)N * 8;
+    CUDA_TRY(cudaMalloc(&op.scratch, bytes));
+    CUDA_TRY(cudaMemset(op.scratch, 0, bytes));
+  }
   p->ops.push_back(op);
   return B2C_OK;
 }
@@ -838,7 +862,26 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           }
         }
         if (R.bad || !r.x || (!r.idx && r.books_use > 0)) return fail(B2C_ERR_WORKSPACE, "op %zu (rvq): unresolved buffer", oi);
-        if (r.books_use > 0) {
+        static int rvq_split = -1;
+        if (rvq_split < 0) {
+          const char* e = getenv("B2C_RVQ_SPLIT");
+          rvq_split = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (r.books_use > 0 && op.type == OP_RVQ && op.scratch && rvq_split && r.qsum) {
+          // per book: scores over (token block x code slice) CTAs with an atomic arg-max, then apply
+          float* resid = reinterpret_cast<float*>(op.scratch);
+          unsigned long long* keys = reinterpret_cast<unsigned long long*>(
+              reinterpret_cast<char*>(op.scratch) + ((size_t)r.N * r.D * 4 + 255) / 256 * 256);
+          const size_t sm = ((size_t)32 * r.D + 64 * (r.D + 1)) * sizeof(float);
+          cudaError_t e = cudaFuncSetAttribute(rvq_scores_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
+          dim3 grid((r.N + 31) / 32, (r.K + 63) / 64);
+          for (int bk = 0; bk < r.books_use; ++bk) {
+            rvq_scores_f32<<<grid, 256, sm, st>>>(bk == 0 ? r.x : resid, r.books + (size_t)bk * r.K * r.D,
+                                                  r.half_n + (size_t)bk * r.K, keys, r.N, r.D, r.K);
+            rvq_apply_f32<<<(r.N + 7) / 8, 256, 0, st>>>(r, r.books + (size_t)bk * r.K * r.D, resid, keys, bk);
+          }
+        } else if (r.books_use > 0) {
           // 32 tokens per CTA when that still gives every SM two CTAs, else 8 (one per warp)
           const bool wide = (long)r.N >= 64L * ctx->sm_count;
           const int tok = wide ? 32 : 8;

@@ -193,7 +193,7 @@ class Engine:
         -> list of dicts {kind, ms, flops, bytes}."""
         ws = self.workspace(prog.ws_bytes)
         arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
-        cap = prog.info["launches"] + 8
+        cap = prog.info["ops"] + 8
         ms = (C.c_float * cap)()
         kind = (C.c_int * cap)()
         fl = (C.c_double * cap)()
@@ -261,7 +261,8 @@ class Emitter:
         return L.ref(0, buf)
 
     def finish(self, n_ext: int, **info) -> Program:
-        return Program(self.h, self.arena.peak + ALIGN, n_ext, dict(info, launches=self.lib.b2c_prog_num_launches(self.h)))
+        return Program(self.h, self.arena.peak + ALIGN, n_ext,
+                       dict(info, launches=self.lib.b2c_prog_num_launches(self.h), ops=self.lib.b2c_prog_num_ops(self.h)))
 
     # ops
     def stem(self, w: ConvW, x, out_raw, out_act, alpha, B, Lx, act_fmt=L.FMT_F32):
