@@ -33,6 +33,10 @@ CODEC_CASES = {
     "cal_b4k256_use3_short": dict(books=4, K=256, B=3, T=8000, kind="sines", calibrate=True, books_use=3),
     # the latency script's input: all-zero frame, B = 1
     "zeros_b1k128": dict(books=1, K=128, B=1, T=24000, kind="zeros"),
+    # more points of the compare_dacvsproposal_5 sweep grid (BOOKS_LIST x EMBED_LIST, :86-88): the smallest
+    # codebook with gaussian frames, and the largest with a books_use prefix (Evaluation/dac_vcpwq_proposed.py stages)
+    "cal_b1k128_normal": dict(books=1, K=128, B=1, T=24000, kind="normal", calibrate=True),
+    "cal_b10k512_use6": dict(books=10, K=512, B=1, T=24000, kind="uniform", calibrate=True, books_use=6),
 }
 
 # name -> (N, D, K) for ResidualVQEMA._nearest_l2 (config 5 subset the CPU finishes in seconds)

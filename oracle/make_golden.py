@@ -52,7 +52,10 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
     # ---- full-path cases: reference ProposedEval.forward_eval ----
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, case in CODEC_CASES.items():
+        if only and name not in only:
+            continue
         model = build_reference_style_model(ns["ProposedEval"], case)
         a, t = codec_inputs(case)
         tl = a.shape[-1] // dac_arch.HOP
@@ -75,6 +78,8 @@ def main():
         )
         print("wrote", name, "y", tuple(y.shape), "idx", tuple(idx.shape))
 
+    if only:
+        return
     # ---- module-level: reference CrossPredictor + ResidualVQEMA on seeded tensors ----
     torch.manual_seed(7)
     pred = ns["CrossPredictor"](c=1024).eval()
