@@ -33,8 +33,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=128, help="frames per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=64,
+                    help="frames per program run (64: measured +7 %% over 32 -- fewer partial waves of tiles on 148 SMs)")
     ap.add_argument("--precision", default=os.environ.get("B2C_PRECISION", "auto"))
     ap.add_argument("--cpu-sample", type=int, default=8, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -107,8 +107,8 @@ class _Top(nn.Module):
     #: contraction arithmetic plan (_lib.PLANS): 'f32' (CUDA-core FFMA everywhere), 'tc' (tcgen05: bf16 hi/lo
     #: split x3 upstream of the quantizer, single-pass bf16 decoder), 'tc_exact', 'bf16', 'bf16x3'
     precision = "tc"
-    #: signals per program launch (bounds the activation workspace)
-    micro_batch = 32
+    #: signals per program launch (bounds the activation workspace: ~72 MB per signal at T = 24000)
+    micro_batch = 64
 
     def _engine(self, device) -> Engine:
         ver = tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())

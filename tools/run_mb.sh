@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for cfg in "64 32" "64 64" "128 64" "96 48"; do
+for cfg in ${CFGS:-"128 64" "128 128" "256 128" "192 96"}; do
   set -- $cfg
   ( timeout 600 python bench.py --steps 4 --warmup 3 --batch $1 --micro-batch $2 --no-cpu-baseline ; echo "rc=$?" ) > gpurun_out/bench_mb_$1_$2.log 2>&1
   python - <<PY
