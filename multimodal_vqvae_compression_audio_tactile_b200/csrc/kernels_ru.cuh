@@ -263,7 +263,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (X3) tma_load_3d(sa + p.a_bytes, &tmA_lo, full, c0, row, b);
             tma_load_2d(sb, &tmB7_hi, full, c0, tap * p.Cout);
             if (X3) tma_load_2d(sb + p.b_bytes, &tmB7_lo, full, c0, tap * p.Cout);
-            if (++cb == q.nk) { cb = 0; ++tap; }
+            if (++cb == q.nk) { cb = 0; ++tap; }    // tap outer, channels ascending (BK-independent order)
           }
         }
       };

@@ -601,8 +601,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             tma_load_2d(sb, &tmB_hi, full, c0, brow);
             if (X3) tma_load_2d(sb + p.b_bytes, &tmB_lo, full, c0, brow);
-            if (++cb == p.n_kblk) { cb = 0; ++tap; }
-          }
+            if (++cb == p.n_kblk) { cb = 0; ++tap; }   // tap outer, channels ascending: the accumulation order does
+          }                                            // not depend on BK, so a frame's bits do not depend on the batch
         }
       }
     }
@@ -1148,17 +1148,27 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   // ... that was before K blocks were grouped per hand-off in the generic kernel; with grouping the generic
   // kernel is as fast or faster on every layer of this model (96 ch: 0.240 vs 0.263 ms, 128 ch: 0.258 vs 0.256),
   // so the slab kernel is kept for experiments (B2C_TC_SLAB=2) and not selected by default.
-  const bool slab_pays = false;
+  // One exception, measured at micro-batch 64: single-pass bf16 k = 7 layers with wide channel blocks (the decoder's
+  // 768- and 384-channel units) gain 8-14 % from the slab kernel when it keeps the generic kernel's N (one m-tile per
+  // item): their A re-reads were a third of the L2 traffic of an L2-bound loop.
+  // (decided from the layer alone -- never from the batch -- and with a fixed K slice, because the slab kernel
+  // accumulates channel-block-major: a layer must use the same kernel and order at every batch size.)
+  const bool slab_wide = !plan->x3 && a.KT >= 3 && largest_bn(a.Cout) >= 192;
+  const bool slab_pays = slab_wide;
   if (a.in_step == 1 && tc_slab_enabled() && (slab_pays || tc_slab_forced())) {
     // slab kernel: narrower channel blocks, several m-tiles per work item
-    const int bn2 = a.Cout % 128 == 0 ? 128 : (a.Cout % 96 == 0 ? 96 : (a.Cout % 64 == 0 ? 64 : bn));
+    int bn2 = a.Cout % 128 == 0 ? 128 : (a.Cout % 96 == 0 ? 96 : (a.Cout % 64 == 0 ? 64 : bn));
+    {
+      const char* e = getenv("B2C_TC_SLAB_WIDE");   // keep the generic kernel's wide N, one m-tile per item
+      if (slab_wide || (e && e[0] == '1')) bn2 = bn;
+    }
     const int stride2 = bn2 <= 64 ? 64 : (bn2 <= 128 ? 128 : 256);
     int mt = 256 / stride2;
     if (mt > 4) mt = 4;
     while (mt > 1 && mt > p.tiles_j) mt >>= 1;
     const int planes = plan->x3 ? 2 : 1;
     for (; mt >= 1 && !plan->slab; mt >>= 1) {
-      for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= 32 && !plan->slab; bk -= 32) {
+      for (int bk = (a.Cin % 64 == 0) ? 64 : 32; bk >= (slab_wide ? ((a.Cin % 64 == 0) ? 64 : 32) : 32) && !plan->slab; bk -= 32) {
         int rows = mt * TC_BM + (a.KT - 1) * a.dil;
         const int n_loads = (rows + 255) / 256;
         const int q = 16 * n_loads;

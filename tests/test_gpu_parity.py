@@ -278,6 +278,8 @@ def test_fused_residual_unit_matches_separate_launches(dev):
             eng.run(prog, [x.data_ptr(), raw.data_ptr(), act.data_ptr()])
             torch.cuda.synchronize()
             res[fused] = (raw.cpu(), act.cpu())
-        # same arithmetic (same MMAs, same epilogue math): only the accumulation grouping of h's bf16 split can differ
-        assert float((res[True][0] - res[False][0]).abs().max()) < 1e-5, (C_, prec)
+        # same MMAs and epilogue math.  bf16x3: identical accumulation order -> equal to fp32 round-off.  Single-pass
+        # bf16 (decoder): the separate k=7 launch of a wide layer runs the slab kernel (channel-block-major sums), so h
+        # can round to the neighbouring bf16 value: differences are one bf16 ulp of h through a 1x1 conv.
+        assert float((res[True][0] - res[False][0]).abs().max()) < (2e-3 if prec == "bf16" else 1e-5), (C_, prec)
         assert float((res[True][1] - res[False][1]).abs().max()) < (2e-2 if prec == "bf16" else 1e-4), (C_, prec)
