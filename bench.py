@@ -270,8 +270,18 @@ def main():
                             for k in ks]
         except Exception:
             traffic_note = None
+    # DRAM bytes per launch of the dominant family, from the committed ncu capture of this same bench command
+    # (profiles/r01_ncu_dram_traffic_conv_mb64.json: dram__bytes_read.sum + dram__bytes_write.sum of every launch of
+    # one program); only valid for the micro-batch it was captured at
+    traffic_alg = dd["bytes"] / dd["launches"]
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_conv_mb64.json")
+    if os.path.isfile(tp) and mb == 64 and dom == "conv_tc_x3":
+        try:
+            traffic = json.load(open(tp))["x3"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sus"], "traffic": traffic,
+                "frac": achieved / peaks["tf_sus"], "traffic": traffic, "traffic_algorithmic": traffic_alg,
                 "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "share_of_step": dd["ms"] / tot_ms, "launches_per_program": dd["launches"],
                 "avg_launch_ms": dd["ms"] / dd["launches"],
@@ -279,9 +289,9 @@ def main():
                 "executed_tflops": executed / (dd["ms"] / 1e3) / 1e12,
                 "executed_frac": executed / (dd["ms"] / 1e3) / 1e12 / peaks["tf_sus"],
                 "note": "achieved = algorithmic conv FLOPs / CUDA-event time of the conv launches of one program; the "
-                        "bf16x3 launches execute 3 MMA FLOPs per algorithmic FLOP (executed_tflops); traffic is null "
-                        "because the 'kernel' is ~90 launches of different shapes -- ncu DRAM bytes of sampled launches "
-                        "are in ncu_samples / profiles/r01_ncu_full_conv_tc.json",
+                        "bf16x3 launches execute 3 MMA FLOPs per algorithmic FLOP (executed_tflops); traffic = ncu DRAM "
+                        "bytes per launch averaged over the family's launches of one program "
+                        "(profiles/r01_ncu_dram_traffic_conv_mb64.json), traffic_algorithmic = the minimal bytes",
                 "ncu_samples": traffic_note}
     if args.profile_out:
         with open(args.profile_out, "w") as fh:

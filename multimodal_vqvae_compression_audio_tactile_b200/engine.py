@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -37,8 +38,12 @@ class Arena:
         self.peak = 0
         self.live = {}
 
+    #: extra bytes added to every allocation (experiment knob: relative placement of the streams a kernel reads
+    #: and writes decides DRAM bank conflicts)
+    PAD = int(os.environ.get("B2C_ARENA_PAD", "0"))
+
     def alloc(self, nbytes: int) -> int:
-        n = (max(int(nbytes), 1) + ALIGN - 1) // ALIGN * ALIGN
+        n = (max(int(nbytes), 1) + self.PAD + ALIGN - 1) // ALIGN * ALIGN
         for i, (off, size) in enumerate(self.free_list):
             if size >= n:
                 if size == n:
