@@ -254,6 +254,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t s = rg.s;
           mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 1);
           const uint32_t full = smem_u32(&bar_full[s]);
+          if (p.dbg & 2) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, sub_bytes * (uint32_t)cnt);
           for (int g = 0; g < cnt; ++g) {
             const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
@@ -273,6 +274,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t s = rg.s;
           mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 2);
           const uint32_t full = smem_u32(&bar_full[s]);
+          if (p.dbg & 2) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, p.b_bytes * planes * (uint32_t)cnt);
           for (int g = 0; g < cnt; ++g) {
             const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + a_in_ring;
@@ -297,6 +299,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t slab_plane = q.slab_plane_bytes >> 4;
     const uint32_t tap_step = ((uint32_t)p.dil * (uint32_t)p.BK * 2u) >> 4;     // descriptor units per tap (slab mode)
     auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t apl, uint32_t first) {
+      if (p.dbg & 4) return;
       if (ksteps == 4) umma_ksteps<X3, 4>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else if (ksteps == 2) umma_ksteps<X3, 2>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else umma_ksteps<X3, 1>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
@@ -390,7 +393,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(smem_u32(&bar_t1full[g]), par, 8);
         mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);
         tc_fence_after();
-        ru_epilogue_h_g<X3>(q, stg_g, g, tmem_base + g * p.acc_stride, hbuf, warp, lane);
+        if (!(p.dbg & 1)) ru_epilogue_h_g<X3>(q, stg_g, g, tmem_base + g * p.acc_stride, hbuf, warp, lane);
         tc_fence_before();
         fence_proxy_async();
         epi_group_sync(g);
@@ -400,7 +403,13 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         mbar_wait(smem_u32(&bar_t2full[g]), par, 10);
         tc_fence_after();
-        tc_epilogue_tile_g(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
+        if (p.dbg & 1) {
+          tc_fence_before();
+          epi_group_sync(g);
+          if (leader) mbar_arrive(smem_u32(&bar_t2empty[g]));
+        } else {
+          tc_epilogue_tile_g(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
+        }
       }
     } else
     for (int i = 0; i < my_tiles; ++i) {
@@ -474,6 +483,10 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   TcConvParams& p = q.e;
   plan->x3 = precision == 1 ? 1 : 0;
   const int planes = plan->x3 ? 2 : 1;
+  {
+    const char* e = getenv("B2C_TC_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.B = B; p.Lin = L; p.Cin = C; p.Cout = C; p.KT = 7; p.in_step = 1; p.dil = dil; p.n_phase = 1;
   p.Lj = L; p.out_step = 1; p.Lout = L;
   p.in_off[0] = -3 * dil; p.out_off[0] = 0;

@@ -50,7 +50,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+#ifdef B2C_MBAR_POLL
+  // experiment: non-suspending poll
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
+    if (mbar_test_wait(bar, parity)) return;
+  printf("b2c conv_tc: mbarrier poll timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x);
+  __trap();
+#endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (clock64() - t0 < 3000000000LL)   // ~1.5 s at 1.9 GHz
