@@ -283,3 +283,18 @@ def test_fused_residual_unit_matches_separate_launches(dev):
         # can round to the neighbouring bf16 value: differences are one bf16 ulp of h through a 1x1 conv.
         assert float((res[True][0] - res[False][0]).abs().max()) < (2e-3 if prec == "bf16" else 1e-5), (C_, prec)
         assert float((res[True][1] - res[False][1]).abs().max()) < (2e-2 if prec == "bf16" else 1e-4), (C_, prec)
+
+
+def test_host_entry_pipelined_and_ragged_tail(dev, oracle_models):
+    """forward_eval_host: equal micro-batches go through b2c_prog_run_host_pipelined (copy stream overlap), the
+    remainder through b2c_prog_run_host; both must give the device entry's bits."""
+    name = "c3_b10k128"
+    case = dict(cases.CODEC_CASES[name], B=5, T=6400)
+    net = gpu_model(oracle_models(name), case)
+    net.micro_batch = 2                      # 2 + 2 pipelined, 1 tail
+    a, t = cases.codec_inputs(case)
+    y = net.forward_eval(a.to(dev), t.to(dev)).cpu()
+    idx = net.last_indices.cpu()
+    yh, ih = net.forward_eval_host(a.pin_memory(), t.pin_memory())
+    assert torch.equal(yh, y) and torch.equal(ih, idx)
+    assert net.last_host_bytes == (2 * a.numel() * 4, y.numel() * 4 + idx.numel() * 4)
