@@ -80,6 +80,9 @@ typedef uint64_t b2c_ref;
 
 const char* b2c_last_error(void);
 int b2c_abi_version(void);
+/* developer aid (timing experiments, B2C_TC_DEBUG bit 8): copies out and resets the pipeline-event trace CTA 0 of the
+ * fused residual-unit kernel recorded: entries (tag << 56) | (tile << 44) | SM clock.  Returns the entry count. */
+int b2c_debug_ru_trace(unsigned long long* dst, int cap);
 
 /* ---------------- context + packed weights ---------------- */
 int b2c_ctx_create(int device, b2c_ctx** out);

@@ -57,6 +57,7 @@ _i = C.c_int
 SIGNATURES = {
     "b2c_last_error": (C.c_char_p, []),
     "b2c_abi_version": (_i, []),
+    "b2c_debug_ru_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "b2c_ctx_create": (_i, [_i, C.POINTER(C.c_void_p)]),
     "b2c_ctx_destroy": (_i, [C.c_void_p]),
     "b2c_ctx_weight_bytes": (C.c_size_t, [C.c_void_p]),

@@ -36,6 +36,17 @@ static int fail(int code, const char* fmt, ...) {
 extern "C" const char* b2c_last_error(void) { return g_err; }
 extern "C" int b2c_abi_version(void) { return B2C_ABI_VERSION; }
 
+// timing experiments only (B2C_TC_DEBUG bit 8): copy out and reset the fused-unit pipeline trace of CTA 0
+extern "C" int b2c_debug_ru_trace(unsigned long long* dst, int cap) {
+  if (cap < 8192) return fail(B2C_ERR_ARG, "b2c_debug_ru_trace: cap < 8192");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(dst, b2c::g_ru_trace, 8192 * sizeof(unsigned long long)));
+  void* sym = nullptr;
+  CUDA_TRY(cudaGetSymbolAddress(&sym, b2c::g_ru_trace));
+  CUDA_TRY(cudaMemset(sym, 0, 8192 * sizeof(unsigned long long)));
+  return 8192;
+}
+
 // ------------------------------------------------------------------------------------------
 // context + weights
 // ------------------------------------------------------------------------------------------

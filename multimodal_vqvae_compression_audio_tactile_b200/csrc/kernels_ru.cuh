@@ -32,6 +32,17 @@ struct TcRuParams {
   uint32_t slab_plane_bytes; // slab_rows * BK * 2
 };
 
+// Timeline trace (B2C_TC_DEBUG bit 8, timing experiments only): CTA 0 records (tag, tile, SM clock) of its pipeline
+// events for a few steady-state tiles; b2c_debug_ru_trace() reads them back.
+__device__ unsigned long long g_ru_trace[8192];
+// role = 0 TMA thread, 1 MMA warp, 2 / 3 epilogue group leaders; every role appends to its own quarter with a private
+// counter (plain stores: an atomic's return latency would sit on the critical path being measured)
+__device__ __forceinline__ void ru_trace(int dbg, int role, uint32_t& cnt, int tag, int tile) {
+  if ((dbg & 8) && blockIdx.x == 0 && tile >= 8 && tile < 14 && cnt < 2048u)
+    g_ru_trace[role * 2048 + cnt++] = ((unsigned long long)tag << 56) | ((unsigned long long)tile << 44) |
+                                      ((unsigned long long)clock64() & ((1ull << 44) - 1));
+}
+
 // epilogue A of one tile: TMEM acc1 -> staging -> (+b7, snake2, bf16 split) -> swizzled K-major h in shared memory
 template <int X3>
 __device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB7_hi, const __grid_constant__ CUtensorMap tmB7_lo,
                const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
-               const TcRuParams q) {
+               const __grid_constant__ TcRuParams q) {
   const TcConvParams& p = q.e;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
@@ -163,7 +174,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_aempty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t planes = X3 ? 2u : 1u;
   const uint32_t a_in_ring = q.slab ? 0u : p.a_bytes * planes;       // bytes of the A part of a ring sub-block
@@ -203,6 +214,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int n7 = p.KT * q.nk;                          // K blocks of GEMM 1
   const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int la = q.nbuf - 1;                           // GEMM-1 lookahead in tiles
+  uint32_t tcnt = 0;                                   // trace entries of this thread's role (debug only)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -253,6 +265,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int cnt = min(p.kgroup, n7 - k0);
           const uint32_t s = rg.s;
           mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 1);
+          ru_trace(p.dbg, 0, tcnt, 1, i);
           const uint32_t full = smem_u32(&bar_full[s]);
           if (p.dbg & 2) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, sub_bytes * (uint32_t)cnt);
@@ -268,11 +281,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
       };
-      auto produce_w1 = [&]() {
+      auto produce_w1 = [&](int i) {
         for (int k0 = 0; k0 < q.nk; k0 += p.kgroup, rg.next(p.stages)) {
           const int cnt = min(p.kgroup, q.nk - k0);
           const uint32_t s = rg.s;
           mbar_wait(smem_u32(&bar_empty[s]), rg.par ^ 1u, 2);
+          ru_trace(p.dbg, 0, tcnt, 2, i);
           const uint32_t full = smem_u32(&bar_full[s]);
           if (p.dbg & 2) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, p.b_bytes * planes * (uint32_t)cnt);
@@ -286,7 +300,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int i = 0; i < la && i < my_tiles; ++i) produce_conv7(i);
       for (int i = 0; i < my_tiles; ++i) {
         if (i + la < my_tiles) produce_conv7(i + la);
-        produce_w1();
+        produce_w1(i);
       }
     }
   } else if (warp == 1) {
@@ -308,6 +322,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
       mbar_wait(smem_u32(&bar_t1empty[buf]), par ^ 1u, 3);
       tc_fence_after();
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 10, i);
       const uint32_t d = tmem_base + buf * p.acc_stride;
       if (q.slab) {
         for (int cb = 0; cb < q.nk; ++cb, ra.next(2)) {
@@ -336,6 +351,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t s = rg.s;
         mbar_wait(smem_u32(&bar_full[s]), rg.par, 4);
         tc_fence_after();
+        if (lane == 0) ru_trace(p.dbg, 1, tcnt, 11, i);
         for (int g = 0; g < cnt; ++g) {
           const uint32_t sa = smem0 + s * stage_bytes + g * sub_bytes;
           issue(d, (sa & 0x3FFFFu) >> 4, ((sa + p.a_bytes * planes) & 0x3FFFFu) >> 4, a_plane, (k0 + g) != 0);
@@ -343,18 +359,22 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         umma_commit_w(smem_u32(&bar_empty[s]));
       }
       umma_commit_w(smem_u32(&bar_t1full[buf]));
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 12, i);
     };
     auto gemm2 = [&](int i) {
       const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
       mbar_wait(smem_u32(&bar_hfull), (uint32_t)i & 1u, 5);           // h(i) is in shared memory
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 13, i);
       mbar_wait(smem_u32(&bar_t2empty[buf]), par ^ 1u, 6);
       tc_fence_after();
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 14, i);
       const uint32_t d = tmem_base + (q.nbuf + buf) * p.acc_stride;
       for (int k0 = 0; k0 < q.nk; k0 += p.kgroup, rg.next(p.stages)) {
         const int cnt = min(p.kgroup, q.nk - k0);
         const uint32_t s = rg.s;
         mbar_wait(smem_u32(&bar_full[s]), rg.par, 7);
         tc_fence_after();
+        if (lane == 0) ru_trace(p.dbg, 1, tcnt, 15, i);
         for (int g = 0; g < cnt; ++g) {
           const uint32_t sb = smem0 + s * stage_bytes + g * sub_bytes + a_in_ring;
           const uint32_t ha = hbuf_u32 + (uint32_t)(k0 + g) * q.h_block_bytes;
@@ -364,6 +384,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       umma_commit_w(smem_u32(&bar_hempty));          // h may be overwritten once these MMAs retire
       umma_commit_w(smem_u32(&bar_t2full[buf]));
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 16, i);
     };
     for (int i = 0; i < la && i < my_tiles; ++i) gemm1(i);
     for (int i = 0; i < my_tiles; ++i) {
@@ -390,9 +411,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int b2 = t2 / p.tiles_j;
           tc_prefetch_res_g(p, b2, 0, t2 - b2 * p.tiles_j, 0);
         }
+        if (leader) ru_trace(p.dbg, 2 + g, tcnt, 20, i);
         mbar_wait(smem_u32(&bar_t1full[g]), par, 8);
+        if (leader) ru_trace(p.dbg, 2 + g, tcnt, 21, i);
         mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);
         tc_fence_after();
+        if (leader) ru_trace(p.dbg, 2 + g, tcnt, 22, i);
         if (!(p.dbg & 1)) ru_epilogue_h_g<X3>(q, stg_g, g, tmem_base + g * p.acc_stride, hbuf, warp, lane);
         tc_fence_before();
         fence_proxy_async();
@@ -400,9 +424,11 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (leader) {
           mbar_arrive(smem_u32(&bar_t1empty[g]));
           mbar_arrive(smem_u32(&bar_hfull));
+          ru_trace(p.dbg, 2 + g, tcnt, 23, i);
         }
         mbar_wait(smem_u32(&bar_t2full[g]), par, 10);
         tc_fence_after();
+        if (leader) ru_trace(p.dbg, 2 + g, tcnt, 24, i);
         if (p.dbg & 1) {
           tc_fence_before();
           epi_group_sync(g);
@@ -410,6 +436,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else {
           tc_epilogue_tile_g(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
         }
+        if (leader) ru_trace(p.dbg, 2 + g, tcnt, 25, i);
       }
     } else
     for (int i = 0; i < my_tiles; ++i) {
@@ -507,8 +534,15 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
     if (e && e[0] == '1') want_slab = true;
   }
   bool done = false;
+  int force_bk = 0, force_g = 0;                  // experiment knobs
+  {
+    const char* e = getenv("B2C_RU_BK");
+    if (e) force_bk = atoi(e);
+    e = getenv("B2C_RU_KGROUP");
+    if (e) force_g = atoi(e);
+  }
   for (int slab = want_slab ? 1 : 0; slab >= 0 && !done; --slab) {
-    for (int bk = (C % 64 == 0) ? 64 : 32; bk >= 32 && !done; bk -= 32) {
+    for (int bk = (C % 64 == 0 && force_bk != 32) ? 64 : 32; bk >= 32 && !done; bk -= 32) {
       p.BK = bk;
       q.nk = C / bk;
       p.n_kblk = q.nk;
@@ -536,6 +570,7 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
       if (g > 8) g = 8;
       if (slab && g > 7) g = 7;
       while (g > 1 && subs / g < 2) --g;
+      if (force_g > 0 && force_g <= subs) g = force_g;
       p.kgroup = g;
       p.stages = subs / g;
       if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;

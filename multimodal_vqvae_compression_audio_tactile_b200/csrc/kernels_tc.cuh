@@ -547,7 +547,7 @@ template <int X3, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const TcConvParams p) {
+               const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
@@ -555,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sub_bytes = (p.a_bytes + p.b_bytes) * (X3 ? 2u : 1u);   // one K block: A (+lo) | B (+lo)
   const uint32_t stage_bytes = sub_bytes * (uint32_t)p.kgroup;
@@ -764,7 +764,7 @@ template <int X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                const TcConvParams p) {
+                const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_afull[TC2_MAX_SA];
   __shared__ __align__(8) uint64_t bar_aempty[TC2_MAX_SA];
@@ -774,7 +774,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t planes = X3 ? 2u : 1u;
   const uint32_t a_slot = p.a_plane_bytes * planes;
@@ -1330,7 +1330,7 @@ __global__ void nearest_prep(const float* __restrict__ x, __nv_bfloat16* __restr
 // query rows: one warp per row, coalesced loads and plane stores; |row|^2 only feeds the error bound
 __global__ void __launch_bounds__(256) nearest_prep_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, float* __restrict__ norm2, int n, int d) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const int r = blockIdx.x * 8 + warp;
   if (r >= n) return;
   float s = 0.f;
@@ -1365,7 +1365,7 @@ __global__ void __launch_bounds__(256) nearest_finalize(const float4* __restrict
                                                         const float* __restrict__ hn, const float* __restrict__ xnorm2,
                                                         const int* __restrict__ emax2_bits, int N, int D, int K,
                                                         int* __restrict__ idx) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const int row = blockIdx.x * 8 + warp;
   if (row >= N) return;
   const float4* cr = cand + (size_t)row * n_tiles;
@@ -1432,7 +1432,7 @@ struct TcSearchParams {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 nearest_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                  const TcSearchParams q) {
+                  const __grid_constant__ TcSearchParams q) {
   const TcConvParams& p = q.e;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_afull[2];
@@ -1442,7 +1442,7 @@ nearest_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smemB = smem0 + (uint32_t)q.a_bufs * q.a_buf_bytes;
   if (warp == 0 && lane == 0) {
