@@ -43,114 +43,73 @@ __device__ __forceinline__ void ru_trace(int dbg, int role, uint32_t& cnt, int t
                                       ((unsigned long long)clock64() & ((1ull << 44) - 1));
 }
 
-// epilogue A of one tile: TMEM acc1 -> staging -> (+b7, snake2, bf16 split) -> swizzled K-major h in shared memory
-template <int X3>
-__device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
-                                              uint8_t* hbuf, int warp, int lane) {
+// epilogue A of one tile: TMEM acc1 -> registers -> (+b7, snake2, bf16 split) -> swizzled K-major h in shared memory.
+// No staging tile and no barrier inside: a thread owns one accumulator row (its TMEM lane) and NC consecutive channels
+// of every 32-channel chunk, i.e. whole 16-byte units of the row UMMA reads; the per-channel constants are the same
+// for every lane of a warp (broadcast loads).  Row r's 16-byte unit u sits at unit (u ^ swizzle(r)): the 8 lanes of a
+// quarter-warp hit 8 different units = all 32 banks.
+template <int X3, int NC>
+__device__ __forceinline__ void ru_h_store(const TcRuParams& q, const float* v, int r, int co, uint8_t* hbuf) {
   const TcConvParams& p = q.e;
-  const int ew = warp - 2;
-  const int quad = warp & 3;
-  const int cg8 = ew >> 2;
-  const int et = threadIdx.x - 64;
-  const int cq = et & 7;
-  const int r0 = et >> 3;
-  const int nchunks = p.BN >> 5;
-  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
-  const uint32_t row_bytes = (uint32_t)p.BK * 2;
-  for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-    float* sb = stg + (p.stg_bufs == 2 ? (chunk_ctr & 1u) * (TC_BM * TC_STG_LD) : 0u);
-    const int co = c * 32 + cq * 4;
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q.bias7) bb = __ldg(reinterpret_cast<const float4*>(q.bias7 + co));
-    const float4 al = __ldg(reinterpret_cast<const float4*>(q.alpha2 + co));
-    const float4 ia = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + co));
-    {
-      float v[8];
-      tmem_ld8(t_src + c * 32, v);
-      float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    const int kb = co / p.BK, cin = co - kb * p.BK;
-    const uint32_t chunk16 = (uint32_t)cin >> 3, within = ((uint32_t)cin & 7u) * 2u;
+  const int kb = co / p.BK, cin = co - kb * p.BK;
+  const uint32_t sw = p.BK == 64 ? ((uint32_t)r & 7u) : (((uint32_t)r >> 1) & 3u);
+  uint8_t* row = hbuf + (uint32_t)kb * q.h_block_bytes + (uint32_t)r * ((uint32_t)p.BK * 2u);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = r0 + 64 * i;
-      float4 a = *reinterpret_cast<const float4*>(sb + r * TC_STG_LD + cq * 4);
-      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-      float4 w;
-      w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
-      w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
-      // K-major swizzled position of (row r, channel co): 16-byte chunk index XOR the row bits the TMA/UMMA swizzle
-      // uses (128B: r & 7; 64B: (r >> 1) & 3)
-      const uint32_t sw = p.BK == 64 ? ((uint32_t)r & 7u) : (((uint32_t)r >> 1) & 3u);
-      uint8_t* dst = hbuf + (uint32_t)kb * q.h_block_bytes + (uint32_t)r * row_bytes + ((chunk16 ^ sw) << 4) + within;
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
-      *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-      if (X3) {
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
-        const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
-        *reinterpret_cast<uint2*>(dst + q.h_plane_bytes) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  for (int u = 0; u < NC / 8; ++u) {
+    float w[8];
+    const int c0 = co + 8 * u;
+    const float4 b0 = q.bias7 ? __ldg(reinterpret_cast<const float4*>(q.bias7 + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b1 = q.bias7 ? __ldg(reinterpret_cast<const float4*>(q.bias7 + c0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(q.alpha2 + c0)), a1 = __ldg(reinterpret_cast<const float4*>(q.alpha2 + c0 + 4));
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + c0)), i1 = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + c0 + 4));
+    const float* x = v + 8 * u;
+    w[0] = snake_sel<!X3>(x[0] + b0.x, a0.x, i0.x); w[1] = snake_sel<!X3>(x[1] + b0.y, a0.y, i0.y);
+    w[2] = snake_sel<!X3>(x[2] + b0.z, a0.z, i0.z); w[3] = snake_sel<!X3>(x[3] + b0.w, a0.w, i0.w);
+    w[4] = snake_sel<!X3>(x[4] + b1.x, a1.x, i1.x); w[5] = snake_sel<!X3>(x[5] + b1.y, a1.y, i1.y);
+    w[6] = snake_sel<!X3>(x[6] + b1.z, a1.z, i1.z); w[7] = snake_sel<!X3>(x[7] + b1.w, a1.w, i1.w);
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(w[2 * e], w[2 * e + 1]);
+    uint8_t* dst = row + ((((uint32_t)(cin >> 3) + (uint32_t)u) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<const uint32_t*>(&h[0]), *reinterpret_cast<const uint32_t*>(&h[1]),
+                                                *reinterpret_cast<const uint32_t*>(&h[2]), *reinterpret_cast<const uint32_t*>(&h[3]));
+    if (X3) {
+      __nv_bfloat162 l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        l[e] = __floats2bfloat162_rn(w[2 * e] - f.x, w[2 * e + 1] - f.y);
       }
+      *reinterpret_cast<uint4*>(dst + q.h_plane_bytes) =
+          make_uint4(*reinterpret_cast<const uint32_t*>(&l[0]), *reinterpret_cast<const uint32_t*>(&l[1]),
+                     *reinterpret_cast<const uint32_t*>(&l[2]), *reinterpret_cast<const uint32_t*>(&l[3]));
     }
-    if (p.stg_bufs != 2) asm volatile("bar.sync 1, 512;" ::: "memory");
   }
 }
 
-// the same for one 8-warp epilogue group (see tc_epilogue_tile_g): thread = (float4 column group, rows r0 + 32 i)
+// 16 epilogue warps in lock step: warp = (TMEM lane quadrant, 8-channel slice of the chunk)
 template <int X3>
-__device__ __forceinline__ void ru_epilogue_h_g(const TcRuParams& q, float* stg_g, int g, uint32_t t_acc, uint8_t* hbuf,
-                                                int warp, int lane) {
-  const TcConvParams& p = q.e;
-  const int wg = (warp - 2) & 7;
-  const int quad = warp & 3;
-  const int half = wg >> 2;
-  const int et = (threadIdx.x - 64) & 255;
-  const int cq = et & 7;
-  const int r0 = et >> 3;
-  const int nchunks = p.BN >> 5;
-  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + half * 16;
-  const uint32_t row_bytes = (uint32_t)p.BK * 2;
+__device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, uint32_t t_acc, uint8_t* hbuf, int warp, int lane) {
+  const int quad = warp & 3, cg8 = (warp - 2) >> 2;
+  const int nchunks = q.e.BN >> 5;
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
   for (int c = 0; c < nchunks; ++c) {
-    const int co = c * 32 + cq * 4;
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q.bias7) bb = __ldg(reinterpret_cast<const float4*>(q.bias7 + co));
-    const float4 al = __ldg(reinterpret_cast<const float4*>(q.alpha2 + co));
-    const float4 ia = __ldg(reinterpret_cast<const float4*>(q.inv_alpha2 + co));
-    {
-      float v[16];
-      tmem_ld16(t_src + c * 32, v);
-      float* dst = stg_g + (quad * 32 + lane) * TC_STG_LD + half * 16;
-#pragma unroll
-      for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
-    }
-    epi_group_sync(g);
-    const int kb = co / p.BK, cin = co - kb * p.BK;
-    const uint32_t chunk16 = (uint32_t)cin >> 3, within = ((uint32_t)cin & 7u) * 2u;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + 32 * i;
-      float4 a = *reinterpret_cast<const float4*>(stg_g + r * TC_STG_LD + cq * 4);
-      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-      float4 w;
-      w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
-      w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
-      const uint32_t sw = p.BK == 64 ? ((uint32_t)r & 7u) : (((uint32_t)r >> 1) & 3u);
-      uint8_t* dst = hbuf + (uint32_t)kb * q.h_block_bytes + (uint32_t)r * row_bytes + ((chunk16 ^ sw) << 4) + within;
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
-      *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-      if (X3) {
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y);
-        const __nv_bfloat162 l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
-        *reinterpret_cast<uint2*>(dst + q.h_plane_bytes) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-      }
-    }
-    epi_group_sync(g);
+    float v[8];
+    tmem_ld8(t_src + c * 32, v);
+    ru_h_store<X3, 8>(q, v, quad * 32 + lane, c * 32 + cg8 * 8, hbuf);
+  }
+}
+
+// one 8-warp epilogue group: warp = (TMEM lane quadrant, 16-channel half of the chunk)
+template <int X3>
+__device__ __forceinline__ void ru_epilogue_h_g(const TcRuParams& q, uint32_t t_acc, uint8_t* hbuf, int warp, int lane) {
+  const int quad = warp & 3, half = ((warp - 2) & 7) >> 2;
+  const int nchunks = q.e.BN >> 5;
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + half * 16;
+  for (int c = 0; c < nchunks; ++c) {
+    float v[16];
+    tmem_ld16(t_src + c * 32, v);
+    ru_h_store<X3, 16>(q, v, quad * 32 + lane, c * 32 + half * 16, hbuf);
   }
 }
 
@@ -417,7 +376,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);
         tc_fence_after();
         if (leader) ru_trace(p.dbg, 2 + g, tcnt, 22, i);
-        if (!(p.dbg & 1)) ru_epilogue_h_g<X3>(q, stg_g, g, tmem_base + g * p.acc_stride, hbuf, warp, lane);
+        if (!(p.dbg & 1)) ru_epilogue_h_g<X3>(q, tmem_base + g * p.acc_stride, hbuf, warp, lane);
         tc_fence_before();
         fence_proxy_async();
         epi_group_sync(g);
@@ -434,7 +393,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           epi_group_sync(g);
           if (leader) mbar_arrive(smem_u32(&bar_t2empty[g]));
         } else {
-          tc_epilogue_tile_g(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
+          tc_epilogue_tile_g<!X3>(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
         }
         if (leader) ru_trace(p.dbg, 2 + g, tcnt, 25, i);
       }
@@ -453,7 +412,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(smem_u32(&bar_t1full[buf]), par, 8);
       mbar_wait(smem_u32(&bar_hempty), ((uint32_t)i & 1u) ^ 1u, 9);       // GEMM 2 of tile i-1 has read h
       tc_fence_after();
-      ru_epilogue_h<X3>(q, stg, chunk_ctr, tmem_base + buf * p.acc_stride, hbuf, warp, lane);
+      ru_epilogue_h<X3>(q, tmem_base + buf * p.acc_stride, hbuf, warp, lane);
       tc_fence_before();
       fence_proxy_async();                                                // generic-proxy smem writes -> async proxy (UMMA)
       asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -464,7 +423,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // ---- B: acc2 -> y
       mbar_wait(smem_u32(&bar_t2full[buf]), par, 10);
       tc_fence_after();
-      tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + (q.nbuf + buf) * p.acc_stride, b, 0, jt, 0,
+      tc_epilogue_tile<!X3>(p, stg, chunk_ctr, tmem_base + (q.nbuf + buf) * p.acc_stride, b, 0, jt, 0,
                        smem_u32(&bar_t2empty[buf]), warp, lane);
     }
   }
@@ -525,13 +484,15 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   p.tmem_cols = 2 * q.nbuf * p.acc_stride;
   q.h_plane_bytes = TC_BM * C * 2;
   const int h_total = (int)q.h_plane_bytes * planes;
-  // Slab mode halves the L2 -> SM traffic but measured no faster on B200 (64-ch bf16x3: 0.289 vs 0.289 ms, 128-ch:
-  // 0.398 vs 0.334 ms): these units are bound by per-tile pipeline hand-offs, not by L2 bandwidth.  Off by default
-  // (B2C_RU_SLAB=1 enables it for experiments).
-  bool want_slab = false;
+  // Slab mode: one activation slab per channel block serves the 7 taps, so the TMA ring carries weight tiles only
+  // (352 -> 176 KB of shared-memory fill per 64-channel bf16x3 tile).  Measured on B200 once the MMA issue loop was
+  // off the critical path: 64-ch bf16x3 0.285 -> 0.264 ms; 128-ch bf16x3 0.330 -> 0.375 and 96-ch bf16 0.308 -> 0.351
+  // (the slab slots cost those shapes ring stages).  Hence: on for C = 64 bf16x3 only; B2C_RU_SLAB=0/1 overrides.
+  bool want_slab = (C == 64 && plan->x3);
   {
     const char* e = getenv("B2C_RU_SLAB");
     if (e && e[0] == '1') want_slab = true;
+    if (e && e[0] == '0') want_slab = false;
   }
   bool done = false;
   int force_bk = 0, force_g = 0;                  // experiment knobs

@@ -285,6 +285,7 @@ __device__ __forceinline__ void tc_prefetch_res(const TcConvParams& p, int b, in
 // barrier the 512 threads re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the
 // bias / residual loads and the raw / activated stores are coalesced.  Two staging tiles alternate: one
 // barrier per chunk.  When tempty_bar != 0 it is arrived on once the accumulator has been drained.
+template <int SFU>
 __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
                                                  int b, int ph, int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
   const int ew = warp - 2;
@@ -341,8 +342,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
       if (p.out_act) {
         float4 w;
         if (p.act == ACT_SNAKE) {
-          w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
-          w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+          w.x = snake_sel<SFU>(a.x, al.x, ia.x); w.y = snake_sel<SFU>(a.y, al.y, ia.y);
+          w.z = snake_sel<SFU>(a.z, al.z, ia.z); w.w = snake_sel<SFU>(a.w, al.w, ia.w);
         } else {
           w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
           w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
@@ -394,6 +395,7 @@ __device__ __forceinline__ void tc_prefetch_res_g(const TcConvParams& p, int b, 
   }
 }
 
+template <int SFU>
 __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float* stg_g, int g, uint32_t t_acc, int b, int ph,
                                                    int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
   const int wg = (warp - 2) & 7;
@@ -449,8 +451,8 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
       if (p.out_act) {
         float4 w;
         if (p.act == ACT_SNAKE) {
-          w.x = snake_fast(a.x, al.x, ia.x); w.y = snake_fast(a.y, al.y, ia.y);
-          w.z = snake_fast(a.z, al.z, ia.z); w.w = snake_fast(a.w, al.w, ia.w);
+          w.x = snake_sel<SFU>(a.x, al.x, ia.x); w.y = snake_sel<SFU>(a.y, al.y, ia.y);
+          w.z = snake_sel<SFU>(a.z, al.z, ia.z); w.w = snake_sel<SFU>(a.w, al.w, ia.w);
         } else {
           w.x = apply_act(a.x, p.act, 0.f); w.y = apply_act(a.y, p.act, 0.f);
           w.z = apply_act(a.z, p.act, 0.f); w.w = apply_act(a.w, p.act, 0.f);
@@ -698,7 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           epi_group_sync(g);
           if (((threadIdx.x - 64) & 255) == 0) mbar_arrive(smem_u32(&bar_tempty[g]));
         } else {
-          tc_epilogue_tile_g(p, stg_g, g, tmem_base + g * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[g]), warp, lane);
+          tc_epilogue_tile_g<!X3>(p, stg_g, g, tmem_base + g * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[g]), warp, lane);
         }
       }
     } else {
@@ -729,7 +731,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           asm volatile("bar.sync 1, 512;" ::: "memory");
           if (threadIdx.x == 64) mbar_arrive(smem_u32(&bar_tempty[acc]));
         } else if (EPI == 0)
-          tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
+          tc_epilogue_tile<!X3>(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
                            warp, lane);
         else
           tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, jt, nt, smem_u32(&bar_tempty[acc]), warp, lane);
@@ -909,7 +911,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait_epilogue(smem_u32(&bar_tfull[acc]), apar, 6);
       tc_fence_after();
       for (int m = 0; m < n_m; ++m)
-        tc_epilogue_tile(p, stg, chunk_ctr, tmem_base + acc * set_cols + m * p.acc_stride, b, ph, jg * p.MT + m, nt,
+        tc_epilogue_tile<!X3>(p, stg, chunk_ctr, tmem_base + acc * set_cols + m * p.acc_stride, b, ph, jg * p.MT + m, nt,
                          m == n_m - 1 ? smem_u32(&bar_tempty[acc]) : 0u, warp, lane);
     }
   }
