@@ -915,14 +915,30 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         d.codes = R.get<int>(op.r[2]);
         d.w = ctx->w[op.wid].dev;
         if (R.bad || !d.z || !d.zq || !d.codes) return fail(B2C_ERR_WORKSPACE, "op %zu (dac rvq): unresolved buffer", oi);
-        int blocks = (d.N + DACRVQ_WARPS - 1) / DACRVQ_WARPS;
         const size_t sm = 2 * (size_t)(17 * d.C + 9 * d.K + 8) * sizeof(float);
         if (sm > 227 * 1024) return fail(B2C_ERR_UNSUPPORTED, "dac rvq: C=%d K=%d needs %zu bytes of shared memory", d.C, d.K, sm);
-#define B2C_DACRVQ(CPL)                                                                                         \
-  {                                                                                                             \
-    cudaError_t e = cudaFuncSetAttribute(dac_rvq_f32<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "dac rvq smem: %s", cudaGetErrorString(e));                 \
-    dac_rvq_f32<CPL><<<blocks, 32 * DACRVQ_WARPS, sm, st>>>(d);                                                 \
+        // Large batches: two tokens per warp (each weight read from shared memory serves both) and the warp count
+        // that minimises (waves of CTAs) x (per-CTA time ~ fixed stage streaming + warps); small batches keep one
+        // token per warp and 8 warps (more CTAs in flight, shortest latency).  Results do not depend on the choice.
+        int tpw = 1, warps = DACRVQ_WARPS;
+        if (d.C / 32 <= 32 && (long)d.N >= (long)DACRVQ_WARPS * ctx->sm_count) {
+          tpw = 2;
+          long best_cost = -1;
+          for (int w = 4; w <= DACRVQ_MAX_WARPS; ++w) {
+            const long ctas = (d.N + 2L * w - 1) / (2L * w);
+            const long waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+            const long cost = waves * (6 + w);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; warps = w; }
+          }
+        }
+        const int blocks = (d.N + tpw * warps - 1) / (tpw * warps);
+#define B2C_DACRVQ(CPL)                                                                                             \
+  {                                                                                                                 \
+    cudaError_t e = tpw == 2 ? cudaFuncSetAttribute(dac_rvq_f32<CPL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) \
+                             : cudaFuncSetAttribute(dac_rvq_f32<CPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "dac rvq smem: %s", cudaGetErrorString(e));                     \
+    if (tpw == 2) dac_rvq_f32<CPL, 2><<<blocks, 32 * warps, sm, st>>>(d);                                           \
+    else dac_rvq_f32<CPL, 1><<<blocks, 32 * warps, sm, st>>>(d);                                                    \
   }
         switch (d.C / 32) {
           case 32: B2C_DACRVQ(32) break;

@@ -842,27 +842,40 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
                : "memory");
 }
 
-constexpr int DACRVQ_WARPS = 8;    // tokens per CTA (16 was measured slower on B200: 0.61 vs 0.52 ms at 2400 tokens)
+constexpr int DACRVQ_WARPS = 8;    // warps per CTA of the one-token-per-warp form (16 was measured slower on B200)
+constexpr int DACRVQ_MAX_WARPS = 10;
 
-template <int CPL>
-__global__ void __launch_bounds__(32 * DACRVQ_WARPS, 1) dac_rvq_f32(const DacRvqArgs p) {
+// T tokens per warp: every shared-memory read of a stage weight (in_proj row, normalised codebook column, out_proj
+// row) then serves T tokens -- the kernel is bound by those reads (96 KB per token and stage at T = 1) and by the
+// 106 KB of stage weights each CTA streams from L2 per stage, which T x more tokens per CTA amortise.  Per-token
+// arithmetic and its order are identical for every T (bit-identical results); blockDim.x / 32 warps per CTA.
+template <int CPL, int T>
+__global__ void __launch_bounds__(32 * DACRVQ_MAX_WARPS, 1) dac_rvq_f32(const DacRvqArgs p) {
   extern __shared__ __align__(16) float wsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * DACRVQ_WARPS + warp;
-  const bool live = n < p.N;
+  const int nwarps = blockDim.x >> 5;
+  const int n0 = (blockIdx.x * nwarps + warp) * T;
   const int C = p.C, K = p.K;
   const int staged = 17 * C + 9 * K + 8;
-  float r[CPL], zq[CPL];
+  float r[T][CPL], zq[T][CPL];
+  bool live[T];
+  int bb[T], tt[T];
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    r[i] = live ? __ldg(p.z + (long)n * C + lane + 32 * i) : 0.f;
-    zq[i] = 0.f;
+  for (int u = 0; u < T; ++u) {
+    const int n = n0 + u;
+    live[u] = n < p.N;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      r[u][i] = live[u] ? __ldg(p.z + (long)n * C + lane + 32 * i) : 0.f;
+      zq[u][i] = 0.f;
+    }
+    bb[u] = live[u] ? n / p.Tl : 0;
+    tt[u] = live[u] ? n - bb[u] * p.Tl : 0;
   }
-  const int b = live ? n / p.Tl : 0, t = live ? n - b * p.Tl : 0;
   auto prefetch = [&](int st, int buf) {
     const float4* src = reinterpret_cast<const float4*>(p.w + (long)st * p.stage_stride);
     float4* dst = reinterpret_cast<float4*>(wsm + (long)buf * staged);
-    for (int i = threadIdx.x; i < staged / 4; i += 32 * DACRVQ_WARPS) cp_async16(dst + i, src + i);
+    for (int i = threadIdx.x; i < staged / 4; i += blockDim.x) cp_async16(dst + i, src + i);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   prefetch(0, 0);
@@ -881,73 +894,107 @@ __global__ void __launch_bounds__(32 * DACRVQ_WARPS, 1) dac_rvq_f32(const DacRvq
     const float* WoutT = c2 + K;
     const float* bout = WoutT + 8 * C;
     const float* cb = p.w + (long)st * p.stage_stride + staged;
-    if (live) {
+    if (live[0]) {
       // in_proj (1x1 conv C -> 8)
-      float ze[8];
+      float ze[T][8];
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
-        float s = 0.f;
+        float s[T];
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) s = fmaf(Win[d * C + lane + 32 * i], r[i], s);
+        for (int u = 0; u < T; ++u) s[u] = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        ze[d] = __fadd_rn(s, bin[d]);
+        for (int i = 0; i < CPL; ++i) {
+          const float wv = Win[d * C + lane + 32 * i];
+#pragma unroll
+          for (int u = 0; u < T; ++u) s[u] = fmaf(wv, r[u][i], s[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+          ze[u][d] = __fadd_rn(s[u], bin[d]);
+        }
       }
       // F.normalize(encodings): x / max(|x|, 1e-12)
-      float nn = 0.f;
+      float en2[T][8], e2[T];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) nn = fmaf(ze[d], ze[d], nn);
-      const float den = fmaxf(sqrtf(nn), 1e-12f);
-      float en[8];
-      float e2 = 0.f;
+      for (int u = 0; u < T; ++u) {
+        float nn = 0.f;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { en[d] = __fdiv_rn(ze[d], den); }
+        for (int d = 0; d < 8; ++d) nn = fmaf(ze[u][d], ze[u][d], nn);
+        const float den = fmaxf(sqrtf(nn), 1e-12f);
+        float en[8];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) e2 = __fadd_rn(e2, __fmul_rn(en[d], en[d]));
+        for (int d = 0; d < 8; ++d) en[d] = __fdiv_rn(ze[u][d], den);
+        e2[u] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) e2[u] = __fadd_rn(e2[u], __fmul_rn(en[d], en[d]));
+#pragma unroll
+        for (int d = 0; d < 8; ++d) en2[u][d] = 2.f * en[d];
+      }
       // dist = |enc|^2 - 2 enc.cb + |cb|^2 ; first minimum of dist (== first maximum of -dist)
-      float best = INFINITY;
-      int bi = 0x7fffffff;
+      float best[T];
+      int bi[T];
+#pragma unroll
+      for (int u = 0; u < T; ++u) { best[u] = INFINITY; bi[u] = 0x7fffffff; }
       for (int k = lane; k < K; k += 32) {
-        float dot = (2.f * en[0]) * cbnT[k];
+        float cv[8];
 #pragma unroll
-        for (int d = 1; d < 8; ++d) dot = fmaf(2.f * en[d], cbnT[d * K + k], dot);
-        float dist = __fadd_rn(__fsub_rn(e2, dot), c2[k]);
-        if (dist < best) { best = dist; bi = k; }
+        for (int d = 0; d < 8; ++d) cv[d] = cbnT[d * K + k];
+        const float ck = c2[k];
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+          float dot = en2[u][0] * cv[0];
+#pragma unroll
+          for (int d = 1; d < 8; ++d) dot = fmaf(en2[u][d], cv[d], dot);
+          const float dist = __fadd_rn(__fsub_rn(e2[u], dot), ck);
+          if (dist < best[u]) { best[u] = dist; bi[u] = k; }
+        }
       }
+      float stv[T][8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float os = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
-      }
-      if (bi >= K) bi = 0;
-      if (lane == 0) p.codes[((long)b * p.n_q + st) * p.Tl + t] = bi;
-      // straight-through value z_e + (z_q - z_e), then out_proj (1x1 conv 8 -> C)
-      float stv[8];
-      {
-        float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8));
-        float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8 + 4));
-        float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      for (int u = 0; u < T; ++u) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) stv[d] = __fadd_rn(ze[d], __fsub_rn(qv[d], ze[d]));
+        for (int o = 16; o > 0; o >>= 1) {
+          const float os = __shfl_xor_sync(0xffffffffu, best[u], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi[u], o);
+          if (os < best[u] || (os == best[u] && oi < bi[u])) { best[u] = os; bi[u] = oi; }
+        }
+        if (bi[u] >= K) bi[u] = 0;
+        if (lane == 0 && live[u]) p.codes[((long)bb[u] * p.n_q + st) * p.Tl + tt[u]] = bi[u];
+        // straight-through value z_e + (z_q - z_e), then out_proj (1x1 conv 8 -> C)
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi[u] * 8));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi[u] * 8 + 4));
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) stv[u][d] = __fadd_rn(ze[u][d], __fsub_rn(qv[d], ze[u][d]));
       }
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         const int c = lane + 32 * i;
-        float o = WoutT[c] * stv[0];
+        float wv[8];
 #pragma unroll
-        for (int d = 1; d < 8; ++d) o = fmaf(WoutT[d * C + c], stv[d], o);
-        o = __fadd_rn(o, bout[c]);
-        zq[i] = __fadd_rn(zq[i], o);
-        r[i] = __fsub_rn(r[i], o);
+        for (int d = 0; d < 8; ++d) wv[d] = WoutT[d * C + c];
+        const float bo = bout[c];
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+          float o = wv[0] * stv[u][0];
+#pragma unroll
+          for (int d = 1; d < 8; ++d) o = fmaf(wv[d], stv[u][d], o);
+          o = __fadd_rn(o, bo);
+          zq[u][i] = __fadd_rn(zq[u][i], o);
+          r[u][i] = __fsub_rn(r[u][i], o);
+        }
       }
     }
     __syncthreads();   // this buffer is refilled by the prefetch issued at the top of iteration st + 1
   }
-  if (live) {
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) p.zq[(long)n * C + lane + 32 * i] = zq[i];
-  }
+  for (int u = 0; u < T; ++u)
+    if (live[u]) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) p.zq[(long)(n0 + u) * C + lane + 32 * i] = zq[u][i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
