@@ -807,7 +807,26 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           dim3 grid((L + 127) / 128, B);
           const size_t xn = (size_t)B * L * w.cin;
           cudaError_t e;
-          if (op.x_fmt == B2C_FMT_BF16X2) {
+          if (w.cin % 32 == 0 && w.cin <= 128) {
+            // sliding-window head: weights in registers, each staged row read once per channel group
+            const size_t sw_sm = (size_t)(128 + 6) * (w.cin + 4) * sizeof(float);
+            const bool planes = op.x_fmt == B2C_FMT_BF16X2;
+#define B2C_HEAD_SW(UPT)                                                                                                   \
+  {                                                                                                                        \
+    e = planes ? cudaFuncSetAttribute(head_k7_tanh_sw<FMT_PLANES, UPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_sm) \
+               : cudaFuncSetAttribute(head_k7_tanh_sw<FMT_HI, UPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_sm);    \
+    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "head smem: %s", cudaGetErrorString(e));                              \
+    if (planes) head_k7_tanh_sw<FMT_PLANES, UPT><<<grid, 128, sw_sm, st>>>(x, w.dev, w.bias, y, L, xn);                   \
+    else head_k7_tanh_sw<FMT_HI, UPT><<<grid, 128, sw_sm, st>>>(x, w.dev, w.bias, y, L, xn);                              \
+  }
+            switch (w.cin / 32) {
+              case 1: B2C_HEAD_SW(1) break;
+              case 2: B2C_HEAD_SW(2) break;
+              case 3: B2C_HEAD_SW(3) break;
+              default: B2C_HEAD_SW(4) break;
+            }
+#undef B2C_HEAD_SW
+          } else if (op.x_fmt == B2C_FMT_BF16X2) {
             e = cudaFuncSetAttribute(head_k7_tanh_tiled<FMT_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_sm);
             if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "head smem: %s", cudaGetErrorString(e));
             head_k7_tanh_tiled<FMT_PLANES><<<grid, 128, tiled_sm, st>>>(x, w.dev, w.bias, y, L, w.cin, xn);
@@ -883,14 +902,20 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           float* resid = reinterpret_cast<float*>(op.scratch);
           unsigned long long* keys = reinterpret_cast<unsigned long long*>(
               reinterpret_cast<char*>(op.scratch) + ((size_t)r.N * r.D * 4 + 255) / 256 * 256);
-          const size_t sm = ((size_t)32 * r.D + 64 * (r.D + 1)) * sizeof(float);
-          cudaError_t e = cudaFuncSetAttribute(rvq_scores_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          // 128-code slices (4 codes per lane) once the token blocks alone fill the GPU, else 64-code slices (more CTAs)
+          const bool wide_codes = (long)((r.N + 31) / 32) * ((r.K + 127) / 128) >= 2L * ctx->sm_count;
+          const int ch = wide_codes ? 128 : 64;
+          const size_t sm = ((size_t)32 * r.D + (size_t)ch * (r.D + 4)) * sizeof(float);
+          cudaError_t e = wide_codes ? cudaFuncSetAttribute(rvq_scores_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                                     : cudaFuncSetAttribute(rvq_scores_f32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
           if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
-          dim3 grid((r.N + 31) / 32, (r.K + 63) / 64);
+          dim3 grid((r.N + 31) / 32, (r.K + ch - 1) / ch);
           for (int bk = 0; bk < r.books_use; ++bk) {
-            rvq_scores_f32<<<grid, 256, sm, st>>>(bk == 0 ? r.x : resid, r.books + (size_t)bk * r.K * r.D,
-                                                  r.half_n + (size_t)bk * r.K, keys, r.N, r.D, r.K);
-            rvq_apply_f32<<<(r.N + 7) / 8, 256, 0, st>>>(r, r.books + (size_t)bk * r.K * r.D, resid, keys, bk);
+            const float* src = bk == 0 ? r.x : resid;
+            const float* book = r.books + (size_t)bk * r.K * r.D;
+            if (wide_codes) rvq_scores_f32<4><<<grid, 256, sm, st>>>(src, book, r.half_n + (size_t)bk * r.K, keys, r.N, r.D, r.K);
+            else rvq_scores_f32<2><<<grid, 256, sm, st>>>(src, book, r.half_n + (size_t)bk * r.K, keys, r.N, r.D, r.K);
+            rvq_apply_f32<<<(r.N + 7) / 8, 256, 0, st>>>(r, book, resid, keys, bk);
           }
         } else if (r.books_use > 0) {
           // 32 tokens per CTA when that still gives every SM two CTAs, else 8 (one per warp)

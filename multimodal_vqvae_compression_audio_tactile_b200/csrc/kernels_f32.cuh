@@ -354,6 +354,93 @@ __global__ void __launch_bounds__(256) stem_k7_planes(const float* __restrict__ 
   }
 }
 
+// Decoder head, sliding window (tensor-core plans, Cin = 32 * UPT): the CTA stages 128 + 6 channel-last rows in shared
+// memory as fp32; thread = (16 segments of 8 positions) x (8 channel groups).  A thread keeps the 7 x (4 * UPT) weights
+// of its channel group in registers and walks the 14 rows of its segment: each row is loaded once (UPT float4 reads,
+// the 8 lanes of a quarter-warp read 8 different 16-byte units: no bank conflicts) and feeds up to 7 outputs, so
+// shared-memory reads drop 8x against the one-position-per-thread form, which was bound by them (0.37 ms per 64
+// frames for 2 x 6.1 GFLOP).  The 8 channel-group partials of a position are lanes g = 0..7: three shuffles.
+template <int FMT, int UPT>
+__global__ void __launch_bounds__(128) head_k7_tanh_sw(const void* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int L,
+                                                        size_t x_n) {
+  constexpr int TP = 128, Cin = 32 * UPT, ld = Cin + 4;
+  extern __shared__ __align__(16) float hsm[];
+  float* xs = hsm;                    // [TP + 6][ld]
+  const int b = blockIdx.y, l0 = blockIdx.x * TP;
+  const int g = threadIdx.x & 7, seg = threadIdx.x >> 3;
+  float wr[7][4 * UPT];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w + r * Cin + 4 * (g + 8 * u)));
+      wr[r][4 * u] = v.x; wr[r][4 * u + 1] = v.y; wr[r][4 * u + 2] = v.z; wr[r][4 * u + 3] = v.w;
+    }
+  constexpr int vec_per_row = Cin >> 3;
+  for (int v = threadIdx.x; v < (TP + 6) * vec_per_row; v += 128) {
+    const int r = v / vec_per_row, c = (v - r * vec_per_row) * 8;
+    const int l = l0 + r - 3;
+    float f[8];
+    if (l >= 0 && l < L) {
+      const size_t e = ((size_t)b * L + l) * Cin + c;
+      const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(xb + e));
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(hp[q]); f[2 * q] = t2.x; f[2 * q + 1] = t2.y; }
+      if (FMT == FMT_PLANES) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(xb + x_n + e));
+        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&lo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(lp[q]); f[2 * q] += t2.x; f[2 * q + 1] += t2.y; }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = 0.f;
+    }
+    *reinterpret_cast<float4*>(xs + r * ld + c) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(xs + r * ld + c + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {            // staged row seg * 8 + j = input position l0 + seg * 8 + j - 3
+    const float* xr = xs + (seg * 8 + j) * ld;
+    float xv[4 * UPT];
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + 4 * (g + 8 * u));
+      xv[4 * u] = v.x; xv[4 * u + 1] = v.y; xv[4 * u + 2] = v.z; xv[4 * u + 3] = v.w;
+    }
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int o = j - r;                  // output seg * 8 + o uses this row with tap r
+      if (o >= 0 && o < 8) {
+#pragma unroll
+        for (int c = 0; c < 4 * UPT; ++c) acc[o] = fmaf(xv[c], wr[r][c], acc[o]);
+      }
+    }
+  }
+  const float bv = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float v = acc[o];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    acc[o] = v;
+  }
+  // lane g of each group of 8 writes output o = g: one coalesced 32-byte store per segment
+  float mine = acc[0];
+#pragma unroll
+  for (int o = 1; o < 8; ++o) mine = (g == o) ? acc[o] : mine;
+  const int l = l0 + seg * 8 + g;
+  if (l < L) y[(size_t)b * L + l] = tanhf(__fadd_rn(mine, bv));
+}
+
 // Decoder head, tiled: a CTA stages 128 + 6 rows of the channel-last input (contiguous in memory) in shared
 // memory as fp32 with a padded row (Cin + 4 words: conflict-free float4 reads), thread t computes position t.
 // Cin % 8 == 0.  Reads each input element once from HBM.
@@ -717,14 +804,19 @@ __device__ __forceinline__ unsigned long long rvq_key(float score, int idx) {
   return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx);
 }
 
+// CPT codes per lane (CH = 32 * CPT codes per CTA) x 4 tokens per warp.  With D % 4 == 0 the shared-memory tiles are
+// read as float4 along d: 4 + CPT 16-byte loads feed 16 * CPT FMAs (the 2-code scalar form was bound by its 6 loads
+// per 8 FMAs).  Every (token, code) dot product is one fmaf chain over d = 0 .. D-1 in either form: identical bits.
+template <int CPT>
 __global__ void __launch_bounds__(256) rvq_scores_f32(const float* __restrict__ res, const float* __restrict__ book,
                                                       const float* __restrict__ hn, unsigned long long* __restrict__ keys,
                                                       int N, int D, int K) {
-  constexpr int TPW = 4, CH = 64, TOK = 32;
-  extern __shared__ float sm[];
-  const int DP = D + 1;
+  constexpr int TPW = 4, CH = 32 * CPT, TOK = 32;
+  extern __shared__ __align__(16) float sm[];
+  const bool vec = (D & 3) == 0;
+  const int DP = vec ? D + 4 : D + 1;   // row pitch of the code tile: conflict-free for float4 / scalar reads
   float* xs = sm;               // [TOK][D]
-  float* es = sm + TOK * D;     // [CH][D+1]
+  float* es = sm + TOK * D;     // [CH][DP]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TOK, c0 = blockIdx.y * CH;
   for (int i = threadIdx.x; i < TOK * D; i += 256) xs[i] = (n0 + i / D < N) ? __ldg(res + (long)n0 * D + i) : 0.f;
@@ -733,19 +825,40 @@ __global__ void __launch_bounds__(256) rvq_scores_f32(const float* __restrict__ 
     es[r * DP + d] = (c0 + r < K) ? __ldg(book + (long)c0 * D + i) : 0.f;
   }
   __syncthreads();
-  float acc[TPW][2];
+  float acc[TPW][CPT];
 #pragma unroll
-  for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = 0.f;
-  const float* e0 = es + lane * DP;
-  const float* e1 = es + (lane + 32) * DP;
+  for (int t = 0; t < TPW; ++t)
+#pragma unroll
+    for (int h = 0; h < CPT; ++h) acc[t][h] = 0.f;
   const float* xw = xs + warp * TPW * D;
-  for (int d = 0; d < D; ++d) {
-    const float ev0 = e0[d], ev1 = e1[d];
+  if (vec) {
+    for (int d = 0; d < D; d += 4) {
+      float4 ev[CPT], xv[TPW];
 #pragma unroll
-    for (int t = 0; t < TPW; ++t) {
-      const float xv = xw[t * D + d];
-      acc[t][0] = fmaf(xv, ev0, acc[t][0]);
-      acc[t][1] = fmaf(xv, ev1, acc[t][1]);
+      for (int h = 0; h < CPT; ++h) ev[h] = *reinterpret_cast<const float4*>(es + (lane + 32 * h) * DP + d);
+#pragma unroll
+      for (int t = 0; t < TPW; ++t) xv[t] = *reinterpret_cast<const float4*>(xw + t * D + d);
+#pragma unroll
+      for (int t = 0; t < TPW; ++t)
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) {
+          float a = acc[t][h];
+          a = fmaf(xv[t].x, ev[h].x, a); a = fmaf(xv[t].y, ev[h].y, a);
+          a = fmaf(xv[t].z, ev[h].z, a); a = fmaf(xv[t].w, ev[h].w, a);
+          acc[t][h] = a;
+        }
+    }
+  } else {
+    for (int d = 0; d < D; ++d) {
+      float ev[CPT];
+#pragma unroll
+      for (int h = 0; h < CPT; ++h) ev[h] = es[(lane + 32 * h) * DP + d];
+#pragma unroll
+      for (int t = 0; t < TPW; ++t) {
+        const float xv = xw[t * D + d];
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) acc[t][h] = fmaf(xv, ev[h], acc[t][h]);
+      }
     }
   }
   float best[TPW];
@@ -753,7 +866,7 @@ __global__ void __launch_bounds__(256) rvq_scores_f32(const float* __restrict__ 
 #pragma unroll
   for (int t = 0; t < TPW; ++t) { best[t] = -INFINITY; bidx[t] = 0x7fffffff; }
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < CPT; ++h) {
     const int code = c0 + lane + 32 * h;
     if (code < K) {
       const float hv = __ldg(hn + code);
@@ -778,8 +891,6 @@ __global__ void __launch_bounds__(256) rvq_scores_f32(const float* __restrict__ 
     if (lane == 0 && n < N && bi < K) atomicMax(keys + n, rvq_key(bs, bi));
   }
 }
-
-// one warp per token: winner -> index, q_sum = (q_sum + (q - r)) + r, r -= q  (:433-434), key reset for the next book
 __global__ void __launch_bounds__(256) rvq_apply_f32(const RvqArgs p, const float* __restrict__ book, float* __restrict__ res,
                                                      unsigned long long* __restrict__ keys, int bk) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
