@@ -861,7 +861,10 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         a.out = R.get<float>(op.r[2]);
         if (R.bad || !a.q || !a.kv || !a.out) return fail(B2C_ERR_WORKSPACE, "op %zu (attention): unresolved buffer", oi);
         int blocks = a.q_mode != 1 ? a.B * a.nchunks : a.B * a.nfix;
-        attention_chunk_f32<<<blocks, 32 * a.heads, 0, st>>>(a);
+        // a warp walks its queries serially: split the queries of a chunk over 4 CTAs (large batches) or one CTA per
+        // query (small batches, where the walk is the whole latency); the K / V rows are re-read from L2
+        const int qsplit = a.q_mode == 1 ? 1 : (blocks >= ctx->sm_count ? 4 : (a.chunk < 16 ? a.chunk : 16));
+        attention_chunk_f32<<<dim3(blocks, qsplit), 32 * a.heads, 0, st>>>(a);
         break;
       }
       case OP_RVQ:
@@ -897,7 +900,20 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           const char* e = getenv("B2C_RVQ_SPLIT");
           rvq_split = (e && e[0] == '0') ? 0 : 1;
         }
-        if (r.books_use > 0 && op.type == OP_RVQ && op.scratch && rvq_split && r.qsum) {
+        static int rvq_fused = -1;
+        if (rvq_fused < 0) {
+          const char* e = getenv("B2C_RVQ_FUSED");
+          rvq_fused = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (r.books_use > 0 && op.type == OP_RVQ && r.qsum && rvq_fused && (r.D & 3) == 0 && r.D <= 128 &&
+            (long)((r.N + 31) / 32) * 2 >= ctx->sm_count) {
+          // enough 32-token blocks to occupy the GPU: one launch for all books.  (16-token CTAs, two per SM, measured
+          // slower: 0.37 vs 0.28 ms at 4800 tokens -- the code tiles are then streamed twice as often.)
+          const size_t sm = ((size_t)32 * r.D + (size_t)2 * 128 * (r.D + 4)) * sizeof(float);
+          cudaError_t e = cudaFuncSetAttribute(rvq_books_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
+          rvq_books_f32<4><<<(r.N + 31) / 32, 256, sm, st>>>(r);
+        } else if (r.books_use > 0 && op.type == OP_RVQ && op.scratch && rvq_split && r.qsum) {
           // per book: scores over (token block x code slice) CTAs with an atomic arg-max, then apply
           float* resid = reinterpret_cast<float*>(op.scratch);
           unsigned long long* keys = reinterpret_cast<unsigned long long*>(

@@ -616,6 +616,8 @@ __global__ void __launch_bounds__(256) attention_chunk_f32(const AttnArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= p.heads) return;
   const int C = p.heads * 128;
+  // gridDim.y > 1 (q_mode != 1, large batches): the queries of a chunk are split over gridDim.y CTAs -- a warp walks
+  // its queries serially (16 dot products x 5 shuffles each), so shorter walks are what shortens the kernel
   int b, ck;
   if (p.q_mode != 1) { b = blockIdx.x / p.nchunks; ck = blockIdx.x % p.nchunks; }
   else { b = blockIdx.x / p.nfix; ck = blockIdx.x % p.nfix + 1; }
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(256) attention_chunk_f32(const AttnArgs p) {
   }
   const int nq = p.q_mode != 1 ? tk : 1;
   const float inv_sqrt_dh = 11.313708498984761f;  // sqrt(128): the reference divides by it (:401)
-  for (int i = 0; i < nq; ++i) {
+  for (int i = blockIdx.y; i < nq; i += gridDim.y) {
     const float* qrow = p.q_mode == 0 ? p.q + (long)i * C
                         : p.q_mode == 1 ? p.q + (long)blockIdx.x * C
                                         : p.q + ((long)b * p.Tl + s + i) * C;
@@ -798,6 +800,12 @@ __global__ void __launch_bounds__(256) rvq_f32(const RvqArgs p) {
 // torch.argmax's first maximum.  Scores use rvq_f32's arithmetic (sequential fmaf over d, minus 0.5|e|^2), so the
 // indices are bit-identical to the fused kernel's.  The batch-1 streaming path drops from ~0.6 ms to < 0.1 ms.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+
 __device__ __forceinline__ unsigned long long rvq_key(float score, int idx) {
   unsigned int u = __float_as_uint(score);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // monotone map float -> uint
@@ -891,6 +899,143 @@ __global__ void __launch_bounds__(256) rvq_scores_f32(const float* __restrict__ 
     if (lane == 0 && n < N && bi < K) atomicMax(keys + n, rvq_key(bs, bi));
   }
 }
+// All books in ONE launch (large batches): a CTA owns 32 tokens (4 per warp) for the whole residual loop.  Per book the
+// code slices (128 codes) stream through a double-buffered shared-memory tile (cp.async), every lane keeps the first
+// maximum over its codes across the slices, one warp reduction per book gives the index, and the warp that owns a
+// token applies q_sum / residual itself -- no grid-wide hand-off between the score and apply steps, 1 launch instead
+// of 2 per book.  Scores, tie-breaking and the q_sum / residual op order are those of rvq_scores_f32 + rvq_apply_f32
+// (identical bits); D % 4 == 0, D <= 128.  TPW tokens per warp: 4, or 2 when that is what gives every SM two CTAs.
+template <int TPW>
+__global__ void __launch_bounds__(256) rvq_books_f32(const RvqArgs p) {
+  constexpr int CPT = 4, CH = 128, TOK = 8 * TPW;
+  extern __shared__ __align__(16) float sm[];
+  const int D = p.D, DP = D + 4, K = p.K;
+  float* xs = sm;                       // [TOK][D] residual (rows of warp w are touched by warp w only)
+  float* es0 = sm + TOK * D;            // 2 x [CH][DP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TOK;
+  const int n_slices = (K + CH - 1) / CH;
+  const int vec_row = D >> 2;           // 16-byte units per code row
+  auto prefetch = [&](int bk, int sl, int buf) {
+    const float* src = p.books + ((size_t)bk * K + (size_t)sl * CH) * D;
+    float* dst = es0 + (size_t)buf * CH * DP;
+    const int rows = min(CH, K - sl * CH);
+    for (int i = threadIdx.x; i < rows * vec_row; i += 256) {
+      const int r = i / vec_row, u = i - r * vec_row;
+      cp_async16(dst + r * DP + 4 * u, src + (size_t)r * D + 4 * u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0, 0);
+  for (int i = threadIdx.x; i < TOK * D; i += 256) xs[i] = (n0 + i / D < p.N) ? __ldg(p.x + (size_t)n0 * D + i) : 0.f;
+  float qs[TPW][4];
+#pragma unroll
+  for (int t = 0; t < TPW; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qs[t][j] = 0.f;
+  const float* xw = xs + warp * TPW * D;
+  int it = 0;
+  for (int bk = 0; bk < p.books_use; ++bk) {
+    float best[TPW];
+    int bidx[TPW];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) { best[t] = -INFINITY; bidx[t] = 0x7fffffff; }
+    for (int sl = 0; sl < n_slices; ++sl, ++it) {
+      // next slice (possibly of the next book) goes into the other buffer while this one is scored
+      int nb = bk, ns = sl + 1;
+      if (ns == n_slices) { ns = 0; ++nb; }
+      if (nb < p.books_use) {
+        prefetch(nb, ns, (it + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const float* es = es0 + (size_t)(it & 1) * CH * DP;
+      float acc[TPW][CPT];
+#pragma unroll
+      for (int t = 0; t < TPW; ++t)
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) acc[t][h] = 0.f;
+      for (int d = 0; d < D; d += 4) {
+        float4 ev[CPT], xv[TPW];
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) ev[h] = *reinterpret_cast<const float4*>(es + (lane + 32 * h) * DP + d);
+#pragma unroll
+        for (int t = 0; t < TPW; ++t) xv[t] = *reinterpret_cast<const float4*>(xw + t * D + d);
+#pragma unroll
+        for (int t = 0; t < TPW; ++t)
+#pragma unroll
+          for (int h = 0; h < CPT; ++h) {
+            float a = acc[t][h];
+            a = fmaf(xv[t].x, ev[h].x, a); a = fmaf(xv[t].y, ev[h].y, a);
+            a = fmaf(xv[t].z, ev[h].z, a); a = fmaf(xv[t].w, ev[h].w, a);
+            acc[t][h] = a;
+          }
+      }
+#pragma unroll
+      for (int h = 0; h < CPT; ++h) {
+        const int code = sl * CH + lane + 32 * h;
+        if (code < K) {
+          const float hv = __ldg(p.half_n + (size_t)bk * K + code);
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) {
+            const float sc = __fsub_rn(acc[t][h], hv);
+            if (sc > best[t]) { best[t] = sc; bidx[t] = code; }
+          }
+        }
+      }
+      __syncthreads();      // the buffer scored here is refilled by the prefetch of the next iteration
+    }
+    // index of the first maximum, then q_sum = q_sum + (q - r) + r ; r -= q for this warp's tokens (:433-434)
+    const float* book = p.books + (size_t)bk * K * D;
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float bs = best[t];
+      int bi = bidx[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+      }
+      if (bi >= K) bi = 0;
+      const int n = n0 + warp * TPW + t;
+      if (n >= p.N) continue;
+      float* xr = xs + (warp * TPW + t) * D;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) {
+          const float q = __ldg(book + (size_t)bi * D + d);
+          const float r = xr[d];
+          qs[t][j] = __fadd_rn(__fadd_rn(qs[t][j], __fsub_rn(q, r)), r);
+          xr[d] = __fsub_rn(r, q);
+        }
+      }
+      if (lane == 0) {
+        if (p.idx_flat) p.idx[n] = bi;
+        else {
+          int b, tt;
+          if (p.row_mode == ROWS_DENSE) { b = n / p.Tl; tt = n - b * p.Tl; }
+          else { b = n / p.nfix; tt = p.chunk * (n - b * p.nfix + 1); }
+          p.idx[((long)b * p.books_use + bk) * p.Tl + tt] = bi;
+        }
+      }
+    }
+    __syncwarp();           // the residual rows written above are read by the other lanes of this warp next book
+  }
+#pragma unroll
+  for (int t = 0; t < TPW; ++t) {
+    const int n = n0 + warp * TPW + t;
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane + 32 * j;
+      if (d < D) p.qsum[(size_t)n * D + d] = qs[t][j];
+    }
+  }
+}
 __global__ void __launch_bounds__(256) rvq_apply_f32(const RvqArgs p, const float* __restrict__ book, float* __restrict__ res,
                                                      unsigned long long* __restrict__ keys, int bk) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -946,12 +1091,6 @@ struct DacRvqArgs {
   int N, C, K, n_q, Tl;
   long stage_stride;
 };
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
-               : "memory");
-}
 
 constexpr int DACRVQ_WARPS = 8;    // warps per CTA of the one-token-per-warp form (16 was measured slower on B200)
 constexpr int DACRVQ_MAX_WARPS = 10;
