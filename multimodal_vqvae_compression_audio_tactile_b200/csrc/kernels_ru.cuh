@@ -170,6 +170,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();
   const int n7 = p.KT * q.nk;                          // K blocks of GEMM 1
   const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int la = q.nbuf - 1;                           // GEMM-1 lookahead in tiles
@@ -597,13 +598,13 @@ inline int tc_ru_launch(TcRuPlan& plan, const TcRuArgs& a, const TcWeight& w7, c
   if (plan.x3) {
     e = cudaFuncSetAttribute(conv_ru_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_ru_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
-                                                                plan.mB1_hi, plan.mB1_lo, q);
+    tc_launch(conv_ru_kernel<1>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
+              plan.mB1_hi, plan.mB1_lo, q);
   } else {
     e = cudaFuncSetAttribute(conv_ru_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_ru_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
-                                                                plan.mB1_hi, plan.mB1_lo, q);
+    tc_launch(conv_ru_kernel<0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
+              plan.mB1_hi, plan.mB1_lo, q);
   }
   return 0;
 }

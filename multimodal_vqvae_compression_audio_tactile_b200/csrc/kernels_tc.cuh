@@ -99,6 +99,15 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor in the stream still runs.  Everything before pdl_sync() (mbarrier init, TMEM allocation, tensor-map
+// prefetch -- nothing that touches the predecessor's output) then overlaps the predecessor's tail; pdl_sync() waits
+// for the predecessor's completion and memory flush, and releases this grid's own successor (whose CTAs take an SM
+// as soon as one of ours exits, and wait in turn).  Both instructions are no-ops in a normally launched grid.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -581,6 +590,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();
   const int n_kiter = p.KT * p.n_kblk;
 
   if (warp == 0) {
@@ -803,6 +813,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();
   const uint32_t set_cols = (uint32_t)(p.MT * p.acc_stride);
 
   if (warp == 0) {
@@ -952,6 +963,31 @@ __global__ void merge_planes_f32(const __nv_bfloat16* __restrict__ hi, const __n
   float v = __bfloat162float(hi[i]);
   if (lo) v += __bfloat162float(lo[i]);
   out[i] = v;
+}
+
+
+// Launch with the programmatic-serialization attribute (see pdl_sync()); B2C_PDL=0 launches normally.
+inline bool tc_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1283,22 +1319,22 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
     if (plan.x3) {
       e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
       if (e != cudaSuccess) return -2;
-      conv_tc2_kernel<1><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+      tc_launch(conv_tc2_kernel<1>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
     } else {
       e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
       if (e != cudaSuccess) return -2;
-      conv_tc2_kernel<0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+      tc_launch(conv_tc2_kernel<0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
     }
     return 0;
   }
   if (plan.x3) {
     e = cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_tc_kernel<1, 0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    tc_launch(conv_tc_kernel<1, 0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
-    conv_tc_kernel<0, 0><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    tc_launch(conv_tc_kernel<0, 0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
   }
   return 0;
 }
@@ -1467,6 +1503,7 @@ nearest_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();
   const uint32_t a_plane = (uint32_t)p.n_kblk * q.a_blk_bytes;   // bytes from the hi to the lo plane of the rows
   const uint32_t b_plane = (uint32_t)p.n_kblk * q.b_blk_bytes;
 

@@ -183,6 +183,25 @@ def test_batch_invariance_and_ragged_micro_batches(plan, dev, oracle_models):
     assert torch.isfinite(y1).all() and float(y1.abs().max()) <= 1.0
 
 
+def test_large_batch_kernel_variants_equal_small_batch(dev, oracle_models):
+    """The kernels only large batches select (one-launch residual VQ over all books, two tokens per warp in the
+    DAC residual VQ, query-split attention, wide code slices) give the bits of the small-batch kernels: 40 frames
+    in one program (3000 tokens) against the same frames in programs of 5."""
+    name = "cal_b8k512"
+    case = cases.CODEC_CASES[name]
+    net = gpu_model(oracle_models(name), case, "tc")
+    a, t = cases.codec_inputs(dict(case, B=40))
+    a, t = a.to(dev), t.to(dev)
+    net.micro_batch = 40
+    y1 = net.forward_eval(a, t)
+    i1 = net.last_indices.clone()
+    net.micro_batch = 5
+    y2 = net.forward_eval(a, t)
+    assert torch.equal(i1, net.last_indices)
+    assert torch.equal(y1, y2)
+    assert int(i1.min()) >= 0 and int(i1.max()) < case["K"] and len(torch.unique(i1)) > 8
+
+
 def test_host_buffer_entry_matches_device_entry(dev, oracle_models):
     name = "c3_b10k128"
     case = cases.CODEC_CASES[name]
