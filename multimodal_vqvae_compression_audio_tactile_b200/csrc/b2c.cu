@@ -330,12 +330,24 @@ extern "C" int b2c_prog_destroy(b2c_prog* p) {
   delete p;
   return B2C_OK;
 }
+// residual VQ over all books in ONE launch (rvq_books_f32): when the 32-token blocks alone occupy the GPU
+static bool rvq_one_launch(const b2c_ctx* ctx, const Op& op) {
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("B2C_RVQ_FUSED");
+    fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  const RvqArgs& r = op.rvq;
+  return fused && op.type == OP_RVQ && r.books_use > 0 && op.r[1] != B2C_NULL_REF && (r.D & 3) == 0 && r.D <= 128 &&
+         (long)((r.N + 31) / 32) * 2 >= ctx->sm_count;
+}
 // kernel launches one run of the program enqueues (an op can be several launches)
 extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   if (!p) return 0;
   int n = 0;
   for (const auto& op : p->ops) {
-    if (op.type == OP_RVQ && op.scratch && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
+    if (rvq_one_launch(p->ctx, op)) n += 1;
+    else if (op.type == OP_RVQ && op.scratch && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
     else if (op.type == OP_NEAREST) n += op.precision == B2C_PREC_F32 ? 2 : 4;                // prep x2, scores, finalise
     else n += 1;
   }
@@ -900,13 +912,7 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           const char* e = getenv("B2C_RVQ_SPLIT");
           rvq_split = (e && e[0] == '0') ? 0 : 1;
         }
-        static int rvq_fused = -1;
-        if (rvq_fused < 0) {
-          const char* e = getenv("B2C_RVQ_FUSED");
-          rvq_fused = (e && e[0] == '0') ? 0 : 1;
-        }
-        if (r.books_use > 0 && op.type == OP_RVQ && r.qsum && rvq_fused && (r.D & 3) == 0 && r.D <= 128 &&
-            (long)((r.N + 31) / 32) * 2 >= ctx->sm_count) {
+        if (r.qsum && rvq_one_launch(ctx, op)) {
           // enough 32-token blocks to occupy the GPU: one launch for all books.  (16-token CTAs, two per SM, measured
           // slower: 0.37 vs 0.28 ms at 4800 tokens -- the code tiles are then streamed twice as often.)
           const size_t sm = ((size_t)32 * r.D + (size_t)2 * 128 * (r.D + 4)) * sizeof(float);

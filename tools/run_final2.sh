@@ -19,6 +19,8 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/bench_plain3.log 2>&1 &&
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_tc_kernel|conv_ru_kernel|conv_tc2_kernel" -s 492 -c 82 --csv --log-file gpurun_out/traffic_conv.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
 echo "traffic rc=$?"; wc -l gpurun_out/traffic_conv.csv
+( timeout 900 python tools/search_sweep.py --out gpurun_out/search_sweep.json ; echo "rc=$?" ) > gpurun_out/search_sweep.log 2>&1
+tail -3 gpurun_out/search_sweep.log | cut -c1-300
 CMD="python tools/tc_selftest.py --group ru --only enc1.d1 --batch 32 --precs bf16x3"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_ru -s 1 -c 1 -f -o gpurun_out/prof_ru_enc1_x3 $CMD > gpurun_out/ncu_run.log 2>&1
