@@ -491,8 +491,13 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
 // quarters; thread = row).  Each thread scans its quarter of the codes keeping (best, first index of best,
 // runner-up); the four quarters of a row are merged through shared memory.  The [N, K] score matrix never
 // leaves TMEM.
+// nt_next == -2: stand-alone call (loads the tile's 0.5|e|^2 itself, two barriers per tile).  Otherwise the caller
+// walks a known tile sequence: the half norms of tile nt_next (-1: none) are requested before this tile is scanned and
+// parked in the other buffer before this tile's merge barrier, so their L2 latency overlaps the scan and the tile
+// needs ONE barrier; `prime` = first tile of the sequence (nothing was parked for it).
 __device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float* stg, uint32_t tcount, uint32_t t_acc,
-                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
+                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane,
+                                                   int nt_next = -2, bool prime = true) {
   const int quad = warp & 3;
   const int part = (warp - 2) >> 2;
   const int et = threadIdx.x - 64;
@@ -503,11 +508,18 @@ __device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float*
   // 0.5|e|^2 of this tile's codes -> shared memory once (a global load per column stalled every compare: with
   // ~210 KB of dynamic shared memory the L1 is a few KB and each load went to L2)
   float* hn_s = stg + 4096 + (tcount & 1u) * 256;      // after the two 8 KB merge tiles
-  if (et < p.BN) {
-    const int col = nt * p.BN + et;
-    hn_s[et] = col < p.n_codes ? __ldg(p.half_norm + col) : 0.f;
+  if (nt_next == -2 || prime) {
+    if (et < p.BN) {
+      const int col = nt * p.BN + et;
+      hn_s[et] = col < p.n_codes ? __ldg(p.half_norm + col) : 0.f;
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
   }
-  asm volatile("bar.sync 1, 512;" ::: "memory");
+  float hn_next = 0.f;
+  if (nt_next >= 0 && et < p.BN) {
+    const int col = nt_next * p.BN + et;
+    if (col < p.n_codes) hn_next = __ldg(p.half_norm + col);
+  }
   float best = -INFINITY, second = -INFINITY;
   int bidx = 0x7fffffff;
   const int ncol = min(cpp, p.n_codes - col0);           // valid codes of this thread's quarter
@@ -515,9 +527,15 @@ __device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float*
     float v[16];
     tmem_ld16(t_src + c, v);
     if (c + 16 <= ncol) {
+      float hv[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 h4 = *reinterpret_cast<const float4*>(hn_s + part * cpp + c + 4 * u);
+        hv[4 * u] = h4.x; hv[4 * u + 1] = h4.y; hv[4 * u + 2] = h4.z; hv[4 * u + 3] = h4.w;
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float sc = __fsub_rn(v[i], hn_s[part * cpp + c + i]);
+        const float sc = __fsub_rn(v[i], hv[i]);
         second = fmaxf(second, fminf(best, sc));         // runner-up = max over all but the (first) best
         if (sc > best) { best = sc; bidx = col0 + c + i; }
       }
@@ -534,6 +552,7 @@ __device__ __forceinline__ void tc_epilogue_argmax(const TcConvParams& p, float*
   }
   float4* sm = reinterpret_cast<float4*>(stg) + (tcount & 1u) * (4 * TC_BM);
   sm[part * TC_BM + row] = make_float4(best, __int_as_float(bidx), second, 0.f);
+  if (nt_next >= 0 && et < p.BN) stg[4096 + ((tcount + 1u) & 1u) * 256 + et] = hn_next;
   tc_fence_before();
   asm volatile("bar.sync 1, 512;" ::: "memory");
   if (et == 0) mbar_arrive(tempty_bar);
@@ -1389,7 +1408,22 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ xr, const
                                              const float* __restrict__ hn, int k, int D) {
   const float* ek = e + (size_t)k * D;
   float acc = 0.f;
-  for (int d = 0; d < D; ++d) acc = fmaf(__ldg(xr + d), __ldg(ek + d), acc);
+  if ((D & 15) == 0 && ((reinterpret_cast<uintptr_t>(ek) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0) {
+    // same fmaf chain, operands fetched 16 elements at a time (four independent 16-byte loads in flight): the scalar
+    // loop pays one L2 round trip per element when a thread walks a code row of its own
+    const float4* e4 = reinterpret_cast<const float4*>(ek);
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    for (int d4 = 0; d4 < (D >> 2); d4 += 4) {
+      const float4 ea = __ldg(e4 + d4), eb = __ldg(e4 + d4 + 1), ec = __ldg(e4 + d4 + 2), ed = __ldg(e4 + d4 + 3);
+      const float4 xa = __ldg(x4 + d4), xb = __ldg(x4 + d4 + 1), xc = __ldg(x4 + d4 + 2), xd = __ldg(x4 + d4 + 3);
+      acc = fmaf(xa.x, ea.x, acc); acc = fmaf(xa.y, ea.y, acc); acc = fmaf(xa.z, ea.z, acc); acc = fmaf(xa.w, ea.w, acc);
+      acc = fmaf(xb.x, eb.x, acc); acc = fmaf(xb.y, eb.y, acc); acc = fmaf(xb.z, eb.z, acc); acc = fmaf(xb.w, eb.w, acc);
+      acc = fmaf(xc.x, ec.x, acc); acc = fmaf(xc.y, ec.y, acc); acc = fmaf(xc.z, ec.z, acc); acc = fmaf(xc.w, ec.w, acc);
+      acc = fmaf(xd.x, ed.x, acc); acc = fmaf(xd.y, ed.y, acc); acc = fmaf(xd.z, ed.z, acc); acc = fmaf(xd.w, ed.w, acc);
+    }
+  } else {
+    for (int d = 0; d < D; ++d) acc = fmaf(__ldg(xr + d), __ldg(ek + d), acc);
+  }
   return __fsub_rn(acc, __ldg(hn + k));
 }
 
@@ -1580,9 +1614,16 @@ nearest_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const int nt0 = sp * q.tiles_per_split, nt1 = min(p.n_ntiles, nt0 + q.tiles_per_split);
       for (int nt = nt0; nt < nt1; ++nt, ++tcount) {
         const uint32_t acc = tcount & 1u, apar = (tcount >> 1) & 1u;
+        // the tile this CTA scans next (possibly the first of its next work item), for the half-norm prefetch
+        int nt_next = nt + 1;
+        if (nt_next == nt1) {
+          const int item2 = item + (int)gridDim.x;
+          nt_next = item2 < q.n_items ? (item2 - (item2 / q.splits) * q.splits) * q.tiles_per_split : -1;
+        }
         mbar_wait(smem_u32(&bar_tfull[acc]), apar, 6);
         tc_fence_after();
-        tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, rbk, nt, smem_u32(&bar_tempty[acc]), warp, lane);
+        tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, rbk, nt, smem_u32(&bar_tempty[acc]), warp, lane,
+                           nt_next, tcount == 0);
       }
     }
   }
