@@ -25,3 +25,8 @@ CMD="python tools/tc_selftest.py --group ru --only enc1.d1 --batch 32 --precs bf
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_ru -s 1 -c 1 -f -o gpurun_out/prof_ru_enc1_x3 $CMD > gpurun_out/ncu_run.log 2>&1
 echo "full rc=$?"; tail -2 gpurun_out/ncu_run.log
+for U in enc1:bf16x3 enc2:bf16x3 dec3:bf16 dec4:bf16; do
+  u=${U%%:*}; p=${U##*:}
+  ( B2C_TC_DEBUG=8 timeout 200 python tools/ru_trace.py --unit $u --prec $p --batch 32 ; echo "rc=$?" ) > gpurun_out/trace_${u}_${p}.log 2>&1
+  head -1 gpurun_out/trace_${u}_${p}.log
+done
