@@ -96,6 +96,12 @@ __device__ __forceinline__ void ru_epilogue_h(const TcRuParams& q, uint32_t t_ac
   for (int c = 0; c < nchunks; ++c) {
     float v[8];
     tmem_ld8(t_src + c * 32, v);
+    if (q.e.pair_off) {
+      float v2[8];
+      tmem_ld8(t_src + q.e.pair_off + c * 32, v2);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] += v2[u];
+    }
     ru_h_store<X3, 8>(q, v, quad * 32 + lane, c * 32 + cg8 * 8, hbuf);
   }
 }
@@ -109,6 +115,12 @@ __device__ __forceinline__ void ru_epilogue_h_g(const TcRuParams& q, uint32_t t_
   for (int c = 0; c < nchunks; ++c) {
     float v[16];
     tmem_ld16(t_src + c * 32, v);
+    if (q.e.pair_off) {
+      float v2[16];
+      tmem_ld16(t_src + q.e.pair_off + c * 32, v2);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] += v2[u];
+    }
     ru_h_store<X3, 16>(q, v, quad * 32 + lane, c * 32 + half * 16, hbuf);
   }
 }
@@ -272,8 +284,14 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     Ring rg, ra;
     const uint32_t slab_plane = q.slab_plane_bytes >> 4;
     const uint32_t tap_step = ((uint32_t)p.dil * (uint32_t)p.BK * 2u) >> 4;     // descriptor units per tap (slab mode)
+    const uint32_t idesc_2n = umma_idesc_bf16(TC_BM, 2 * p.BN);
     auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t apl, uint32_t first) {
       if (p.dbg & 4) return;
+      if (X3 && p.pair_off) {                           // N-stacked weight planes (see umma_ksteps_stacked)
+        if (ksteps == 4) umma_ksteps_stacked<4>(d, a_lo, b_lo, apl, desc_hi, idesc_2n, idesc, first);
+        else umma_ksteps_stacked<2>(d, a_lo, b_lo, apl, desc_hi, idesc_2n, idesc, first);
+        return;
+      }
       if (ksteps == 4) umma_ksteps<X3, 4>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else if (ksteps == 2) umma_ksteps<X3, 2>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else umma_ksteps<X3, 1>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
@@ -481,6 +499,12 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   p.act_plane_elems = (long)B * L * C;
   p.BN = C;
   p.acc_stride = C <= 64 ? 64 : (C <= 128 ? 128 : 256);
+  // C = 64 bf16x3: weight planes stacked along N (A_hi fetched once for hi.hi and hi.lo); the accumulator is then two
+  // 64-column halves that the epilogues add.  4 x 128 TMEM columns still double-buffer both GEMMs.  B2C_RU_STACK=0 off.
+  {
+    const char* e = getenv("B2C_RU_STACK");
+    if (C == 64 && plan->x3 && !(e && e[0] == '0')) { p.pair_off = 64; p.acc_stride = 128; }
+  }
   q.nbuf = 4 * p.acc_stride <= 512 ? 2 : 1;
   p.tmem_cols = 2 * q.nbuf * p.acc_stride;
   q.h_plane_bytes = TC_BM * C * 2;

@@ -200,6 +200,20 @@ __device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t a_lo, uint
     }
   }
 }
+// bf16x3 with the two weight planes stacked along N: B' = [B_hi ; B_lo] is ONE K-major tile of 2N rows (the lo plane
+// follows the hi plane in shared memory), so  D[:, 0:2N] += A_hi . B'^T  gives hi.hi in columns [0, N) and hi.lo in
+// [N, 2N) with A_hi fetched once, and  D[:, 0:N] += A_lo . B_hi^T  completes the first half; the epilogue adds the two
+// halves.  Operand fetch per K step: (4 + 4N/32.. ) -- 14 KB instead of 18 KB at N = 64, where the MMAs are paced by the
+// shared-memory fetch, not by the tensor pipe (tools/micro/umma_rate.cu).
+template <int KS>
+__device__ __forceinline__ void umma_ksteps_stacked(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_plane,
+                                                    uint32_t desc_hi, uint32_t idesc_2n, uint32_t idesc_n, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    umma_bf16_w32(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc_2n, k == 0 ? acc_first : 1u);
+    umma_bf16_w32(d_tmem, a_lo + a_plane + 2 * k, b_lo + 2 * k, desc_hi, idesc_n, 1u);
+  }
+}
 __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -260,6 +274,7 @@ struct TcConvParams {
   int epi_groups; // 2: the 16 epilogue warps work as two independent groups of 8, one per TMEM accumulator buffer
   int kgroup;     // K blocks per pipeline stage of the generic kernel (one mbarrier hand-off per kgroup blocks)
   int dbg;        // B2C_TC_DEBUG bit mask (timing experiments only): 1 skip epilogue work, 2 no TMA, 4 no MMA
+  int pair_off;   // > 0: the accumulator is the sum of two column ranges pair_off apart (N-stacked bf16x3, fused unit)
   int stg_bufs;   // epilogue staging tiles: 2 (one barrier per chunk) or 1 (two barriers, frees 18 KB for the rings)
   uint32_t row_bytes, a_plane_bytes;
 };
@@ -333,6 +348,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
     {
       float v[8];
       tmem_ld8(t_src + c * 32, v);
+      if (p.pair_off) {
+        float v2[8];
+        tmem_ld8(t_src + p.pair_off + c * 32, v2);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] += v2[u];
+      }
       float* dst = sb + (quad * 32 + lane) * TC_STG_LD + cg8 * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -442,6 +463,12 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
     {
       float v[16];
       tmem_ld16(t_src + c * 32, v);
+      if (p.pair_off) {
+        float v2[16];
+        tmem_ld16(t_src + p.pair_off + c * 32, v2);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] += v2[u];
+      }
       float* dst = stg_g + (quad * 32 + lane) * TC_STG_LD + half * 16;
 #pragma unroll
       for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
