@@ -159,6 +159,11 @@ int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv, b2c_ref o
  * (row_mode DENSE: n = b*Tl + t; HEAD: n = (b, j) -> t = chunk*(j+1)). */
 int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N, int row_mode,
                  int B, int Tl, int chunk);
+/* Receiver side of ResidualVQEMA.forward (:421-435): the code indices are an INPUT (int32, the layout b2c_prog_rvq
+ * writes), qsum[n] = sum over the first books_use books of book[idx] (plain fp32 adds in book order).  Not in the
+ * reference, which never decodes from indices; it is what "indices out, reconstruction in" needs. */
+int b2c_prog_rvq_lookup(b2c_prog* p, int books_wid, int books_use, b2c_ref idx, b2c_ref qsum, int N, int row_mode,
+                        int B, int Tl, int chunk);
 /* ResidualVQEMA._nearest_l2 (:417-419) with caller tensors: x [N, D], emb [K, D] -> idx int32 [N].
  * scratch: b2c_nearest_scratch_bytes(N, D, K, precision) bytes.
  *   B2C_PREC_F32: FFMA scores, 32 rows per CTA.  B2C_PREC_BF16X3 / BF16: tcgen05 score GEMM (bf16 hi/lo split,

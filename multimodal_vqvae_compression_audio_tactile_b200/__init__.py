@@ -5,6 +5,7 @@ from ._lib import B2CError, LIB_PATH, load  # noqa: F401
 from .modules import (AR_CHUNK_TOK, CODE_DIM, DAC, CrossPredictor, Decoder, Encoder, PosEnc1D, ProposedEval,  # noqa: F401
                       ResidualVectorQuantize, ResidualVQEMA, TokenNorm, build_proposed)
 from .ops import nearest_code  # noqa: F401
+from .bitstream import bits_per_index, estimated_kbps, pack_indices, packed_bytes, unpack_indices  # noqa: F401
 
 #: contraction arithmetic bench.py / smoke() use by default (see DESIGN.md "Precision")
 DEFAULT_PRECISION = "tc"

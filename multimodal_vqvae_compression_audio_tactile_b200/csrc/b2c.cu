@@ -338,7 +338,7 @@ static bool rvq_one_launch(const b2c_ctx* ctx, const Op& op) {
     fused = (e && e[0] == '0') ? 0 : 1;
   }
   const RvqArgs& r = op.rvq;
-  return fused && op.type == OP_RVQ && r.books_use > 0 && op.r[1] != B2C_NULL_REF && (r.D & 3) == 0 && r.D <= 128 &&
+  return fused && op.type == OP_RVQ && !r.lookup && r.books_use > 0 && op.r[1] != B2C_NULL_REF && (r.D & 3) == 0 && r.D <= 128 &&
          (long)((r.N + 31) / 32) * 2 >= ctx->sm_count;
 }
 // kernel launches one run of the program enqueues (an op can be several launches)
@@ -596,6 +596,29 @@ extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x
     CUDA_TRY(cudaMalloc(&op.scratch, bytes));
     CUDA_TRY(cudaMemset(op.scratch, 0, bytes));
   }
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_rvq_lookup(b2c_prog* p, int books_wid, int books_use, b2c_ref idx, b2c_ref qsum, int N,
+                                   int row_mode, int B, int Tl, int chunk) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_rvq_lookup: NULL program");
+  const Weight* w = get_w(p, books_wid, W_BOOKS, "b2c_prog_rvq_lookup");
+  if (!w) return B2C_ERR_ARG;
+  if (books_use < 0 || books_use > w->n_books)
+    return fail(B2C_ERR_ARG, "b2c_prog_rvq_lookup: books_use %d of %d", books_use, w->n_books);
+  if (N <= 0) return fail(B2C_ERR_ARG, "b2c_prog_rvq_lookup: empty");
+  Op op;
+  op.type = OP_RVQ;
+  blank_refs(op);
+  op.r[1] = qsum; op.r[2] = idx;
+  op.wid = books_wid;
+  RvqArgs& r = op.rvq;
+  memset(&r, 0, sizeof(r));
+  r.N = N; r.D = w->D; r.K = w->K; r.books_use = books_use; r.row_mode = row_mode; r.B = B; r.Tl = Tl > 0 ? Tl : 1;
+  r.chunk = chunk > 0 ? chunk : 1;
+  r.nfix = nfix_of(r.Tl, r.chunk) > 0 ? nfix_of(r.Tl, r.chunk) : 1;
+  r.lookup = 1;
   p->ops.push_back(op);
   return B2C_OK;
 }
@@ -889,6 +912,12 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           r.idx = r.books_use > 0 ? R.get<int>(op.r[2]) : nullptr;
           r.books = w.dev;
           r.half_n = w.aux;
+          if (r.lookup) {
+            if (R.bad || !r.qsum || (r.books_use > 0 && !r.idx))
+              return fail(B2C_ERR_WORKSPACE, "op %zu (rvq lookup): unresolved buffer", oi);
+            rvq_lookup_f32<<<(r.N + 7) / 8, 256, 0, st>>>(r);
+            break;
+          }
         } else {
           r.x = R.get<const float>(op.r[0]);
           r.books = R.get<const float>(op.r[1]);

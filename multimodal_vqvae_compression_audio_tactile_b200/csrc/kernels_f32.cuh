@@ -689,6 +689,7 @@ struct RvqArgs {
   int N, D, K, books_use;
   int row_mode, B, Tl, chunk, nfix;
   int idx_flat;         // 1: idx[n] (nearest op)
+  int lookup;           // 1: receiver side -- idx is an INPUT, qsum = sum over books of book[idx] (b2c_prog_rvq_lookup)
 };
 
 // TPW tokens per warp (8 * TPW per CTA): 4 for large N, 1 when that would leave most SMs idle.
@@ -1034,6 +1035,25 @@ __global__ void __launch_bounds__(256) rvq_books_f32(const RvqArgs p) {
       const int d = lane + 32 * j;
       if (d < D) p.qsum[(size_t)n * D + d] = qs[t][j];
     }
+  }
+}
+// Receiver side of the residual VQ: the code indices are given, qsum[n] = sum_b book_b[idx[b][n]] (books in order, plain
+// fp32 adds).  One warp per token; the index layout is the one rvq_apply_f32 / rvq_books_f32 write.
+__global__ void __launch_bounds__(256) rvq_lookup_f32(const RvqArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  int b, tt;
+  if (p.row_mode == ROWS_DENSE) { b = n / p.Tl; tt = n - b * p.Tl; }
+  else { b = n / p.nfix; tt = p.chunk * (n - b * p.nfix + 1); }
+  for (int d = lane; d < p.D; d += 32) {
+    float qs = 0.f;
+    for (int bk = 0; bk < p.books_use; ++bk) {
+      int bi = p.idx[((long)b * p.books_use + bk) * p.Tl + tt];
+      bi = min(max(bi, 0), p.K - 1);                       // a corrupt index must not read outside the codebook
+      qs = __fadd_rn(qs, __ldg(p.books + ((size_t)bk * p.K + bi) * p.D + d));
+    }
+    p.qsum[(size_t)n * p.D + d] = qs;
   }
 }
 __global__ void __launch_bounds__(256) rvq_apply_f32(const RvqArgs p, const float* __restrict__ book, float* __restrict__ res,

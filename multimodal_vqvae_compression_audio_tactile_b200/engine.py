@@ -354,6 +354,10 @@ class Emitter:
         L.check(self.lib.b2c_prog_rvq(self.h, books_wid, books_use, self._r(x), self._r(qsum), self._r(idx), N,
                                       row_mode, B, Tl, chunk), "b2c_prog_rvq")
 
+    def rvq_lookup(self, books_wid, books_use, idx, qsum, N, row_mode, B, Tl, chunk):
+        L.check(self.lib.b2c_prog_rvq_lookup(self.h, books_wid, books_use, self._r(idx), self._r(qsum), N, row_mode, B,
+                                             Tl, chunk), "b2c_prog_rvq_lookup")
+
     def nearest(self, x, emb, scratch, idx, N, D, K, prec=L.PREC_F32):
         L.check(self.lib.b2c_prog_nearest(self.h, self._r(x), self._r(emb), self._r(scratch), self._r(idx), N, D, K,
                                           prec), "b2c_prog_nearest")
@@ -598,10 +602,21 @@ def emit_residual_code(em: Emitter, pp: PackedPredictor, zt, zt_mode, z_pred, N,
     em.drop(qd)
 
 
+def emit_residual_decode(em: Emitter, pp: PackedPredictor, z_pred, N, B, Tl, chunk, books_use, idx, row_mode, z_hat,
+                         prec):
+    """Receiver side of emit_residual_code: qD = sum of the indexed code vectors; z_hat = proj_up(qD) + z_pred."""
+    qd = em.new(N * pp.code_dim)
+    em.rvq_lookup(pp.books, books_use, idx, qd, N, row_mode, B, Tl, chunk)
+    em.conv(pp.up, qd, 1, N, res=z_pred, out_raw=z_hat, prec=prec)
+    em.drop(qd)
+
+
 def emit_latent_coder(em: Emitter, pp: PackedPredictor, qa, zt, z_run, idx, B, Tl, chunk, books_use, prec):
     """The reference's 5-chunk AR loop (Evaluation/dac_vcpwq_proposed6_latency.py:462-477) as two
     dependent passes: pass 1 = all tokens with a zero query input, pass 2 = the first
-    token of chunks 1.. with the previous chunk's last reconstructed latent as query input."""
+    token of chunks 1.. with the previous chunk's last reconstructed latent as query input.
+    ``zt is None`` emits the RECEIVER: ``idx`` is then an input and the latents are rebuilt from it (pass 1 places
+    every token's code vectors on its prediction, pass 2 redoes the chunk heads with their true query input)."""
     c = pp.c
     N = B * Tl
     # K/V for every token
@@ -622,7 +637,10 @@ def emit_latent_coder(em: Emitter, pp: PackedPredictor, qa, zt, z_run, idx, B, T
     em.drop(q_tab)
     z_pred = emit_predict_rows(em, pp, qn_tab, ctx, N, Tl, chunk, True, prec)
     em.drop(qn_tab)
-    emit_residual_code(em, pp, zt, L.ROWS_DENSE, z_pred, N, B, Tl, chunk, books_use, idx, L.ROWS_DENSE, z_run, prec)
+    if zt is None:      # receiver: idx is an input
+        emit_residual_decode(em, pp, z_pred, N, B, Tl, chunk, books_use, idx, L.ROWS_DENSE, z_run, prec)
+    else:
+        emit_residual_code(em, pp, zt, L.ROWS_DENSE, z_pred, N, B, Tl, chunk, books_use, idx, L.ROWS_DENSE, z_run, prec)
     em.drop(z_pred)
     # pass 2: chunk heads
     nfix = (Tl + chunk - 1) // chunk - 1
@@ -639,8 +657,11 @@ def emit_latent_coder(em: Emitter, pp: PackedPredictor, qa, zt, z_run, idx, B, T
         z_pred2 = emit_predict_rows(em, pp, qn2, ctx2, N2, Tl, chunk, False, prec)
         em.drop(qn2)
         z_hat2 = em.new(N2 * c)
-        emit_residual_code(em, pp, zt, L.ROWS_HEAD, z_pred2, N2, B, Tl, chunk, books_use, idx, L.ROWS_HEAD, z_hat2,
-                           prec)
+        if zt is None:
+            emit_residual_decode(em, pp, z_pred2, N2, B, Tl, chunk, books_use, idx, L.ROWS_HEAD, z_hat2, prec)
+        else:
+            emit_residual_code(em, pp, zt, L.ROWS_HEAD, z_pred2, N2, B, Tl, chunk, books_use, idx, L.ROWS_HEAD, z_hat2,
+                               prec)
         em.drop(z_pred2)
         em.scatter_heads(z_hat2, z_run, B, Tl, chunk, c)
         em.drop(z_hat2)

@@ -531,6 +531,61 @@ class ProposedEval(_Top):
         prog = eng.programs[key] = em.finish(6, Tl=Tl, Lout=pk["t_dec"].out_len(Tl))
         return prog
 
+    def program_decode(self, eng, pk, nb, T, use):
+        """Receiver program: ext slots 1 a [nb,T], 3 y [nb,Lout], 4 idx i32 [nb,use,Tl] (INPUT), 5 audio codes i32."""
+        pe, pd, pt = self._prec("enc"), self._prec("dec"), self._prec("pred")
+        key = ("codec-rx", nb, T, use, pe, pd, pt)
+        prog = eng.programs.get(key)
+        if prog is not None:
+            return prog
+        em = Emitter(eng)
+        c = pk["pp"].c
+        za, Tl = emit_encoder(em, pk["a_enc"], em.ext(1), nb, T, pe)
+        qa = em.new(nb * Tl * c)
+        em.dac_rvq(pk["a_q"], pk["n_q"], za, qa, em.ext(5), nb, Tl)
+        em.drop(za)
+        z_run = em.new(nb * Tl * c)
+        emit_latent_coder(em, pk["pp"], qa, None, z_run, em.ext(4), nb, Tl, AR_CHUNK_TOK, use, pt)
+        em.drop(qa)
+        emit_decoder(em, pk["t_dec"], z_run, em.ext(3), nb, Tl, pd)
+        prog = eng.programs[key] = em.finish(6, Tl=Tl, Lout=pk["t_dec"].out_len(Tl))
+        return prog
+
+    @torch.no_grad()
+    def decode_indices(self, a_1T, idx, books_use=None):
+        """Receiver side of the codec ("indices out, reconstruction in"): the audio frame ``a_1T`` [B, 1, T] and the
+        code indices ``idx`` [B, books_use, Tl] that ``forward_eval`` left in ``last_indices`` -> y [B, 1, Lout].
+        The reference never decodes from indices (it keeps the quantised latents in memory, :462-487); this path
+        rebuilds them: audio encoder + DAC quantizer, the two-pass predictor, the indexed code vectors summed in book
+        order, proj_up, decoder.  It equals ``forward_eval``'s reconstruction up to the rounding of
+        ``q_sum + (q - r) + r`` against ``q_sum + q`` (the sender's straight-through form, :433-434)."""
+        _require_cuda(a_1T, idx)
+        if a_1T.dim() != 3 or a_1T.shape[1] != 1:
+            raise ValueError(f"expected a [B, 1, T] frame, got {tuple(a_1T.shape)}")
+        dev = a_1T.device
+        eng, pk = self._engine(dev)
+        B, _, T = a_1T.shape
+        Tl = pk["t_enc"].out_len(T)
+        if B == 0 or Tl <= 0:
+            raise ValueError(f"empty batch or frame too short (B={B}, T={T})")
+        use = idx.shape[1] if books_use is None else self._books_use(books_use)
+        if idx.dim() != 3 or idx.shape[0] != B or idx.shape[2] != Tl or idx.shape[1] < use or use > len(self.vq.books):
+            raise ValueError(f"expected indices [B={B}, >= {use} books, Tl={Tl}], got {tuple(idx.shape)}")
+        if idx.dtype.is_floating_point:
+            raise ValueError("code indices must be an integer tensor")
+        n_q, Lout = pk["n_q"], pk["t_dec"].out_len(Tl)
+        a = _as_f32(a_1T)
+        ii = idx[:, :use].to(torch.int32).contiguous()
+        y = torch.empty(B, 1, Lout, device=dev, dtype=torch.float32)
+        codes = torch.empty(B, n_q, Tl, device=dev, dtype=torch.int32)
+        mb = min(B, self.micro_batch)
+        for b0 in range(0, B, mb):
+            nb = min(mb, B - b0)
+            prog = self.program_decode(eng, pk, nb, T, use)
+            eng.run(prog, [a[b0:].data_ptr(), 0, y[b0:].data_ptr(), ii[b0:].data_ptr(), codes[b0:].data_ptr(), 0])
+        self.last_audio_codes = codes
+        return y.to(a_1T.dtype)
+
     def _run(self, a_1T, t_1T, books_use, decode, want_latents):
         _require_cuda(a_1T, t_1T)
         if a_1T.shape != t_1T.shape or a_1T.dim() != 3 or a_1T.shape[1] != 1:

@@ -70,3 +70,25 @@ def test_interface_errors():
     with pytest.raises(RuntimeError):
         net.A_ENC.block[0](torch.zeros(1, 1, 8))   # inner layers are fused, not callable
     assert modules.encoder_out_len(net.A_ENC, 24000) == 75
+
+
+def test_bitstream_round_trip_and_rate():
+    """Packed code indices (the payload of ProposedEval.decode_indices): exact round trip, ceil(log2 K) bits per
+    index, and the reference's analytic bitrate (Training/compare_dacvsproposal_5.py:372-373) for power-of-two K."""
+    import torch
+    import multimodal_vqvae_compression_audio_tactile_b200 as pkg
+    g = torch.Generator().manual_seed(5)
+    for K, books in ((128, 10), (512, 8), (1024, 3), (300, 2), (2, 1), (1, 1)):
+        idx = torch.randint(0, K, (3, books, 75), generator=g)
+        buf = pkg.pack_indices(idx, K)
+        assert len(buf) == pkg.packed_bytes(idx.shape, K) == (idx.numel() * pkg.bits_per_index(K) + 7) // 8
+        back = pkg.unpack_indices(buf, idx.shape, K)
+        assert back.dtype == torch.int32 and torch.equal(back.long(), idx)
+        if K & (K - 1) == 0 and K > 1:
+            per_frame_bits = 8 * len(pkg.pack_indices(idx[:1], K))
+            assert abs(per_frame_bits / 1000.0 - pkg.estimated_kbps(books, K)) < 8 / 1000.0   # byte padding only
+    assert pkg.pack_indices(torch.zeros(0, dtype=torch.int64), 512) == b""
+    with pytest.raises(ValueError):
+        pkg.pack_indices(torch.tensor([512]), 512)
+    with pytest.raises(ValueError):
+        pkg.unpack_indices(b"\x00", (3,), 512)

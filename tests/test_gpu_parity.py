@@ -202,6 +202,40 @@ def test_large_batch_kernel_variants_equal_small_batch(dev, oracle_models):
     assert int(i1.min()) >= 0 and int(i1.max()) < case["K"] and len(torch.unique(i1)) > 8
 
 
+@pytest.mark.parametrize("plan", PLANS)
+def test_receiver_rebuilds_the_reconstruction_from_packed_indices(plan, dev, oracle_models):
+    """encode -> indices -> bytes -> indices -> decode: the receiver (audio frame + packed code indices only, no
+    tactile signal) reproduces forward_eval's reconstruction.  Not bit-equal by construction: the sender keeps
+    q_sum + (q - r) + r (:433-434), the receiver sums the code vectors -- the tolerances are this file's decoder
+    tolerances.  Also the prefix property: decoding with fewer books equals forward_eval(books_use=...)."""
+    name = "cal_b4k256_use3_short"
+    case = cases.CODEC_CASES[name]
+    net = gpu_model(oracle_models(name), case, plan)
+    a, t = cases.codec_inputs(case)
+    a, t = a.to(dev), t.to(dev)
+    for use in (case["books_use"], 1):
+        y = net.forward_eval(a, t, books_use=use)
+        idx = net.last_indices.clone()
+        payload = pkg.pack_indices(idx, case["K"])
+        assert len(payload) == pkg.packed_bytes(idx.shape, case["K"])
+        back = pkg.unpack_indices(payload, idx.shape, case["K"], device=dev)
+        assert torch.equal(back, idx.to(torch.int32))
+        y_rx = net.decode_indices(a, back)
+        assert y_rx.shape == y.shape and torch.isfinite(y_rx).all()
+        err = float((y_rx - y).abs().max())
+        assert err <= DEC_TOL[plan], (plan, use, err)
+        assert psnr(y_rx.cpu(), y.cpu()) >= PSNR_MIN[plan]
+    # a different code somewhere changes the output (the indices are really used)
+    bad = back.clone()
+    bad[:, 0, :] = (bad[:, 0, :] + 1) % case["K"]
+    if plan == "f32":   # (the tc plan's bf16 decoder noise is of the size of one changed code's effect)
+        assert float((net.decode_indices(a, bad) - y_rx).abs().max()) > 100 * max(err, 1e-6)
+    with pytest.raises(ValueError):
+        net.decode_indices(a, back[:, :, :-1])
+    with pytest.raises(ValueError):
+        net.decode_indices(a, back.float())
+
+
 def test_host_buffer_entry_matches_device_entry(dev, oracle_models):
     name = "c3_b10k128"
     case = cases.CODEC_CASES[name]
