@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Copy the outputs of tools/run_final2.sh (+ run_multi.sh) from gpurun_out/ into profiles/ under their round names."""
+"""Copy the outputs of tools/run_artifacts.sh (+ run_multi.sh) from gpurun_out/ into profiles/ under their round names."""
 import json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, dst, R = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles"), sys.argv[1] if len(sys.argv) > 1 else "r01"

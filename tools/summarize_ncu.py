@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn the ncu CSV logs of tools/run_final2.sh into the JSON summaries kept under profiles/.
+"""Turn the ncu CSV logs of tools/run_artifacts.sh into the JSON summaries kept under profiles/.
 
     python tools/summarize_ncu.py launches gpurun_out/launches_bench.csv profiles/r01_ncu_launch_list_bench_tc.json
     python tools/summarize_ncu.py traffic  gpurun_out/traffic_conv.csv   profiles/r01_ncu_dram_traffic_conv_mb64.json
