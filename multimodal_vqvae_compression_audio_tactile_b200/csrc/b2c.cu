@@ -348,7 +348,16 @@ extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   for (const auto& op : p->ops) {
     if (rvq_one_launch(p->ctx, op)) n += 1;
     else if (op.type == OP_RVQ && op.scratch && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
-    else if (op.type == OP_NEAREST) n += op.precision == B2C_PREC_F32 ? 2 : 4;                // prep x2, scores, finalise
+    else if (op.type == OP_NEAREST) {
+      if (op.precision == B2C_PREC_F32) n += 2;                       // half norms, scores
+      else {
+        // tcgen05 search: prep x2, scores, finalise (+ re-scan, apply on the rows-resident path)
+        TcSearchParams q;
+        size_t smem = 0;
+        int grid = 0;
+        n += tc_search_plan(op.rvq.N, op.rvq.D, op.rvq.K, p->ctx->sm_count, &q, &smem, &grid) ? 6 : 4;
+      }
+    }
     else n += 1;
   }
   return n;
