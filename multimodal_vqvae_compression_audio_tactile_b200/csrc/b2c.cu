@@ -33,6 +33,26 @@ static int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(B2C_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
+// Every entry point that touches the device selects the context's device for the duration of the call and puts the
+// caller's device back on return: the library never changes the process-wide current device (torch's included), and a
+// program built for device d launches on d whatever device is current.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; ok = false; return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(dev)                                                                          \
+  DeviceGuard guard__(dev);                                                                        \
+  if (!guard__.ok) return fail(B2C_ERR_CUDA, "cannot select CUDA device %d", (int)(dev))
+
 extern "C" const char* b2c_last_error(void) { return g_err; }
 extern "C" int b2c_abi_version(void) { return B2C_ABI_VERSION; }
 
@@ -73,7 +93,8 @@ struct b2c_ctx {
   size_t bytes = 0;
   int sm_count = 148;
   // copy engine side of b2c_prog_run_host_pipelined (created on first use)
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D
+  cudaStream_t out_stream = nullptr;    // D2H
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
@@ -89,7 +110,7 @@ extern "C" int b2c_ctx_create(int device, b2c_ctx** out) {
   int count = 0;
   CUDA_TRY(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return fail(B2C_ERR_ARG, "b2c_ctx_create: device %d of %d", device, count);
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -104,8 +125,9 @@ extern "C" int b2c_ctx_create(int device, b2c_ctx** out) {
 
 extern "C" int b2c_ctx_destroy(b2c_ctx* ctx) {
   if (!ctx) return B2C_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard__(ctx->device);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -142,7 +164,7 @@ static void fold_weight_norm(const float* v, const float* g, size_t n0, size_t i
 extern "C" int b2c_pack_conv(b2c_ctx* ctx, const float* v, const float* g, const float* bias, int cout, int cin,
                              int k, int transposed, int stride, int padding) {
   if (!ctx || !v || cout <= 0 || cin <= 0 || k <= 0) return fail(B2C_ERR_ARG, "b2c_pack_conv: bad argument");
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  DEVICE_GUARD(ctx->device);
   Weight w;
   w.kind = W_CONV;
   w.cout = cout; w.cin = cin; w.k = k; w.transposed = transposed; w.stride = stride; w.padding = padding;
@@ -189,7 +211,7 @@ extern "C" int b2c_pack_conv(b2c_ctx* ctx, const float* v, const float* g, const
 
 extern "C" int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n) {
   if (!ctx || !data || n == 0) return fail(B2C_ERR_ARG, "b2c_pack_vector: bad argument");
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  DEVICE_GUARD(ctx->device);
   Weight w;
   w.kind = W_VEC;
   w.n = n;
@@ -207,7 +229,7 @@ extern "C" int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n) {
 
 extern "C" int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n_books, int K, int D) {
   if (!ctx || !books || n_books <= 0 || K <= 0 || D <= 0) return fail(B2C_ERR_ARG, "b2c_pack_codebooks: bad argument");
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  DEVICE_GUARD(ctx->device);
   std::vector<float> all((size_t)n_books * K * D), hn((size_t)n_books * K);
   for (int b = 0; b < n_books; ++b) {
     if (!books[b]) return fail(B2C_ERR_ARG, "b2c_pack_codebooks: book %d is NULL", b);
@@ -236,7 +258,7 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
   if (!ctx || n_q <= 0 || !in_v || !out_v || !codebook) return fail(B2C_ERR_ARG, "b2c_pack_dac_rvq: bad argument");
   if (d != 8) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: codebook_dim must be 8 (got %d)", d);
   if (c % 32 != 0 || c > 1024) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: latent dim %d (need multiple of 32, <= 1024)", c);
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  DEVICE_GUARD(ctx->device);
   if (K % 4 != 0) return fail(B2C_ERR_UNSUPPORTED, "b2c_pack_dac_rvq: codebook size %d must be a multiple of 4", K);
   // per stage: Win[8][c] | bin[8] | cbnT[8][K] | c2[K] | WoutT[8][c] | bout[c]  (staged in smem) | cb[K][8]
   const long stride = 8L * c + 8 + 8L * K + K + 8L * c + c + 8L * K;
@@ -323,7 +345,7 @@ extern "C" int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out) {
 }
 extern "C" int b2c_prog_destroy(b2c_prog* p) {
   if (p) {
-    cudaSetDevice(p->ctx->device);
+    DeviceGuard guard__(p->ctx->device);
     for (auto& op : p->ops)
       if (op.scratch) cudaFree(op.scratch);
   }
@@ -600,7 +622,7 @@ extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x
   r.idx_flat = 0;
   if (books_use > 0) {
     // split residual VQ: residual [N, D] fp32 + one 64-bit arg-max key per row
-    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    DEVICE_GUARD(p->ctx->device);
     const size_t bytes = ((size_t)N * w->D * 4 + 255) / 256 * 256 + (size_t)N * 8;
     CUDA_TRY(cudaMalloc(&op.scratch, bytes));
     CUDA_TRY(cudaMemset(op.scratch, 0, bytes));
@@ -1152,6 +1174,7 @@ extern "C" int b2c_prog_profile(b2c_prog* p, void* stream, void* workspace, size
                                 void* const* ext, int n_ext, float* ms, int* kind, double* flops, double* bytes,
                                 int cap) {
   if (!p || !ms || !kind || !flops || !bytes) return fail(B2C_ERR_ARG, "b2c_prog_profile: NULL argument");
+  DEVICE_GUARD(p->ctx->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   size_t n = p->ops.size();
   std::vector<cudaEvent_t> ev(2 * n);
@@ -1171,6 +1194,7 @@ extern "C" int b2c_prog_profile(b2c_prog* p, void* stream, void* workspace, size
 extern "C" int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext,
                             int n_ext) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_run: NULL program");
+  DEVICE_GUARD(p->ctx->device);
   Resolver R{reinterpret_cast<char*>(workspace), workspace_bytes, ext, n_ext};
   return run_ops(p, reinterpret_cast<cudaStream_t>(stream), R);
 }
@@ -1179,6 +1203,7 @@ extern "C" int b2c_prog_run_host(b2c_prog* p, void* stream, void* workspace, siz
                                  void* const* ext, int n_ext, const b2c_hostcopy* h2d, int n_h2d,
                                  const b2c_hostcopy* d2h, int n_d2h) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_run_host: NULL program");
+  DEVICE_GUARD(p->ctx->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int i = 0; i < n_h2d; ++i) {
     if (h2d[i].slot < 1 || h2d[i].slot > n_ext || !h2d[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host: bad h2d[%d]", i);
@@ -1198,17 +1223,22 @@ extern "C" int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* work
                                            void* const* ext_sets, int n_ext, const b2c_hostcopy* h2d, int n_h2d,
                                            const b2c_hostcopy* d2h, int n_d2h, int n_micro) {
   if (!p || !ext_sets || n_micro <= 0) return fail(B2C_ERR_ARG, "b2c_prog_run_host_pipelined: bad argument");
+  DEVICE_GUARD(p->ctx->device);
   b2c_ctx* ctx = p->ctx;
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
   if (!ctx->copy_stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
     }
   }
-  cudaStream_t xs = ctx->copy_stream;
+  // Three in-order queues: xs carries only H2D copies, cs the programs, os only D2H copies.  H2D(k+1) therefore waits
+  // for nothing but "the program of k-1 has finished with staging set (k+1)&1" and runs under the program of k; D2H(k)
+  // runs under the program of k+1.  (One copy queue would order H2D(k+1) behind D2H(k), i.e. behind the program of k.)
+  cudaStream_t xs = ctx->copy_stream, os = ctx->out_stream;
   for (int i = 0; i < n_h2d; ++i)
     if (h2d[i].slot < 1 || h2d[i].slot > n_ext || !h2d[i].host) return fail(B2C_ERR_ARG, "b2c_prog_run_host_pipelined: bad h2d[%d]", i);
   for (int i = 0; i < n_d2h; ++i)
@@ -1216,25 +1246,26 @@ extern "C" int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* work
   for (int k = 0; k < n_micro; ++k) {
     const int set = k & 1;
     void* const* ext = ext_sets + (size_t)set * n_ext;
-    // copy stream: inputs of micro-batch k (the compute stream finished reading this set two micro-batches ago)
+    // H2D queue: inputs of micro-batch k (the program of k-2 was the last reader of this staging set)
     if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(xs, ctx->ev_done[set], 0));
     for (int i = 0; i < n_h2d; ++i)
       CUDA_TRY(cudaMemcpyAsync(ext[h2d[i].slot - 1], (const char*)h2d[i].host + (size_t)k * h2d[i].bytes, h2d[i].bytes,
                                cudaMemcpyHostToDevice, xs));
     CUDA_TRY(cudaEventRecord(ctx->ev_in[set], xs));
-    // compute stream: wait for the inputs, and for the D2H that last read this set's outputs
+    // compute queue: wait for the inputs, and for the D2H of k-2 that last read this set's outputs
     CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev_in[set], 0));
     if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev_out[set], 0));
     int rc = b2c_prog_run(p, stream, workspace, workspace_bytes, ext, n_ext);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev_done[set], cs));
-    // copy stream: results of micro-batch k
-    CUDA_TRY(cudaStreamWaitEvent(xs, ctx->ev_done[set], 0));
+    // D2H queue: results of micro-batch k
+    CUDA_TRY(cudaStreamWaitEvent(os, ctx->ev_done[set], 0));
     for (int i = 0; i < n_d2h; ++i)
       CUDA_TRY(cudaMemcpyAsync((char*)d2h[i].host + (size_t)k * d2h[i].bytes, ext[d2h[i].slot - 1], d2h[i].bytes,
-                               cudaMemcpyDeviceToHost, xs));
-    CUDA_TRY(cudaEventRecord(ctx->ev_out[set], xs));
+                               cudaMemcpyDeviceToHost, os));
+    CUDA_TRY(cudaEventRecord(ctx->ev_out[set], os));
   }
+  CUDA_TRY(cudaStreamSynchronize(os));
   CUDA_TRY(cudaStreamSynchronize(xs));
   CUDA_TRY(cudaStreamSynchronize(cs));
   return B2C_OK;

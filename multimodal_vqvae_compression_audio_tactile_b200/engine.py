@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import warnings
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -94,6 +95,43 @@ class Program:
     ws_bytes: int
     n_ext: int
     info: dict = field(default_factory=dict)
+    pinned: bool = False      # captured in a CUDA graph: never evicted
+
+
+class ProgramCache:
+    """key -> Program, least-recently-used eviction: callers with ever-changing shapes (per-file PLC / latency
+    evaluation) would otherwise grow the set of built programs without bound.  Evicted programs are destroyed."""
+
+    def __init__(self, lib, capacity: int = int(os.environ.get("B2C_PROGRAM_CACHE", "48"))):
+        self.lib, self.capacity = lib, max(1, capacity)
+        self._d = {}
+
+    def get(self, key, default=None):
+        p = self._d.get(key)
+        if p is None:
+            return default
+        self._d[key] = self._d.pop(key)      # most recently used last
+        return p
+
+    def __setitem__(self, key, prog: Program):
+        old = self._d.pop(key, None)
+        if old is not None and old is not prog:
+            self.lib.b2c_prog_destroy(old.handle)
+        self._d[key] = prog
+        if len(self._d) > self.capacity:
+            for k in [k for k, v in self._d.items() if not v.pinned][: len(self._d) - self.capacity]:
+                self.lib.b2c_prog_destroy(self._d.pop(k).handle)
+
+    def __len__(self):
+        return len(self._d)
+
+    def values(self):
+        return self._d.values()
+
+    def clear(self):
+        while self._d:
+            _, p = self._d.popitem()
+            self.lib.b2c_prog_destroy(p.handle)
 
 
 class Engine:
@@ -108,15 +146,28 @@ class Engine:
         h = C.c_void_p()
         L.check(self.lib.b2c_ctx_create(idx, C.byref(h)), "b2c_ctx_create")
         self.ctx = h
-        self.programs = {}
+        self.programs = ProgramCache(self.lib)
+        #: records that live as long as the packed weights but are not programs (CUDA-graph captures, host staging)
+        self.aux = {}
         self._ws = None
         self._keep = []  # host arrays kept alive during packing
+        #: layers a tensor-core plan had to run on the FP32 kernel (see Emitter._contract)
+        self.fp32_reroutes = []
+
+    def close(self):
+        """Free the programs, the packed weights and the context (idempotent)."""
+        ctx, self.ctx = self.ctx, None
+        if ctx is None:
+            return
+        self.aux.clear()
+        try:
+            self.programs.clear()
+        finally:
+            self.lib.b2c_ctx_destroy(ctx)
 
     def __del__(self):
         try:
-            for p in self.programs.values():
-                self.lib.b2c_prog_destroy(p.handle)
-            self.lib.b2c_ctx_destroy(self.ctx)
+            self.close()
         except Exception:
             pass
 
@@ -243,6 +294,7 @@ class Emitter:
         L.check(self.lib.b2c_prog_create(eng.ctx, C.byref(h)), "b2c_prog_create")
         self.h = h
         self.arena = Arena()
+        self.fp32_reroutes = 0
 
     # buffers
     def new(self, nfloats: int) -> int:
@@ -267,7 +319,8 @@ class Emitter:
 
     def finish(self, n_ext: int, **info) -> Program:
         return Program(self.h, self.arena.peak + ALIGN, n_ext,
-                       dict(info, launches=self.lib.b2c_prog_num_launches(self.h), ops=self.lib.b2c_prog_num_ops(self.h)))
+                       dict(info, launches=self.lib.b2c_prog_num_launches(self.h), ops=self.lib.b2c_prog_num_ops(self.h),
+                            fp32_reroutes=self.fp32_reroutes))
 
     # ops
     def stem(self, w: ConvW, x, out_raw, out_act, alpha, B, Lx, act_fmt=L.FMT_F32):
@@ -290,7 +343,18 @@ class Emitter:
         """Shared by conv / convT: run the contraction at `prec` when the tensor-core kernel takes the
         layer, else on the FP32 kernel, converting activation storage on either side when the caller's
         formats differ from what that kernel reads / writes."""
-        if not self.tc_ok(w, Lin, prec):
+        if prec != L.PREC_F32 and not self.tc_ok(w, Lin, prec):
+            # Not silent: the layer keeps its results (the FP32 kernel is the more exact arithmetic) but costs several
+            # times the tcgen05 time.  Recorded on the engine and in the program's info, warned once per layer shape;
+            # B2C_STRICT_PRECISION=1 turns it into an error.
+            what = (f"conv {w.cin}->{w.cout} k={w.k} stride={w.stride} dil={w.dilation} at Lin={Lin}: not eligible for "
+                    f"the tcgen05 kernel (precision {prec}); running on the FP32 CUDA-core kernel")
+            if os.environ.get("B2C_STRICT_PRECISION", "0") == "1":
+                raise L.B2CError(what)
+            if what not in self.eng.fp32_reroutes:
+                self.eng.fp32_reroutes.append(what)
+                warnings.warn("b200 codec: " + what, RuntimeWarning, stacklevel=3)
+            self.fp32_reroutes += 1
             prec = L.PREC_F32
         need = L.FMT_OF_PREC[prec]
         n_in, n_out = B * Lin * w.cin, B * Lout * w.cout

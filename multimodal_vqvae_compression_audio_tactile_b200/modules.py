@@ -13,6 +13,7 @@ Forward only (``torch.no_grad`` semantics); CPU tensors raise -- there is no fal
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -111,14 +112,40 @@ class _Top(nn.Module):
     micro_batch = 64
 
     def _engine(self, device) -> Engine:
-        ver = tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+        """(engine, packed weights) for this module on `device`.  A sub-module of a ProposedEval borrows its
+        parent's engine (one set of packed weights per model, not one per module).  The packed copy is rebuilt when a
+        parameter / buffer changes identity, storage or version counter; in-place edits through ``p.data`` bump
+        neither -- call ``invalidate()`` after those."""
+        owner = self.__dict__.get("_b2c_owner")
+        if owner is not None:
+            parent, slot = owner[0](), owner[1]
+            if parent is not None and getattr(parent, slot[0], None) is self:
+                eng, pk = parent._engine(device)
+                return eng, slot[1](pk)
+        ts = list(self.parameters()) + list(self.buffers())
+        ver = tuple((id(p), p.data_ptr(), int(p._version)) for p in ts)
         st = self.__dict__.get("_b2c_state")
         if st is None or st[0] != ver or st[1].device != device:
+            self.__dict__.pop("_b2c_state", None)
+            if st is not None:
+                st[1].close()
             eng = Engine(device)
             packed = self._pack(eng)
             st = (ver, eng, packed)
             self.__dict__["_b2c_state"] = st
         return st[1], st[2]
+
+    def invalidate(self):
+        """Drop the packed weights and built programs; the next call re-packs from the current parameters.  Needed
+        after in-place edits through ``.data`` (the EMA codebook update pattern), which no version counter sees."""
+        st = self.__dict__.pop("_b2c_state", None)
+        if st is not None:
+            st[1].close()
+        owner = self.__dict__.get("_b2c_owner")
+        if owner is not None and owner[0]() is not None:
+            owner[0]().invalidate()
+
+    repack = invalidate
 
     def _pack(self, eng):  # pragma: no cover
         raise NotImplementedError
@@ -136,6 +163,7 @@ class _Top(nn.Module):
     def __getstate__(self):
         d = dict(self.__dict__)
         d.pop("_b2c_state", None)
+        d.pop("_b2c_owner", None)
         return d
 
 
@@ -470,6 +498,13 @@ class ProposedEval(_Top):
         self.vq = ResidualVQEMA(dim=CODE_DIM, n_books=rvq_books, n_embed=rvq_embed)
         self.last_indices = None
         self.last_audio_codes = None
+        # the sub-modules run on this model's engine when called on their own (encode_latents + T_DEC(z), the
+        # reference's latency loop :511-521): one set of packed weights per model
+        me = weakref.ref(self)
+        for name, pick in (("A_ENC", lambda pk: pk["a_enc"]), ("T_ENC", lambda pk: pk["t_enc"]),
+                           ("T_DEC", lambda pk: pk["t_dec"]), ("A_QUANT", lambda pk: pk["a_q"]),
+                           ("predict", lambda pk: pk["pp"]), ("vq", lambda pk: pk["pp"].books)):
+            getattr(self, name).__dict__["_b2c_owner"] = (me, (name, pick))
         #: replay the per-shape program as a CUDA graph (one graph launch instead of ~125 kernel launches):
         #: what the batch-1 streaming path (measure_proposed_latency, :489-525) wants
         self.use_cuda_graph = False
@@ -622,7 +657,7 @@ class ProposedEval(_Top):
         dev = a.device
         prog = self.program(eng, pk, B, T, use, decode=decode, latents_cm=want_latents)
         key = ("graph", id(prog))
-        rec = eng.programs.get(key)
+        rec = eng.aux.get(key)
         if rec is None:
             c, n_q, Tl, Lout = pk["pp"].c, pk["n_q"], prog.info["Tl"], prog.info["Lout"]
             st = dict(a=torch.empty(B, 1, T, device=dev), t=torch.empty(B, 1, T, device=dev),
@@ -642,7 +677,8 @@ class ProposedEval(_Top):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 eng.run(prog, ext)
-            rec = eng.programs[key] = dict(graph=graph, st=st, ws=eng.workspace(prog.ws_bytes))   # keeps the workspace alive
+            prog.pinned = True
+            rec = eng.aux[key] = dict(graph=graph, st=st, prog=prog, ws=eng.workspace(prog.ws_bytes))   # keeps the workspace alive
         st = rec["st"]
         st["a"].copy_(a); st["t"].copy_(t)
         rec["graph"].replay()
@@ -684,9 +720,9 @@ class ProposedEval(_Top):
             idx_out = torch.empty(B, use, Tl, dtype=torch.int32, pin_memory=True)
         mb = min(B, self.micro_batch)
         key = ("hoststage", mb, T, use)
-        st = eng.programs.get(key)
+        st = eng.aux.get(key)
         if st is None:
-            st = eng.programs[key] = [dict(
+            st = eng.aux[key] = [dict(
                 a=torch.empty(mb, T, device=dev), t=torch.empty(mb, T, device=dev),
                 y=torch.empty(mb, Lout, device=dev), idx=torch.empty(mb, max(use, 1), Tl, device=dev, dtype=torch.int32),
                 codes=torch.empty(mb, n_q, Tl, device=dev, dtype=torch.int32)) for _ in range(2)]

@@ -37,6 +37,10 @@ CODEC_CASES = {
     # codebook with gaussian frames, and the largest with a books_use prefix (Evaluation/dac_vcpwq_proposed.py stages)
     "cal_b1k128_normal": dict(books=1, K=128, B=1, T=24000, kind="normal", calibrate=True),
     "cal_b10k512_use6": dict(books=10, K=512, B=1, T=24000, kind="uniform", calibrate=True, books_use=6),
+    # the two remaining points of config 2's five ((1,128) (4,256) (8,512) (10,128) (10,512)) with ALL
+    # books in use on full 1-s frames
+    "cal_b4k256": dict(books=4, K=256, B=1, T=24000, kind="normal", calibrate=True),
+    "cal_b10k512": dict(books=10, K=512, B=1, T=24000, kind="sines", calibrate=True),
 }
 
 # name -> (N, D, K) for ResidualVQEMA._nearest_l2 (config 5 subset the CPU finishes in seconds)

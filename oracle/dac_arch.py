@@ -178,6 +178,10 @@ class VectorQuantize(nn.Module):
             + cb_n.pow(2).sum(1, keepdim=True).t()
         )
         idx = (-dist).max(1)[1].reshape(b, t)
+        # oracle-side addition (not in dac): top-1 / top-2 margin of the score the arg-max decides on, so the parity
+        # tests can tell a floating-point near-tie from a wrong code
+        top2 = (-dist).topk(2, dim=1).values
+        self.last_margin = (top2[:, 0] - top2[:, 1]).reshape(b, t)
         z_q = F.embedding(idx, cb).transpose(1, 2)
         return z_q, idx, dist
 
@@ -208,7 +212,7 @@ class ResidualVectorQuantize(nn.Module):
         residual = z
         commit = 0
         cbl = 0
-        codes, latents = [], []
+        codes, latents, margins = [], [], []
         if n_quantizers is None:
             n_quantizers = self.n_codebooks
         for i, q in enumerate(self.quantizers):
@@ -222,6 +226,8 @@ class ResidualVectorQuantize(nn.Module):
             cbl = cbl + (l_i * mask).mean()
             codes.append(idx_i)
             latents.append(z_e_i)
+            margins.append(q.last_margin)
+        self.last_margins = torch.stack(margins, dim=1)      # [B, n_q, T], oracle-side addition
         return z_q, torch.stack(codes, dim=1), torch.cat(latents, dim=1), commit, cbl
 
 

@@ -189,6 +189,7 @@ class ProposedEval(nn.Module):
             trace.update(
                 za=za, qa=qa, zt=zt, z_run=z_run,
                 a_codes=quant[1] if len(quant) > 1 else None,
+                a_margin=getattr(self.A_QUANT, "last_margins", None),
                 idx=torch.cat(idx_all, dim=-1), margin=torch.cat(mar_all, dim=-1),
                 rD=torch.cat(rd_all, dim=-1), z_pred=torch.cat(zp_all, dim=-1),
             )

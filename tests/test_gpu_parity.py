@@ -1,7 +1,8 @@
 """GPU parity suite (-m gpu): the CUDA path, called through the C-ABI library, against the committed
 golden vectors (made by running the reference's classes) and against the CPU oracle on the same seeded
-inputs.  Indices must be bit-exact except at documented floating-point near-ties (oracle top-1/top-2
-margin < 1e-5); reconstructions within the tolerance written next to each assert."""
+inputs.  Indices must be bit-exact except at documented floating-point near-ties (tests/parity_util.py: the
+first differing stage of a token must sit below the oracle score margin TIE); reconstructions within the
+tolerance written next to each assert."""
 import os
 
 import numpy as np
@@ -10,23 +11,32 @@ import torch
 
 import multimodal_vqvae_compression_audio_tactile_b200 as pkg
 from oracle import cases, proposed
+from parity_util import check_against_oracle, psnr, stage_flips
 
 pytestmark = pytest.mark.gpu
 
 # Arithmetic plans (multimodal_vqvae_compression_audio_tactile_b200/_lib.py PLANS):
 #   f32: FP32 FFMA everywhere.  tc: tcgen05, bf16 hi/lo split x3 (>= 16 mantissa bits) upstream of the
 #   quantizer, single-pass bf16 in the decoder.
-# TIE: oracle top-1/top-2 score margin below which an index flip is a documented floating-point near-tie
-#   (scores are O(1); fp32 summation-order noise is ~1e-6, the bf16x3 contractions add ~1e-5 relative).
-# Y_TOL: max |y - y_ref| when all indices agree (|y| <= ~0.15).  PSNR_MIN: reconstruction PSNR vs the oracle.
+# TIE: oracle top-1/top-2 score margin below which an index flip of the proposed codec's residual VQ is a documented
+#   floating-point near-tie (scores are O(1); fp32 summation-order noise is ~1e-6, the bf16x3 contractions upstream
+#   add ~1e-5 relative).  TIE_CODE: the same for the DAC quantizer's cosine scores (range [-4, 0]); its input is the
+#   encoder output, whose error (ENC_TOL) is what moves them.  The final round-1 build measured 0 flips on every
+#   case (profiles/r01_parity_diag_tc_*.txt): the margins are the documented bound, not a measured slack.
+# Y_TOL: max |y - y_ref| when all indices agree (|y| <= ~0.15; measured 1.1e-3 for plan tc = single-pass bf16
+#   decoder).  PSNR_MIN: reconstruction PSNR vs the oracle (measured 48 dB).
 PLANS = ["f32", "tc"]
 TIE = {"f32": 1e-5, "tc": 5e-5}
-Y_TOL = {"f32": 2e-5, "tc": 4e-3}
+TIE_CODE = {"f32": 2e-5, "tc": 2e-4}
+Y_TOL = {"f32": 2e-5, "tc": 2e-3}
 Z_TOL = {"f32": 1e-4, "tc": 1e-3}
-PSNR_MIN = {"f32": 80.0, "tc": 40.0}
+PSNR_MIN = {"f32": 80.0, "tc": 45.0}
 ENC_TOL = {"f32": 2e-5, "tc": 3e-4}
-DEC_TOL = {"f32": 1e-5, "tc": 4e-3}
+DEC_TOL = {"f32": 1e-5, "tc": 2e-3}
 PRED_TOL = {"f32": 5e-5, "tc": 2e-4}
+# when near-tie flips exist: tokens that flipped or depend on one (parity_util.dependent_tokens), per frame
+MAX_FLIPPED_TOKENS_PER_FRAME = 2
+PSNR_MIN_WITH_FLIPS = 35.0
 
 
 @pytest.fixture(scope="module")
@@ -45,17 +55,26 @@ def gpu_model(ref, case, precision="tc"):
 
 
 def first_mismatch_is_near_tie(idx, gold, margin, tie):
-    bad = idx != gold
-    if not bad.any():
-        return True, 0
-    first = (bad.int().cumsum(dim=1) == 1) & bad
-    return bool((margin[first] < tie).all()), int(bad.sum())
+    ok, n, _, _ = stage_flips(idx, gold, margin, tie)
+    return ok, n
 
 
-def psnr(y, ref):
-    mse = float(((y - ref) ** 2).mean())
-    peak = float(ref.abs().max()) or 1.0
-    return 10 * np.log10(peak * peak / max(mse, 1e-30))
+def compare_frames(y, idx, codes, z, tr, plan, frames_label=""):
+    """The full-path check used by every oracle comparison: near-tie rule on both index sets, then the reconstruction
+    (and latents) within tolerance -- tight when nothing flipped, PSNR-bounded when documented near-ties did."""
+    res = check_against_oracle(idx, codes, tr, TIE[plan], TIE_CODE[plan])
+    B = y.shape[0]
+    if res["exact"]:
+        err = float((y - tr["y"]).abs().max())
+        assert err < Y_TOL[plan], (frames_label, err)
+        assert psnr(y, tr["y"]) > PSNR_MIN[plan], frames_label
+        if z is not None:
+            assert float((z - tr["z_run"]).abs().max()) < Z_TOL[plan], frames_label
+    else:
+        n = res["n_code"] + res["n_own"] + res["n_dependent"]
+        assert n <= MAX_FLIPPED_TOKENS_PER_FRAME * B + (16 if res["n_code"] else 0) * B, (frames_label, res)
+        assert psnr(y, tr["y"]) > PSNR_MIN_WITH_FLIPS, (frames_label, res)
+    return res
 
 
 @pytest.mark.parametrize("plan", PLANS)
@@ -68,27 +87,59 @@ def test_codec_against_golden(name, plan, dev, golden_dir, oracle_models):
     a, t = cases.codec_inputs(case)
     y = net.forward_eval(a.to(dev), t.to(dev), case.get("books_use")).cpu()
     idx = net.last_indices.cpu().long()
-    gold_idx = torch.from_numpy(g["idx"].astype(np.int64))
-    assert tuple(y.shape) == g["y"].shape
-    assert tuple(idx.shape) == tuple(gold_idx.shape)
     codes = net.last_audio_codes.cpu().long()
+    z = net.encode_latents(a.to(dev), t.to(dev), case.get("books_use")).cpu()
+    gold_idx = torch.from_numpy(g["idx"].astype(np.int64))
     gold_codes = torch.from_numpy(g["a_codes"].astype(np.int64))
-    n_code_bad = int((codes != gold_codes).sum())
-    assert n_code_bad <= gold_codes.numel() // 500, f"{n_code_bad} audio-code mismatches"
-    n_bad = int((idx != gold_idx).sum())
-    if n_bad == 0 and n_code_bad == 0:
+    assert tuple(y.shape) == g["y"].shape
+    assert tuple(idx.shape) == tuple(gold_idx.shape) and tuple(codes.shape) == tuple(gold_codes.shape)
+    if torch.equal(idx, gold_idx) and torch.equal(codes, gold_codes):
+        # the golden file (made by the REFERENCE's classes) is the checker
         err = float((y - torch.from_numpy(g["y"])).abs().max())
         assert err < Y_TOL[plan], err
         assert psnr(y, torch.from_numpy(g["y"])) > PSNR_MIN[plan]
-        z = net.encode_latents(a.to(dev), t.to(dev), case.get("books_use")).cpu()
         assert float((z - torch.from_numpy(g["z_run"])).abs().max()) < Z_TOL[plan]
-    else:   # near-tie flips: rebuild the margins with the oracle and check each first flip is a near-tie
+    else:
+        # some index differs: rebuild the score margins with the oracle (pinned bit-equal to the reference classes) and
+        # require every first flip to be a documented near-tie; no other waiver
         tr = {}
         ref.forward_eval(a, t, case.get("books_use"), trace=tr)
-        ok, n = first_mismatch_is_near_tie(idx, tr["idx"], tr["margin"], TIE[plan])
-        assert ok or n_code_bad > 0, f"{n} index mismatches that are not near-ties"
-        assert n <= idx.numel() // 50, f"{n} of {idx.numel()} indices differ"
-        assert psnr(y, torch.from_numpy(g["y"])) > 30.0
+        assert torch.equal(tr["idx"], gold_idx) and torch.equal(tr["a_codes"], gold_codes), "oracle drifted from its golden"
+        compare_frames(y, idx, codes, z, tr, plan, name)
+
+
+@pytest.mark.parametrize("which", ["bench", "calibrated"])
+def test_benchmarked_configuration_against_oracle(which, dev, oracle_models):
+    """The configuration bench.py times (books 8, K 512, plan tc, 64 frames per program) has its own oracle check:
+    frames 0, 31 and 63 of a 64-frame program against the oracle run on those frames alone.  'bench' uses bench.py's
+    exact model and inputs (random-init codebooks, U(-1,1), generator seed 123 = rank 0); 'calibrated' the same
+    shapes with codebooks every stage of which has many live codes."""
+    if which == "bench":
+        case = dict(books=8, K=512)
+        ref = cases.build_reference_style_model(proposed.ProposedEval, case)      # bench.build_oracle()
+        g = torch.Generator().manual_seed(123)
+        a = (torch.rand(128, 1, 24000, generator=g) * 2 - 1)[:64]
+        t = (torch.rand(128, 1, 24000, generator=g) * 2 - 1)[:64]
+    else:
+        case = cases.CODEC_CASES["cal_b8k512"]
+        ref = oracle_models("cal_b8k512")
+        a, t = cases.codec_inputs(dict(case, B=64))
+    net = gpu_model(ref, case, "tc")
+    net.micro_batch = 64
+    y = net.forward_eval(a.to(dev), t.to(dev)).cpu()
+    idx, codes = net.last_indices.cpu().long(), net.last_audio_codes.cpu().long()
+    eng, pk = net._engine(dev)
+    assert any(k[0] == "codec" and k[1] == 64 for k in eng.programs._d), "the 64-frame program must be the one that ran"
+    assert eng.fp32_reroutes == [], eng.fp32_reroutes
+    n_exact = 0
+    for f in (0, 31, 63):
+        tr = {}
+        ref.forward_eval(a[f:f + 1], t[f:f + 1], None, trace=tr)
+        res = compare_frames(y[f:f + 1], idx[f:f + 1], codes[f:f + 1], None, tr, "tc", f"{which} frame {f}")
+        n_exact += int(res["exact"])
+    assert n_exact >= 2, "near-ties are rare: at most one of three frames may contain one"
+    if which == "calibrated":
+        assert len(torch.unique(idx[:, 0])) > 32          # the arg-max is exercised
 
 
 @pytest.mark.parametrize("plan", PLANS)
@@ -105,15 +156,18 @@ def test_stages_teacher_forced(plan, dev, oracle_models):
     assert float((za - tr["za"]).abs().max()) < ENC_TOL[plan]          # |za| ~ 0.1..1
     zt = net.T_ENC(t.to(dev)).cpu()
     assert float((zt - tr["zt"]).abs().max()) < ENC_TOL[plan]
+    # the DAC quantizer runs FP32 in every plan and is fed the oracle's own za here: any code flip must be a near-tie
+    # of the oracle's cosine scores at fp32 summation-order level
     qa, codes, *_ = net.A_QUANT(tr["za"].to(dev))
-    bad = codes.cpu() != tr["a_codes"]
-    assert int(bad.sum()) <= bad.numel() // 1000
-    if not bad.any():
+    ok, n, worst, _ = stage_flips(codes.cpu(), tr["a_codes"], tr["a_margin"], TIE_CODE["f32"])
+    assert ok, (n, worst)
+    if n == 0:
         assert float((qa.cpu() - tr["qa"]).abs().max()) < 5e-5  # |qa| ~ 3
     qa8, codes8, *_ = net.A_QUANT(tr["za"].to(dev), n_quantizers=8)
     q_ref8 = ref.A_QUANT(tr["za"], 8)
     assert tuple(codes8.shape) == tuple(q_ref8[1].shape)
-    assert int((codes8.cpu() != q_ref8[1]).sum()) <= 2
+    ok, n, worst, _ = stage_flips(codes8.cpu(), q_ref8[1], ref.A_QUANT.last_margins, TIE_CODE["f32"])
+    assert ok, (n, worst)
     y = net.T_DEC(tr["z_run"].to(dev)).cpu()
     assert float((y - y_ref).abs().max()) < DEC_TOL[plan]
     zp, zk = cases.predictor_inputs()
@@ -285,15 +339,24 @@ def test_odd_frame_length_uses_fp32_kernel_for_ineligible_layers(dev, oracle_mod
     a, t = cases.codec_inputs(case)
     tr = {}
     y_ref = ref.forward_eval(a, t, None, trace=tr)
-    out = {}
     for plan in PLANS:
         net = gpu_model(ref, case, plan)
-        out[plan] = (net.forward_eval(a.to(dev), t.to(dev)).cpu(), net.last_indices.cpu().long())
-        assert tuple(out[plan][0].shape) == tuple(y_ref.shape)
-        ok, n = first_mismatch_is_near_tie(out[plan][1], tr["idx"], tr["margin"], TIE[plan])
-        assert ok, (plan, n)
-        if n == 0:
-            assert float((out[plan][0] - y_ref).abs().max()) < Y_TOL[plan]
+        if plan == "tc":    # the change of arithmetic is announced, recorded, and can be made an error
+            with pytest.warns(RuntimeWarning, match="not eligible for the tcgen05 kernel"):
+                y = net.forward_eval(a.to(dev), t.to(dev)).cpu()
+            eng, _ = net._engine(dev)
+            assert len(eng.fp32_reroutes) >= 1
+            os.environ["B2C_STRICT_PRECISION"] = "1"
+            try:
+                strict = gpu_model(ref, case, plan)
+                with pytest.raises(pkg.B2CError):
+                    strict.forward_eval(a.to(dev), t.to(dev))
+            finally:
+                del os.environ["B2C_STRICT_PRECISION"]
+        else:
+            y = net.forward_eval(a.to(dev), t.to(dev)).cpu()
+        assert tuple(y.shape) == tuple(y_ref.shape)
+        compare_frames(y, net.last_indices.cpu().long(), net.last_audio_codes.cpu().long(), None, tr, plan, plan)
 
 
 def test_fused_residual_unit_matches_separate_launches(dev):

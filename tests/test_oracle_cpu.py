@@ -107,3 +107,53 @@ def test_predictor_golden(golden_dir):
     with torch.no_grad():
         out = pred(zp, zk)
     assert np.abs(out.numpy() - g["out"]).max() < 1e-4
+
+
+def test_backbone_restatement_against_the_real_dac_package():
+    """Closes the 'parity unpinned' gap of the third-party backbone the day a box has descript-audio-codec: the
+    restatement must have dac.DAC's state-dict keys and shapes, and produce its outputs from the same weights."""
+    dac = pytest.importorskip("dac", reason="descript-audio-codec is not installed (no network in the build image)")
+    torch.manual_seed(0)
+    real = dac.DAC(encoder_dim=64, encoder_rates=[2, 4, 5, 8], decoder_dim=1536, decoder_rates=[8, 5, 4, 2],
+                   n_codebooks=32, codebook_size=1024, codebook_dim=8, sample_rate=24000).eval()
+    mine = dac_arch.DAC().eval()
+    sd_real, sd_mine = real.state_dict(), mine.state_dict()
+    assert sorted(sd_real) == sorted(sd_mine)
+    for k, v in sd_real.items():
+        assert tuple(v.shape) == tuple(sd_mine[k].shape), k
+    mine.load_state_dict(sd_real)
+    x = torch.rand(1, 1, 24000, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    with torch.no_grad():
+        z_r, z_m = real.encoder(x), mine.encoder(x)
+        assert torch.allclose(z_r, z_m, atol=1e-5), float((z_r - z_m).abs().max())
+        q_r, q_m = real.quantizer(z_r), mine.quantizer(z_r)
+        assert torch.equal(q_r[1], q_m[1])                      # codes
+        assert torch.allclose(q_r[0], q_m[0], atol=1e-5)
+        y_r, y_m = real.decoder(q_r[0]), mine.decoder(q_r[0])
+        assert y_r.shape == y_m.shape
+        assert torch.allclose(y_r, y_m, atol=1e-5), float((y_r - y_m).abs().max())
+
+
+def test_near_tie_rule_of_the_parity_suite():
+    """tests/parity_util.py: the first differing stage of a token decides; later stages and dependent tokens do not."""
+    from parity_util import check_against_oracle, dependent_tokens, stage_flips
+    gold = torch.zeros(1, 3, 40, dtype=torch.long)
+    margin = torch.full((1, 3, 40), 0.1)
+    got = gold.clone()
+    assert stage_flips(got, gold, margin, 1e-5)[:2] == (True, 0)
+    got[0, 1, 7] = 5; got[0, 2, 7] = 9            # first flip at stage 1 ...
+    assert stage_flips(got, gold, margin, 1e-5)[0] is False
+    margin[0, 1, 7] = 1e-7                        # ... is a near-tie: the cascade at stage 2 is not judged
+    ok, n, worst, fl = stage_flips(got, gold, margin, 1e-5)
+    assert ok and n == 1 and worst < 1e-6 and bool(fl[0, 7])
+    # a flipped token at the end of a chunk makes the next chunk's head dependent; a flipped DAC code its whole chunk
+    own = torch.zeros(1, 40, dtype=torch.bool); own[0, 15] = True
+    code = torch.zeros(1, 40, dtype=torch.bool); code[0, 35] = True
+    dep = dependent_tokens(code, own)
+    assert dep[0].nonzero().flatten().tolist() == [16] + list(range(32, 40))
+    tr = dict(a_codes=torch.zeros(1, 2, 40, dtype=torch.long), a_margin=torch.full((1, 2, 40), 0.1), idx=gold, margin=margin)
+    res = check_against_oracle(got, torch.zeros(1, 2, 40, dtype=torch.long), tr, 1e-5, 1e-5)
+    assert res == dict(exact=False, n_code=0, n_own=1, n_dependent=0)
+    bad = got.clone(); bad[0, 0, 20] = 3          # a real mismatch is never waived
+    with pytest.raises(AssertionError):
+        check_against_oracle(bad, torch.zeros(1, 2, 40, dtype=torch.long), tr, 1e-5, 1e-5)
