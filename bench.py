@@ -6,7 +6,9 @@
 
 A step = one forward_eval over one batch of synthetic 1-s frames (24 kHz) per GPU; frames are
 independent, so N GPUs run N independent shards (weak scaling, no collective on the hot path; the
-code indices are all-gathered once per step).  One JSON line is printed by rank 0.
+code indices are gathered ONCE, after the timed steps).  One JSON line is printed by rank 0; besides the
+contract's keys it carries `latency` (config 4: batch-1 p50/p99), `search` (config 5 corners, rows sharded
+over the GPUs), `strong_scaling` (fixed global batch, N > 1) and `torch_gpu_baseline` (context).
 """
 from __future__ import annotations
 
@@ -40,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the untimed legs (latency percentiles, search corners, strong-scaling point, torch GPU baseline)")
+    ap.add_argument("--latency-reps", type=int, default=500)
     return ap.parse_args()
 
 
@@ -144,6 +149,123 @@ def run_reference(args):
     }), flush=True)
 
 
+def _pctl(ms):
+    v = sorted(ms)
+    return dict(p50=v[len(v) // 2], p99=v[min(len(v) - 1, int(0.99 * len(v)))], mean=sum(v) / len(v), n=len(v))
+
+
+def _event_times(torch, fn, reps):
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+def latency_leg(torch, net, dev, reps):
+    """Config 4 (Evaluation/dac_vcpwq_proposed6_latency.py:489-525): zeros [1,1,24000] x 2, 3 warm-ups, then
+    encode_latents and T_DEC(z_run) timed separately per repetition -- CUDA events, p50/p99 over `reps`."""
+    a = torch.zeros(1, 1, T, device=dev)
+    t = torch.zeros(1, 1, T, device=dev)
+    for _ in range(3):
+        z = net.encode_latents(a, t)
+        net.T_DEC(z)
+        net.forward_eval(a, t)
+    torch.cuda.synchronize()
+    z = net.encode_latents(a, t).clone()
+    enc = _pctl(_event_times(torch, lambda: net.encode_latents(a, t), reps))
+    dec = _pctl(_event_times(torch, lambda: net.T_DEC(z), reps))
+    fwd = _pctl(_event_times(torch, lambda: net.forward_eval(a, t), reps))
+    net.use_cuda_graph = True
+    try:
+        for _ in range(3):
+            net.forward_eval(a, t)
+        torch.cuda.synchronize()
+        fwd_g = _pctl(_event_times(torch, lambda: net.forward_eval(a, t), reps))
+    finally:
+        net.use_cuda_graph = False
+    eng, pk = net._engine(dev)
+    prog = net.program(eng, pk, 1, T, BOOKS)
+    return {"unit": "ms", "batch": 1, "reps": reps, "input": "zeros [1,1,24000] (the latency script's frame)",
+            "encode_p50": enc["p50"], "encode_p99": enc["p99"], "decode_p50": dec["p50"], "decode_p99": dec["p99"],
+            "forward_p50": fwd["p50"], "forward_p99": fwd["p99"], "forward_graph_p50": fwd_g["p50"],
+            "forward_graph_p99": fwd_g["p99"], "launches_forward": prog.info["launches"],
+            "reference_published_ms": {"encode": [12.83, 16.27], "decode": [2.75, 2.86], "hardware": "unknown GPU, fp16 autocast"}}
+
+
+SEARCH_CORNERS = [  # (N, D, K): config 5 corners incl. the K=8192 / D=96 / N=65536 point of SURVEY 8(d)
+    (65536, 96, 8192), (65536, 256, 8192), (65536, 8, 256), (16384, 64, 2048), (4800, 96, 512), (1024, 128, 4096),
+    (75, 96, 1024), (65536, 96, 1024)]
+
+
+def search_leg(torch, dist, pkg, dev, world, rank, peaks):
+    """Config 5: nearest-code search corners; with N GPUs every rank searches its shard of the N rows (the codebook is
+    replicated), time = max over ranks.  frac = the op's bound (max of the executed-MMA time at the sustained bf16 peak
+    and the algorithmic bytes at the measured HBM rate) / measured time."""
+    from multimodal_vqvae_compression_audio_tactile_b200 import driver
+    rows = []
+    for (N, D, K) in SEARCH_CORNERS:
+        g = torch.Generator().manual_seed(1000003 * D + 7919 * K + N)
+        x = torch.randn(N, D, generator=g) / D ** 0.5
+        emb = torch.randn(K, D, generator=g) / D ** 0.5
+        lo, hi = driver.shard_bounds(N, world, rank)
+        n_loc = hi - lo
+        ms = float("nan")
+        if n_loc > 0:
+            xs, es = x[lo:hi].to(dev), emb.to(dev)
+            for _ in range(3):
+                pkg.nearest_code(xs, es)
+            torch.cuda.synchronize()
+            v = sorted(_event_times(torch, lambda: pkg.nearest_code(xs, es), 10))
+            ms = v[len(v) // 2]
+        mt = torch.tensor([0.0 if ms != ms else ms], device=dev)
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        ms = mt.item()
+        n_max = (N + world - 1) // world
+        flops = 2.0 * n_max * D * K
+        byts = 4.0 * (n_max * D + K * D) + 4.0 * n_max
+        bound_ms = max(3.0 * flops / (peaks["tf_sus"] * 1e12), byts / (peaks["hbm"] * 1e9)) * 1e3
+        rows.append({"N": N, "D": D, "K": K, "rows_per_gpu": n_max, "ms": ms, "frac": bound_ms / ms if ms > 0 else None,
+                     "tflops_algorithmic_all_gpus": 2.0 * N * D * K / ms / 1e9 if ms > 0 else None})
+    return rows
+
+
+def torch_gpu_leg(torch, ref, dev, frames=16, reps=3):
+    """Untimed-context leg ('the bar for the new kernels is PyTorch-eager cuDNN/cuBLAS on the same B200'):
+    the reference's own classes on the restated backbone, moved to the GPU, eager, fp32 (TF32 off) and under bf16
+    autocast.  Not the product, not part of `value`."""
+    import copy
+    out = {"frames_per_step": frames, "unit": UNIT}
+    try:
+        m = copy.deepcopy(ref).to(dev).eval()
+        g = torch.Generator().manual_seed(123)
+        a = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
+        t = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16), ("fp16_autocast", torch.float16)):
+            def run():
+                with torch.no_grad():
+                    if ctx is None:
+                        return m.forward_eval(a, t)
+                    with torch.autocast("cuda", dtype=ctx):
+                        return m.forward_eval(a, t)
+            run(); run()
+            torch.cuda.synchronize()
+            ms = sorted(_event_times(torch, run, reps))[reps // 2]
+            out[name] = frames / (ms / 1e3)
+        del m
+        torch.cuda.empty_cache()
+    except Exception as e:   # context only: never fails the bench
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -174,7 +296,9 @@ def main():
     net.precision = prec
     net.micro_batch = args.micro_batch
 
+    # weak scaling: every rank owns B frames of a world*B global batch (driver.ShardedCodec: contiguous shards)
     B = args.batch
+    codec = driver.ShardedCodec(driver.codec_forward_fn(net))
     g = torch.Generator().manual_seed(123 + rank)
     a_host = (torch.rand(B, 1, T, generator=g) * 2 - 1).pin_memory()
     t_host = (torch.rand(B, 1, T, generator=g) * 2 - 1).pin_memory()
@@ -188,12 +312,7 @@ def main():
 
     def step():
         flush.zero_()                      # L2 flush between steps (inside the timed region, ~0.1 ms)
-        y = net.forward_eval(a_dev, t_dev)
-        idx = net.last_indices
-        if world > 1:                      # the only exchange: final gather of the code indices
-            out = [torch.empty_like(idx) for _ in range(world)]
-            dist.all_gather(out, idx)
-        return y
+        return codec.run_local(a_dev, t_dev)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -204,7 +323,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        y, idx = step()
     e1.record()
     barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -212,6 +331,16 @@ def main():
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = ms_total.item() / args.steps
     value = world * B / (ms_step / 1e3)
+    # the path's only exchange: ONE final gather of the code indices (north_star), after the timed steps; timed on its own
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    codec.gather_indices(idx)                      # NCCL warm-up (communicator set-up)
+    barrier()
+    g0.record()
+    idx_all = codec.gather_indices(idx)
+    g1.record()
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
+    assert idx_all.shape[0] == world * B
 
     # e2e: same metric through the host-buffer C-ABI entry (H2D + program + D2H inside the timed region)
     y_host = torch.empty(B, 1, net.out_len(T), dtype=torch.float32).pin_memory()       # caller-owned pinned result buffers,
@@ -230,14 +359,37 @@ def main():
     e2e_val = world * B / (e2e_ms.item() / 1e3)
     h2d_b, d2h_b = net.last_host_bytes
     clocks = sampler.stop() if rank == 0 else None
+
+    # strong-scaling point: a FIXED global batch (one rank's weak-scaling batch) split over the ranks
+    strong = None
+    if world > 1 and not args.no_extras:
+        lo, hi = driver.shard_bounds(B, world, rank)
+        a_s, t_s = a_dev[lo:hi], t_dev[lo:hi]
+        for _ in range(3):
+            net.forward_eval(a_s, t_s)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            flush.zero_()
+            net.forward_eval(a_s, t_s)
+        s1.record()
+        barrier()
+        sm = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        dist.all_reduce(sm, op=dist.ReduceOp.MAX)
+        strong = {"global_batch": B, "frames_per_gpu": hi - lo, "ms_per_step": sm.item() / args.steps,
+                  "value": B / (sm.item() / args.steps / 1e3), "unit": UNIT}
+
+    peaks = load_peaks()
+    search = None if args.no_extras else search_leg(torch, dist, pkg, dev, world, rank, peaks)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    latency = None if args.no_extras else latency_leg(torch, net, dev, args.latency_reps)
 
     # ---- roofline of the dominant kernel (conv implicit GEMM), measured live with CUDA events ----
-    peaks = load_peaks()
     eng, pk = net._engine(dev)
     mb = min(B, net.micro_batch)
     prog = net.program(eng, pk, mb, T, BOOKS)
@@ -259,29 +411,23 @@ def main():
     # bf16x3 contractions (everything upstream of the quantizer in plan "tc") issue 3 tensor-core FLOPs per
     # algorithmic FLOP: launches before the decoder's first conv are the x3 ones
     executed = dd["flops"] * (3.0 if dom.endswith("_x3") else 1.0)
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_conv_tc.json")
-    if os.path.isfile(tpath):
-        try:
-            ks = json.load(open(tpath))["kernels"]
-            traffic_note = [dict(kernel=k["Kernel Name"][:40], us=float(k["gpu__time_duration.sum"]),
-                                 dram_MB=float(k["dram__bytes_read.sum"]) + float(k["dram__bytes_write.sum"]),
-                                 tensor_pct=float(k["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]))
-                            for k in ks]
-        except Exception:
-            traffic_note = None
     # DRAM bytes per launch of the dominant family, from the committed ncu capture of this same bench command
-    # (profiles/r01_ncu_dram_traffic_conv_mb64.json: dram__bytes_read.sum + dram__bytes_write.sum of every launch of
-    # one program); only valid for the micro-batch it was captured at
+    # (dram__bytes_read.sum + dram__bytes_write.sum of every launch of one program); only valid for the micro-batch
+    # it was captured at
+    traffic, traffic_src = None, None
     traffic_alg = dd["bytes"] / dd["launches"]
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_conv_mb64.json")
-    if os.path.isfile(tp) and mb == 64 and dom == "conv_tc_x3":
-        try:
-            traffic = json.load(open(tp))["x3"]["dram_bytes_per_launch"]
-        except Exception:
-            traffic = None
+    for name in ("r02_ncu_dram_traffic_conv_mb64.json", "r01_ncu_dram_traffic_conv_mb64.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(tp) and mb == 64 and dom == "conv_tc_x3":
+            try:
+                traffic = json.load(open(tp))["x3"]["dram_bytes_per_launch"]
+                traffic_src = "profiles/" + name
+                break
+            except Exception:
+                traffic = None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sus"], "traffic": traffic, "traffic_algorithmic": traffic_alg,
+                "traffic_source": traffic_src,
                 "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "share_of_step": dd["ms"] / tot_ms, "launches_per_program": dd["launches"],
                 "avg_launch_ms": dd["ms"] / dd["launches"],
@@ -290,9 +436,8 @@ def main():
                 "executed_frac": executed / (dd["ms"] / 1e3) / 1e12 / peaks["tf_sus"],
                 "note": "achieved = algorithmic conv FLOPs / CUDA-event time of the conv launches of one program; the "
                         "bf16x3 launches execute 3 MMA FLOPs per algorithmic FLOP (executed_tflops); traffic = ncu DRAM "
-                        "bytes per launch averaged over the family's launches of one program "
-                        "(profiles/r01_ncu_dram_traffic_conv_mb64.json), traffic_algorithmic = the minimal bytes",
-                "ncu_samples": traffic_note}
+                        "bytes per launch averaged over the family's launches of one program, traffic_algorithmic = "
+                        "the minimal bytes"}
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"by_kind": by_kind, "launches": prof, "micro_batch": mb}, fh, indent=1)
@@ -306,19 +451,29 @@ def main():
         "data": "synthetic (random-init weights seed 7, U(-1,1) frames)",
         "config": {"workload": WORKLOAD, "books": BOOKS, "codes": K_CODES, "frames_per_gpu_per_step": B,
                    "micro_batch": mb, "precision": prec, "l2": "256 MiB flush between steps, inside the timed region",
-                   "parallelism": f"batch-sharded x{world}, no hot-path collective"},
+                   "parallelism": f"batch-sharded x{world} (driver.ShardedCodec), no hot-path collective; one index "
+                                  f"gather after the timed steps (final_gather_ms)"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b},
         "gpu_launches": launches_per_step * args.steps,
+        "final_gather_ms": gather_ms,
         "roofline": roofline,
         "kernel_time_ms_per_program": {k: round(v["ms"], 3) for k, v in by_kind.items()},
     }
+    if strong is not None:
+        out["strong_scaling"] = strong
+    if latency is not None:
+        out["latency"] = latency
+    if search is not None:
+        out["search"] = search
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, ts = cpu_time_forward(ref, args.cpu_sample, 2, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{args.cpu_sample} one-second frames, 1 warm-up + 2 timed forward_eval, "
                                          f"fp32 torch CPU ({sum(ts):.1f} s)"}
+    if not args.no_extras:
+        out["torch_gpu_baseline"] = torch_gpu_leg(torch, ref, dev)
     print(json.dumps(out), flush=True)
 
 

@@ -48,6 +48,19 @@ class ShardedCodec:
     def local_slice(self, n_items: int):
         return shard_bounds(n_items, self.world, self.rank)
 
+    def run_local(self, a_local: torch.Tensor, t_local: torch.Tensor, books_use=None):
+        """The hot path on this rank's own shard: no communication at all.  -> (y_local, idx_local)."""
+        return self.forward_fn(a_local, t_local, books_use)
+
+    def gather_indices(self, idx_local: torch.Tensor, counts=None) -> torch.Tensor:
+        """The path's only exchange: every rank's code indices, concatenated in rank order (called once, after the
+        last step).  counts[r] = rows of rank r (default: equal shards)."""
+        if self.world == 1:
+            return idx_local
+        if counts is None:
+            counts = [idx_local.shape[0]] * self.world
+        return gather_ragged(idx_local, counts, self.group)
+
     def run(self, a_global: torch.Tensor, t_global: torch.Tensor, books_use=None, gather_y: bool = False):
         """a_global/t_global: the full [B, 1, T] batch, identical on every rank (or only this rank's
         slice is read).  Returns (y_local, idx_global[, y_global])."""

@@ -227,7 +227,7 @@ class Encoder(_Top):
         mb = min(B, self.micro_batch)
         for b0 in range(0, B, mb):
             nb = min(mb, B - b0)
-            key = ("enc", nb, T, self._prec("enc"))
+            key = ("enc", id(pk), nb, T, self._prec("enc"))      # id(pk): A_ENC and T_ENC share one engine
             prog = eng.programs.get(key)
             if prog is None:
                 em = Emitter(eng)
@@ -271,7 +271,7 @@ class Decoder(_Top):
         mb = min(B, self.micro_batch)
         for b0 in range(0, B, mb):
             nb = min(mb, B - b0)
-            key = ("dec", nb, Tl, self._prec("dec"))
+            key = ("dec", id(pk), nb, Tl, self._prec("dec"))
             prog = eng.programs.get(key)
             if prog is None:
                 em = Emitter(eng)
@@ -316,7 +316,7 @@ class ResidualVectorQuantize(_Top):
         zin = _as_f32(z)
         zq = torch.empty(B, c, Tl, device=z.device, dtype=torch.float32)
         codes = torch.empty(B, n_q, Tl, device=z.device, dtype=torch.int64)
-        key = ("dacq", B, Tl, n_q)
+        key = ("dacq", wid, B, Tl, n_q)
         prog = eng.programs.get(key)
         if prog is None:
             em = Emitter(eng)
@@ -399,7 +399,7 @@ class CrossPredictor(_Top):
         prec = self._prec("pred")
         a, k = _as_f32(zt_prev), _as_f32(za)
         out = torch.empty(B, c, Tc, device=za.device, dtype=torch.float32)
-        key = ("pred", B, Tc, prec)
+        key = ("pred", id(pp), B, Tc, prec)
         prog = eng.programs.get(key)
         if prog is None:
             em = Emitter(eng)
@@ -456,7 +456,7 @@ class ResidualVQEMA(_Top):
         zin = _as_f32(z)
         out = torch.empty(B, D, T, device=z.device, dtype=torch.float32)
         idx = torch.empty(B, use, T, device=z.device, dtype=torch.int64)
-        key = ("vq", B, T, use)
+        key = ("vq", wid, B, T, use)
         prog = eng.programs.get(key)
         if prog is None:
             em = Emitter(eng)

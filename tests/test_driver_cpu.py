@@ -37,6 +37,10 @@ def _worker(rank, world, port, q):
     y_ref, idx_ref = _fake_forward(a, t, None)
     lo, hi = sc.local_slice(7)
     ok = torch.equal(y_local, y_ref[lo:hi]) and torch.equal(idx_all, idx_ref) and torch.equal(y_all, y_ref)
+    # bench.py's use: the hot path on the rank's own shard (no communication), one gather after the last step
+    y2, idx2 = sc.run_local(a[lo:hi], t[lo:hi])
+    counts = [b - a_ for a_, b in (driver.shard_bounds(7, world, r) for r in range(world))]
+    ok = ok and torch.equal(y2, y_ref[lo:hi]) and torch.equal(sc.gather_indices(idx2, counts), idx_ref)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
