@@ -38,7 +38,7 @@ typedef struct b2c_ctx b2c_ctx;
 typedef struct b2c_prog b2c_prog;
 typedef uint64_t b2c_ref;
 
-#define B2C_ABI_VERSION 2
+#define B2C_ABI_VERSION 3
 #define B2C_NULL_REF ((b2c_ref)0xFFFFFFFFFFFFFFFFull)
 #define B2C_REF(slot, off) ((((b2c_ref)(slot)) << 56) | (b2c_ref)(off))
 
@@ -103,6 +103,9 @@ int b2c_pack_conv(b2c_ctx* ctx, const float* v, const float* g, const float* bia
 int b2c_pack_vector(b2c_ctx* ctx, const float* data, size_t n);
 /* ResidualVQEMA.books (:412-415): n_books host pointers to [K, D]; also stores 0.5*|e|^2 */
 int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n_books, int K, int D);
+/* After an in-place change of ResidualVQEMA.books[book] on the device (ema_step, Training/compare_dacvsproposal_3.py:
+ * 264-276): copy the new rows (device pointer, [K, D]) into the packed codebooks and recompute 0.5*|e|^2 on `stream`. */
+int b2c_codebooks_refresh(b2c_ctx* ctx, int wid, int book, const float* dev_book, void* stream);
 /* dac ResidualVectorQuantize: per stage in_proj (v,g,bias) [d,c,1], out_proj (v,g,bias) [c,d,1],
  * codebook [K,d]; arrays of n_q host pointers each. */
 int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, const float* const* in_v, const float* const* in_g,
@@ -150,6 +153,22 @@ int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int 
 int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub, int pe_wid,
                        int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk,
                        int out_fmt);
+/* The same LayerNorm on dense rows with a token mask: rows whose row_mask byte is non-zero read `a` as zeros
+ * (AllPredPLC.forward_step: zt_in = zt_full * ~mask, PLC/PLC1_eval.py:497, then CrossPredictor's pos + ln_q :402-405). */
+int b2c_prog_layernorm_masked(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, b2c_ref row_mask, int pe_wid,
+                              int pe_mode, b2c_ref out, int N, int C, int Tl, int chunk, int out_fmt);
+/* softmax(Q K^T / sqrt(dh)) V over ALL T keys of a frame: the packet-loss-concealment forward calls CrossPredictor
+ * once over the whole file (PLC/PLC1_eval.py:500, attention :411-412; PosEnc1D max_len 8192).  q [B*T, heads*dh],
+ * kv [B*T, 2*heads*dh] (K | V), out [B*T, heads*dh].  Flash-style online softmax: the [T, T] scores never exist. */
+int b2c_prog_attention_full(b2c_prog* p, b2c_ref q, b2c_ref kv, b2c_ref out, int B, int T, int heads, int dh);
+/* out[n, :] = row_mask[n] ? a[n, :] : b[n, :]   (z_filled = torch.where(mask, z_pred, zt_in), PLC/PLC1_eval.py:503) */
+int b2c_prog_select_rows(b2c_prog* p, b2c_ref row_mask, b2c_ref a, b2c_ref b, b2c_ref out, int N, int C);
+/* One book of ResidualVQEMA.ema_step (Training/compare_dacvsproposal_3.py:264-276) given idx = nearest code of every
+ * row (b2c_prog_nearest): emb[k] = decay*emb[k] + one_minus_decay * mean(x[idx == k]) for every code that was hit; the
+ * rows of a code are added in row order like index_add_ on the CPU.  x [N, D], idx int32 [N], emb [K, D] updated IN
+ * PLACE, counts int32 [K] (optional: bincount). */
+int b2c_prog_ema_update(b2c_prog* p, b2c_ref x, b2c_ref idx, b2c_ref emb, b2c_ref counts, int N, int D, int K, float decay,
+                        float one_minus_decay);
 /* softmax(Q K^T / sqrt(dh)) V inside each chunk (:401-402).
  *   kv [B*Tl, 2*heads*dh] (K | V).  q_mode 0: q is a [chunk, heads*dh] table (row = position in chunk),
  *   out rows dense [B*Tl].  q_mode 1: q is [B*nfix, heads*dh], one query per chunk head, out [B*nfix]. */

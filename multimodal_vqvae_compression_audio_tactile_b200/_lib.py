@@ -13,7 +13,7 @@ NULL_REF = 0xFFFFFFFFFFFFFFFF
 ACT_NONE, ACT_SNAKE, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 PREC_F32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 FMT_F32, FMT_BF16X2, FMT_BF16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 ROWS_DENSE, ROWS_HEAD, ROWS_HEAD_PREV, ROWS_ZERO = 0, 1, 2, 3
 PE_NONE, PE_CHUNK_POS, PE_ROW0, PE_ROW_N = 0, 1, 2, 3
 
@@ -77,6 +77,11 @@ SIGNATURES = {
     "b2c_prog_ru": (_i, [C.c_void_p, _i, _i, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i]),
     "b2c_prog_head": (_i, [C.c_void_p, _i, _ref, _ref, _i, _i, _i]),
     "b2c_prog_layernorm": (_i, [C.c_void_p, _i, _i, _ref, _i, _ref, _i, _i, _i, C.c_float, _ref, _i, _i, _i, _i, _i]),
+    "b2c_prog_layernorm_masked": (_i, [C.c_void_p, _i, _i, _ref, _ref, _i, _i, _ref, _i, _i, _i, _i, _i]),
+    "b2c_prog_attention_full": (_i, [C.c_void_p, _ref, _ref, _ref, _i, _i, _i, _i]),
+    "b2c_prog_select_rows": (_i, [C.c_void_p, _ref, _ref, _ref, _ref, _i, _i]),
+    "b2c_prog_ema_update": (_i, [C.c_void_p, _ref, _ref, _ref, _ref, _i, _i, _i, C.c_float, C.c_float]),
+    "b2c_codebooks_refresh": (_i, [C.c_void_p, _i, _i, C.c_void_p, C.c_void_p]),
     "b2c_prog_convert": (_i, [C.c_void_p, _ref, _i, _ref, _i, C.c_size_t]),
     "b2c_prog_attention": (_i, [C.c_void_p, _ref, _i, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_rvq": (_i, [C.c_void_p, _i, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),

@@ -13,6 +13,7 @@
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_ru.cuh"
+#include "kernels_ext.cuh"
 
 using namespace b2c;
 
@@ -251,6 +252,29 @@ extern "C" int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n
   return (int)ctx->w.size() - 1;
 }
 
+// 0.5 * |e_k|^2 with the arithmetic of b2c_pack_codebooks (separate multiply and add, ascending d)
+static __global__ void half_sqnorm_seq_f32(const float* __restrict__ emb, float* __restrict__ out, int K, int D) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) { const float e = emb[(long)k * D + d]; s = __fadd_rn(s, __fmul_rn(e, e)); }
+  out[k] = 0.5f * s;
+}
+
+extern "C" int b2c_codebooks_refresh(b2c_ctx* ctx, int wid, int book, const float* dev_book, void* stream) {
+  if (!ctx || wid < 0 || wid >= (int)ctx->w.size() || ctx->w[wid].kind != W_BOOKS || !dev_book)
+    return fail(B2C_ERR_ARG, "b2c_codebooks_refresh: bad argument");
+  Weight& w = ctx->w[wid];
+  if (book < 0 || book >= w.n_books) return fail(B2C_ERR_ARG, "b2c_codebooks_refresh: book %d of %d", book, w.n_books);
+  DEVICE_GUARD(ctx->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* dst = w.dev + (size_t)book * w.K * w.D;
+  CUDA_TRY(cudaMemcpyAsync(dst, dev_book, (size_t)w.K * w.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  half_sqnorm_seq_f32<<<(w.K + 127) / 128, 128, 0, st>>>(dst, w.aux + (size_t)book * w.K, w.K, w.D);
+  CUDA_TRY(cudaPeekAtLastError());
+  return B2C_OK;
+}
+
 extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, const float* const* in_v,
                                 const float* const* in_g, const float* const* in_b, const float* const* out_v,
                                 const float* const* out_g, const float* const* out_b,
@@ -305,7 +329,7 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
 // programs
 // ------------------------------------------------------------------------------------------
 enum OpType { OP_STEM, OP_CONV, OP_HEAD, OP_LN, OP_ATTN, OP_RVQ, OP_NEAREST, OP_DACRVQ, OP_SCATTER, OP_TRANSPOSE,
-              OP_WIDEN, OP_CONV_TC, OP_CONVERT, OP_RU_TC };
+              OP_WIDEN, OP_CONV_TC, OP_CONVERT, OP_RU_TC, OP_ATTN_FULL, OP_SELECT, OP_EMA };
 
 struct Op {
   OpType type;
@@ -320,6 +344,7 @@ struct Op {
   TcRuPlan ru;
   void* scratch = nullptr;   // device memory owned by the op (split residual VQ: residual rows + arg-max keys)
   int i[8] = {0};
+  float f[2] = {0.f, 0.f};
   size_t n = 0;
   int precision = 0;
   int x_fmt = 0, act_fmt = 0;
@@ -559,9 +584,26 @@ extern "C" int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, 
 
 static int nfix_of(int Tl, int chunk) { return (Tl + chunk - 1) / chunk - 1; }
 
+static int add_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub, int pe_wid,
+                         int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk,
+                         int out_fmt, b2c_ref row_mask);
+
 extern "C" int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub,
                                   int pe_wid, int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C,
                                   int Tl, int chunk, int out_fmt) {
+  return add_layernorm(p, gamma_wid, beta_wid, a, a_mode, sub, pe_wid, pe_mode, tanh_post, post_scale, out, N, C, Tl,
+                       chunk, out_fmt, B2C_NULL_REF);
+}
+extern "C" int b2c_prog_layernorm_masked(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, b2c_ref row_mask, int pe_wid,
+                                         int pe_mode, b2c_ref out, int N, int C, int Tl, int chunk, int out_fmt) {
+  if (row_mask == B2C_NULL_REF) return fail(B2C_ERR_ARG, "b2c_prog_layernorm_masked: row_mask is required");
+  return add_layernorm(p, gamma_wid, beta_wid, a, B2C_ROWS_DENSE, B2C_NULL_REF, pe_wid, pe_mode, 0, 1.0f, out, N, C, Tl,
+                       chunk, out_fmt, row_mask);
+}
+
+static int add_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_ref a, int a_mode, b2c_ref sub, int pe_wid,
+                         int pe_mode, int tanh_post, float post_scale, b2c_ref out, int N, int C, int Tl, int chunk,
+                         int out_fmt, b2c_ref row_mask) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_layernorm: NULL program");
   if (!get_w(p, gamma_wid, W_VEC, "b2c_prog_layernorm(gamma)") || !get_w(p, beta_wid, W_VEC, "b2c_prog_layernorm(beta)"))
     return B2C_ERR_ARG;
@@ -571,7 +613,7 @@ extern "C" int b2c_prog_layernorm(b2c_prog* p, int gamma_wid, int beta_wid, b2c_
   Op op;
   op.type = OP_LN;
   blank_refs(op);
-  op.r[0] = a; op.r[1] = sub; op.r[2] = out;
+  op.r[0] = a; op.r[1] = sub; op.r[2] = out; op.r[3] = row_mask;
   op.wid = gamma_wid; op.wid2 = beta_wid; op.wid3 = pe_wid;
   LnArgs& l = op.ln;
   memset(&l, 0, sizeof(l));
@@ -597,6 +639,45 @@ extern "C" int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv
   a.nchunks = (Tl + chunk - 1) / chunk;
   a.nfix = a.nchunks - 1;
   if (q_mode == 1 && a.nfix <= 0) return B2C_OK;  // single chunk: nothing to re-do
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_attention_full(b2c_prog* p, b2c_ref q, b2c_ref kv, b2c_ref out, int B, int T, int heads, int dh) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_attention_full: NULL program");
+  if (dh != 128 || heads < 1) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_attention_full: head dim 128 only (got %d x %d)", heads, dh);
+  if (B <= 0 || T <= 0 || B > 65535 || heads > 65535) return fail(B2C_ERR_ARG, "b2c_prog_attention_full: bad sizes");
+  Op op;
+  op.type = OP_ATTN_FULL;
+  blank_refs(op);
+  op.r[0] = q; op.r[1] = kv; op.r[2] = out;
+  op.i[0] = B; op.i[1] = T; op.i[2] = heads;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_select_rows(b2c_prog* p, b2c_ref row_mask, b2c_ref a, b2c_ref b, b2c_ref out, int N, int C) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_select_rows: NULL program");
+  if (N <= 0 || C <= 0 || (C & 3)) return fail(B2C_ERR_ARG, "b2c_prog_select_rows: N > 0 and C a multiple of 4");
+  Op op;
+  op.type = OP_SELECT;
+  blank_refs(op);
+  op.r[0] = row_mask; op.r[1] = a; op.r[2] = b; op.r[3] = out;
+  op.i[0] = N; op.i[1] = C;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+
+extern "C" int b2c_prog_ema_update(b2c_prog* p, b2c_ref x, b2c_ref idx, b2c_ref emb, b2c_ref counts, int N, int D, int K,
+                                   float decay, float one_minus_decay) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_ema_update: NULL program");
+  if (N <= 0 || D <= 0 || K <= 0 || D > 256) return fail(B2C_ERR_ARG, "b2c_prog_ema_update: bad sizes (D <= 256)");
+  Op op;
+  op.type = OP_EMA;
+  blank_refs(op);
+  op.r[0] = x; op.r[1] = idx; op.r[2] = emb; op.r[3] = counts;
+  op.i[0] = N; op.i[1] = D; op.i[2] = K;
+  op.f[0] = decay; op.f[1] = one_minus_decay;
   p->ops.push_back(op);
   return B2C_OK;
 }
@@ -916,6 +997,7 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         l.gamma = ctx->w[op.wid].dev;
         l.beta = ctx->w[op.wid2].dev;
         l.pe = l.pe_mode != PE_NONE ? ctx->w[op.wid3].dev : nullptr;
+        l.rmask = R.get<const unsigned char>(op.r[3]);
         if (R.bad || !l.out || (l.a_mode != ROWS_ZERO && !l.a)) return fail(B2C_ERR_WORKSPACE, "op %zu (layernorm): unresolved buffer", oi);
         layernorm_rows_f32<<<(l.N + 7) / 8, 256, 0, st>>>(l);
         break;
@@ -1089,6 +1171,37 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         }
         break;
       }
+      case OP_ATTN_FULL: {
+        AttnFullArgs a;
+        a.q = R.get<const float>(op.r[0]);
+        a.kv = R.get<const float>(op.r[1]);
+        a.out = R.get<float>(op.r[2]);
+        a.B = op.i[0]; a.T = op.i[1]; a.heads = op.i[2];
+        if (R.bad || !a.q || !a.kv || !a.out) return fail(B2C_ERR_WORKSPACE, "op %zu (full attention): unresolved buffer", oi);
+        cudaError_t e = cudaFuncSetAttribute(attention_full_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM);
+        if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "full attention smem: %s", cudaGetErrorString(e));
+        attention_full_f32<<<dim3((a.T + AF_BQ - 1) / AF_BQ, a.heads, a.B), 256, AF_SMEM, st>>>(a);
+        break;
+      }
+      case OP_SELECT: {
+        const unsigned char* mk = R.get<const unsigned char>(op.r[0]);
+        const float* a = R.get<const float>(op.r[1]);
+        const float* b = R.get<const float>(op.r[2]);
+        float* out = R.get<float>(op.r[3]);
+        if (R.bad || !mk || !a || !b || !out) return fail(B2C_ERR_WORKSPACE, "op %zu (select rows): unresolved buffer", oi);
+        const long total4 = (long)op.i[0] * (op.i[1] / 4);
+        select_rows_f32<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(mk, a, b, out, total4, op.i[1] / 4);
+        break;
+      }
+      case OP_EMA: {
+        const float* x = R.get<const float>(op.r[0]);
+        const int* idx = R.get<const int>(op.r[1]);
+        float* emb = R.get<float>(op.r[2]);
+        int* counts = R.get<int>(op.r[3]);
+        if (R.bad || !x || !idx || !emb) return fail(B2C_ERR_WORKSPACE, "op %zu (ema update): unresolved buffer", oi);
+        ema_update_f32<<<op.i[2], 128, 0, st>>>(x, idx, emb, counts, op.i[0], op.i[1], op.f[0], op.f[1]);
+        break;
+      }
       case OP_WIDEN: {
         const int* in = R.get<const int>(op.r[0]);
         long long* out = R.get<long long>(op.r[1]);
@@ -1163,6 +1276,13 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
       *bytes = 4.0 * (2.0 * d.N * d.C + (double)d.n_q * d.stage_stride + (double)d.N * d.n_q);
       break;
     }
+    case OP_ATTN_FULL: {
+      const double B = op.i[0], T = op.i[1], H = op.i[2];
+      *kind = B2C_KIND_ATTENTION; *flops = 4.0 * B * H * T * T * 128; *bytes = 4.0 * 4.0 * B * T * H * 128;
+      break;
+    }
+    case OP_SELECT: *bytes = 8.0 * op.i[0] * op.i[1]; break;
+    case OP_EMA: *bytes = 4.0 * ((double)op.i[0] * op.i[1] + 2.0 * op.i[2] * op.i[1] + op.i[0]); break;
     case OP_SCATTER: *bytes = 8.0 * op.i[0] * op.i[4] * op.i[3]; break;
     case OP_TRANSPOSE: *bytes = 8.0 * op.i[0] * op.i[1] * op.i[2]; break;
     case OP_WIDEN: *bytes = 12.0 * op.n; break;

@@ -553,6 +553,7 @@ struct LnArgs {
   int a_mode, pe_mode, tanh_post;
   float post_scale;
   int out_fmt;
+  const unsigned char* rmask;   // optional [N]: rows with a non-zero byte read a as zeros (PLC: zt * ~mask, PLC1_eval.py:491)
 };
 
 __device__ __forceinline__ long gather_row(int n, int mode, int Tl, int chunk, int nfix) {
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_f32(const LnArgs p) {
   if (n >= p.N) return;
   const int C = p.C;
   const float* ar = nullptr;
-  if (p.a_mode != ROWS_ZERO) ar = p.a + gather_row(n, p.a_mode, p.Tl, p.chunk, p.nfix) * (long)C;
+  if (p.a_mode != ROWS_ZERO && !(p.rmask && p.rmask[n])) ar = p.a + gather_row(n, p.a_mode, p.Tl, p.chunk, p.nfix) * (long)C;
   const float* sr = p.sub ? p.sub + (long)n * C : nullptr;
   const float* pr = nullptr;
   if (p.pe_mode == PE_CHUNK_POS) pr = p.pe + (long)((n % p.Tl) % p.chunk) * C;

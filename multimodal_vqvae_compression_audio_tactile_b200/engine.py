@@ -410,6 +410,23 @@ class Emitter:
                                             tanh_post, post_scale, self._r(out), N, Cc, Tl, chunk, out_fmt),
                 "b2c_prog_layernorm")
 
+    def layernorm_masked(self, gamma, beta, a, row_mask, out, N, Cc, Tl, chunk, *, pe=-1, pe_mode=L.PE_NONE,
+                         out_fmt=L.FMT_F32):
+        L.check(self.lib.b2c_prog_layernorm_masked(self.h, gamma, beta, self._r(a), self._r(row_mask), pe, pe_mode,
+                                                   self._r(out), N, Cc, Tl, chunk, out_fmt), "b2c_prog_layernorm_masked")
+
+    def attention_full(self, q, kv, out, B, T, heads, dh):
+        L.check(self.lib.b2c_prog_attention_full(self.h, self._r(q), self._r(kv), self._r(out), B, T, heads, dh),
+                "b2c_prog_attention_full")
+
+    def select_rows(self, row_mask, a, b, out, N, Cc):
+        L.check(self.lib.b2c_prog_select_rows(self.h, self._r(row_mask), self._r(a), self._r(b), self._r(out), N, Cc),
+                "b2c_prog_select_rows")
+
+    def ema_update(self, x, idx, emb, counts, N, D, K, decay, one_minus_decay):
+        L.check(self.lib.b2c_prog_ema_update(self.h, self._r(x), self._r(idx), self._r(emb), self._r(counts), N, D, K,
+                                             decay, one_minus_decay), "b2c_prog_ema_update")
+
     def attention(self, q, q_mode, kv, out, B, Tl, chunk, heads, dh):
         L.check(self.lib.b2c_prog_attention(self.h, self._r(q), q_mode, self._r(kv), self._r(out), B, Tl, chunk,
                                             heads, dh), "b2c_prog_attention")
@@ -645,6 +662,31 @@ def emit_predict_rows(em: Emitter, pp: PackedPredictor, qn, ctx, N, Tl, chunk, q
     z_pred = em.new(N * c)
     em.conv(pp.w2, f1, 1, N, res=y1, out_raw=z_pred, prec=prec, x_fmt=f)
     em.drop(f1, y1)
+    return z_pred
+
+
+def emit_predict_full(em: Emitter, pp: PackedPredictor, zq, row_mask, za, B, T, pe_wid, prec):
+    """CrossPredictor.forward over ALL T tokens of every frame in one pass (the packet-loss-concealment use,
+    PLC/PLC1_eval.py:400-415): q = ln_q(pos(zq * ~mask)), kv = ln_kv(pos(za)), full multi-head attention, out + q,
+    + ffn.  zq, za: [B*T, C] channel-last fp32; row_mask: [B*T] bytes or None.  Returns z_pred [B*T, C]."""
+    c, N = pp.c, B * T
+    f = L.FMT_OF_PREC[prec]
+    qn = em.new(N * c)
+    if row_mask is None:
+        em.layernorm(pp.lnq_g, pp.lnq_b, zq, L.ROWS_DENSE, qn, N, c, T, T, pe=pe_wid, pe_mode=L.PE_CHUNK_POS)
+    else:
+        em.layernorm_masked(pp.lnq_g, pp.lnq_b, zq, row_mask, qn, N, c, T, T, pe=pe_wid, pe_mode=L.PE_CHUNK_POS)
+    kvn = em.new(N * c)
+    em.layernorm(pp.lnkv_g, pp.lnkv_b, za, L.ROWS_DENSE, kvn, N, c, T, T, pe=pe_wid, pe_mode=L.PE_CHUNK_POS, out_fmt=f)
+    q, kv = em.new(N * c), em.new(N * 2 * c)
+    em.conv(pp.wq, qn, 1, N, out_raw=q, prec=prec)
+    em.conv(pp.wkv, kvn, 1, N, out_raw=kv, prec=prec, x_fmt=f)
+    em.drop(kvn)
+    ctx = em.new(N * c)
+    em.attention_full(q, kv, ctx, B, T, pp.heads, pp.dh)
+    em.drop(q, kv)
+    z_pred = emit_predict_rows(em, pp, qn, ctx, N, T, T, False, prec)
+    em.drop(qn)
     return z_pred
 
 

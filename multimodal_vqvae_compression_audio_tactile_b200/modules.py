@@ -12,6 +12,7 @@ Forward only (``torch.no_grad`` semantics); CPU tensors raise -- there is no fal
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import weakref
 
@@ -20,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .engine import (Emitter, Engine, PackedDecoder, PackedEncoder, PackedPredictor, emit_decoder, emit_encoder,
-                     emit_latent_coder, emit_predict_rows)
+                     emit_latent_coder, emit_predict_full, emit_predict_rows)
 
 CODE_DIM = 96       # Evaluation/dac_vcpwq_proposed6_latency.py:336
 AR_CHUNK_TOK = 16   # :337
@@ -134,6 +135,13 @@ class _Top(nn.Module):
             st = (ver, eng, packed)
             self.__dict__["_b2c_state"] = st
         return st[1], st[2]
+
+    def _adopt(self, **slots):
+        """Make the named sub-modules run on THIS module's engine when they are called on their own: slot name ->
+        function picking the sub-module's packed weights out of this module's."""
+        me = weakref.ref(self)
+        for name, pick in slots.items():
+            getattr(self, name).__dict__["_b2c_owner"] = (me, (name, pick))
 
     def invalidate(self):
         """Drop the packed weights and built programs; the next call re-packs from the current parameters.  Needed
@@ -370,8 +378,23 @@ class TokenNorm(_Fused):
         self.ln = nn.LayerNorm(c)
 
 
+def pe_table(eng, pp, predictor, rows: int) -> int:
+    """Weight id of a packed positional table with at least `rows` rows (the codec path packs 64; the full-length
+    predictor of the packet-loss-concealment forward needs T_lat <= max_len = 8192, PLC/PLC1_eval.py:337)."""
+    have = getattr(pp, "pe_long_rows", 0)
+    max_len = predictor.pos.pe.shape[0]
+    if rows > max_len:
+        raise ValueError(f"sequence of {rows} tokens exceeds PosEnc1D max_len = {max_len}")
+    if rows > have:
+        n = min(max_len, max(rows, 2 * have, 512))
+        pp.pe_long = eng.pack_vec(predictor.pos.pe[:n].contiguous())
+        pp.pe_long_rows = n
+    return pp.pe_long
+
+
 class CrossPredictor(_Top):
-    """:362-407.  Standalone ``forward(zt_prev, za)`` handles one chunk of <= 16 tokens."""
+    """:362-407.  ``forward(zt_prev, za)``: chunks of <= 16 tokens run the codec path's chunk-local attention kernel,
+    longer sequences (the PLC scripts call it once over the whole file, PLC/PLC1_eval.py:500) the full-length one."""
 
     def __init__(self, c, heads=8, mlp_mul=2, dropout=0.1):
         super().__init__()
@@ -393,14 +416,23 @@ class CrossPredictor(_Top):
         if zt_prev.shape != za.shape or zt_prev.dim() != 3:
             raise ValueError("CrossPredictor expects two [B, C, Tc] tensors of the same shape")
         B, c, Tc = zt_prev.shape
-        if Tc > 16:
-            raise L.B2CError("CrossPredictor: chunks longer than 16 tokens (the PLC full-length use) are not built yet")
+        if B == 0 or Tc == 0:
+            raise ValueError("CrossPredictor: empty input")
         eng, pp = self._engine(zt_prev.device)
         prec = self._prec("pred")
         a, k = _as_f32(zt_prev), _as_f32(za)
         out = torch.empty(B, c, Tc, device=za.device, dtype=torch.float32)
         key = ("pred", id(pp), B, Tc, prec)
         prog = eng.programs.get(key)
+        if prog is None and Tc > 16:
+            em = Emitter(eng)
+            N = B * Tc
+            zp, zk = em.new(N * c), em.new(N * c)
+            em.transpose(em.ext(1), zp, B, c, Tc)
+            em.transpose(em.ext(2), zk, B, c, Tc)
+            zpred = emit_predict_full(em, pp, zp, None, zk, B, Tc, pe_table(eng, pp, self, Tc), prec)
+            em.transpose(zpred, em.ext(3), B, Tc, c)
+            prog = eng.programs[key] = em.finish(3)
         if prog is None:
             em = Emitter(eng)
             N = B * Tc
@@ -443,6 +475,45 @@ class ResidualVQEMA(_Top):
 
     def _pack(self, eng):
         return eng.pack_books(list(self.books))
+
+    #: EMA_DECAY of the training scripts (Training/compare_dacvsproposal_3.py:62, constructor argument `decay`)
+    decay = 0.99
+
+    @torch.no_grad()
+    def ema_step(self, z_tokens):
+        """ResidualVQEMA.ema_step (Training/compare_dacvsproposal_3.py:264-276): for EVERY book (the same tokens X,
+        no residual update between books) idx = nearest code, then the rows of the codes that were hit move towards
+        the mean of their tokens: emb[k] = decay*emb[k] + (1-decay)*mean.  In place on ``books[i].data``; the packed
+        copy the CUDA programs read is refreshed in the same stream.  ``last_ema_counts`` [n_books, K] = the bincounts."""
+        _require_cuda(z_tokens)
+        B, D, T = z_tokens.shape
+        if B * T == 0:
+            return
+        K = self.books[0].shape[0]
+        if any(b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous() for b in self.books):
+            raise L.B2CError("ema_step: the codebooks must be contiguous fp32 CUDA parameters")
+        eng, wid = self._engine(z_tokens.device)
+        N = B * T
+        x = _as_f32(z_tokens)
+        prec = L.PREC_BF16X3 if eng.lib.b2c_nearest_tc_eligible(N, D, K) else L.PREC_F32
+        key = ("ema", wid, B, T, prec)
+        prog = eng.programs.get(key)
+        if prog is None:
+            em = Emitter(eng)
+            xr = em.new(N * D)
+            em.transpose(em.ext(1), xr, B, D, T)
+            scratch = em.arena.alloc(int(eng.lib.b2c_nearest_scratch_bytes(N, D, K, prec)))
+            ii = em.new(N)
+            em.nearest(xr, em.ext(2), scratch, ii, N, D, K, prec)
+            em.ema_update(xr, ii, em.ext(2), em.ext(3), N, D, K, float(self.decay), float(1.0 - self.decay))
+            prog = eng.programs[key] = em.finish(3)
+        counts = torch.empty(len(self.books), K, device=z_tokens.device, dtype=torch.int32)
+        stream = torch.cuda.current_stream(z_tokens.device).cuda_stream
+        for i, book in enumerate(self.books):
+            eng.run(prog, [x.data_ptr(), book.data_ptr(), counts[i].data_ptr()])
+            L.check(eng.lib.b2c_codebooks_refresh(eng.ctx, wid, i, C.c_void_p(book.data_ptr()), C.c_void_p(stream)),
+                    "b2c_codebooks_refresh")
+        self.last_ema_counts = counts      # (raw-pointer writes move no version counter; the packed copy is in sync)
 
     @torch.no_grad()
     def forward(self, z, n_books_use=None, return_indices=False):
@@ -500,11 +571,8 @@ class ProposedEval(_Top):
         self.last_audio_codes = None
         # the sub-modules run on this model's engine when called on their own (encode_latents + T_DEC(z), the
         # reference's latency loop :511-521): one set of packed weights per model
-        me = weakref.ref(self)
-        for name, pick in (("A_ENC", lambda pk: pk["a_enc"]), ("T_ENC", lambda pk: pk["t_enc"]),
-                           ("T_DEC", lambda pk: pk["t_dec"]), ("A_QUANT", lambda pk: pk["a_q"]),
-                           ("predict", lambda pk: pk["pp"]), ("vq", lambda pk: pk["pp"].books)):
-            getattr(self, name).__dict__["_b2c_owner"] = (me, (name, pick))
+        self._adopt(A_ENC=lambda pk: pk["a_enc"], T_ENC=lambda pk: pk["t_enc"], T_DEC=lambda pk: pk["t_dec"],
+                    A_QUANT=lambda pk: pk["a_q"], predict=lambda pk: pk["pp"], vq=lambda pk: pk["pp"].books)
         #: replay the per-shape program as a CUDA graph (one graph launch instead of ~125 kernel launches):
         #: what the batch-1 streaming path (measure_proposed_latency, :489-525) wants
         self.use_cuda_graph = False

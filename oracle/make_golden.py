@@ -78,6 +78,39 @@ def main():
         )
         print("wrote", name, "y", tuple(y.shape), "idx", tuple(idx.shape))
 
+    if only and "plc" not in only and "ema" not in only:
+        return
+    # ---- packet-loss concealment: the reference's AllPredPLC (PLC/PLC1_eval.py) with a seeded token mask ----
+    if not only or "plc" in only:
+        from oracle import plc
+        pns = ref_loader.load_reference_classes(ref_loader.PLC_SCRIPT, ref_loader.PLC_WANTED)
+        model = plc.build_plc_model(pns["AllPredPLC"])
+        for name, case in plc.PLC_CASES.items():
+            a, t = codec_inputs(case)
+            tl = a.shape[-1] // dac_arch.HOP
+            mask = plc.plc_mask(case, tl)
+            # the reference draws the mask inside forward_step (torch.rand on the default generator): hand it ours
+            pns["make_token_loss_mask"] = lambda batch_size, T_lat, packet_tok, p_loss, device, _m=mask: _m
+            with torch.no_grad():
+                out = model.forward_step(a, t)
+            assert torch.equal(out["latent_mask"][:, 0], mask)
+            np.savez_compressed(os.path.join(OUT, f"plc_{name}.npz"), y_hat=out["y_hat"].numpy(), mask=mask.numpy(),
+                                fingerprint=weights_fingerprint(model))
+            print("wrote plc", name, tuple(out["y_hat"].shape), int(mask.sum()), "of", mask.numel(), "tokens masked")
+    # ---- ResidualVQEMA.ema_step of Training/compare_dacvsproposal_3.py ----
+    if not only or "ema" in only:
+        tns = ref_loader.load_reference_classes(ref_loader.TRAIN_SCRIPT, ref_loader.TRAIN_WANTED)
+        torch.manual_seed(7)
+        vq = tns["ResidualVQEMA"](dim=96, n_books=4, n_embed=128, decay=0.99)
+        z = 0.3 * torch.randn(3, 96, 75, generator=torch.Generator().manual_seed(123))
+        blobs = dict(n_books=4, decay=0.99, z_tokens=z.numpy())
+        for i, b in enumerate(vq.books):
+            blobs[f"book{i}_before"] = b.detach().clone().numpy()
+        vq.ema_step(z)
+        for i, b in enumerate(vq.books):
+            blobs[f"book{i}_after"] = b.detach().clone().numpy()
+        np.savez_compressed(os.path.join(OUT, "ema_step.npz"), **blobs)
+        print("wrote ema_step")
     if only:
         return
     # ---- module-level: reference CrossPredictor + ResidualVQEMA on seeded tensors ----

@@ -142,6 +142,31 @@ class ResidualVQEMA(nn.Module):
         return q_sum.view(b, t, d).permute(0, 2, 1).contiguous()
 
 
+def ema_step(books, z_tokens: torch.Tensor, decay: float) -> list:
+    """ResidualVQEMA.ema_step (Training/compare_dacvsproposal_3.py:264-276), in place on ``books`` (a list of [K, D]
+    tensors or parameters).  Every book sees the SAME tokens X (no residual update between books).  Returns the
+    per-book nearest-code indices and score margins (oracle-side additions for the parity tests)."""
+    b, d, t = z_tokens.shape
+    x = z_tokens.permute(0, 2, 1).reshape(b * t, d)
+    info = []
+    with torch.no_grad():
+        for cb in books:
+            emb = cb.data
+            sc = x.to(emb) @ emb.t() - 0.5 * (emb * emb).sum(dim=1).unsqueeze(0)       # :269
+            idx = sc.argmax(dim=1)
+            top2 = sc.topk(2, dim=1).values
+            k = emb.size(0)
+            counts = torch.bincount(idx, minlength=k).float().unsqueeze(1)            # :271
+            sums = torch.zeros_like(emb)
+            sums.index_add_(0, idx, x.to(emb))                                        # :272
+            mask = counts.squeeze(1) > 0
+            means = torch.zeros_like(emb)
+            means[mask] = sums[mask] / (counts[mask] + 1e-9)                          # :274
+            emb[mask] = decay * emb[mask] + (1.0 - decay) * means[mask]              # :275
+            info.append(dict(idx=idx, margin=top2[:, 0] - top2[:, 1], counts=counts.squeeze(1).long()))
+    return info
+
+
 class ProposedEval(nn.Module):
     """:437-487 (training twin: Training/compare_dacvsproposal_3.py:300-340)."""
 
@@ -202,6 +227,31 @@ class ProposedEval(nn.Module):
         if trace is not None:
             trace["y"] = y
         return y
+
+    # ---- receiver: the reference never decodes from indices; this is its loop with the lookup in place of the search ----
+    @torch.no_grad()
+    def decode_from_indices(self, a_1T, idx, books_use=None):
+        """What a receiver holding the audio frame and the code indices [B, books, Tl] computes: the chunk loop of
+        encode_latents (:462-477) with qD = sum over books of book[idx] (plain sums in book order) in place of the
+        residual search, then T_DEC (:486).  Oracle for ProposedEval.decode_indices of the CUDA path."""
+        za = self.A_ENC(a_1T)
+        qa = self.A_QUANT(za)[0]
+        b, c, tl = qa.shape
+        use = idx.shape[1] if books_use is None else min(books_use, idx.shape[1])
+        z_run = torch.zeros_like(qa)
+        for s in range(0, tl, AR_CHUNK_TOK):
+            e = min(tl, s + AR_CHUNK_TOK)
+            zt_prev = torch.zeros(b, c, e - s, dtype=qa.dtype)
+            if s == 0:
+                zt_prev[..., 1:] = z_run[..., s:e - 1]
+            else:
+                zt_prev[...] = z_run[..., s - 1:e - 1]
+            z_pred = self.predict(zt_prev, qa[..., s:e])
+            qd = torch.zeros(b, CODE_DIM, e - s, dtype=qa.dtype)
+            for k in range(use):
+                qd = qd + F.embedding(idx[:, k, s:e], self.vq.books[k].detach()).permute(0, 2, 1)
+            z_run[..., s:e] = self.proj_up(qd) + z_pred
+        return self.T_DEC(z_run), z_run
 
     # ---- the two-pass schedule the CUDA path uses (SURVEY.md section 3.2) ----
     @torch.no_grad()

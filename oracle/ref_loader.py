@@ -22,11 +22,19 @@ def available() -> bool:
     return os.path.isfile(REF_SCRIPT)
 
 
-def load_reference_classes(path: str = REF_SCRIPT) -> dict:
+PLC_SCRIPT = os.path.join(REF_ROOT, "PLC", "PLC1_eval.py")
+PLC_WANTED = ("PACKET_TOK", "PACKET_LOSS_PROB", "finite_or_zero", "PosEnc1D", "TokenNorm", "CrossPredictor",
+              "make_token_loss_mask", "AllPredPLC")
+TRAIN_SCRIPT = os.path.join(REF_ROOT, "Training", "compare_dacvsproposal_3.py")
+TRAIN_WANTED = ("CODE_DIM", "RVQ_N_BOOKS", "RVQ_EMBED", "EMA_DECAY", "AR_CHUNK_TOK", "ResidualVQEMA")
+
+
+def load_reference_classes(path: str = REF_SCRIPT, wanted=None) -> dict:
     import torch
     import torch.nn as nn
     import torch.nn.functional as F
 
+    WANTED = globals()["WANTED"] if wanted is None else wanted
     with open(path, "r") as fh:
         tree = ast.parse(fh.read(), filename=path)
     ns = {"math": math, "torch": torch, "nn": nn, "F": F}

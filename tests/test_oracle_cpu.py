@@ -157,3 +157,61 @@ def test_near_tie_rule_of_the_parity_suite():
     bad = got.clone(); bad[0, 0, 20] = 3          # a real mismatch is never waived
     with pytest.raises(AssertionError):
         check_against_oracle(bad, torch.zeros(1, 2, 40, dtype=torch.long), tr, 1e-5, 1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_plc_restatement_equals_reference_classes():
+    """oracle/plc.py against the reference's own AllPredPLC (PLC/PLC1_eval.py, ast-extracted): same weights, same
+    frame, same token mask (drawn by the reference's make_token_loss_mask under a seed) -> bit-equal output."""
+    from oracle import plc
+    ns = ref_loader.load_reference_classes(ref_loader.PLC_SCRIPT, ref_loader.PLC_WANTED)
+    ns["DEVICE"] = "cpu"
+    ref = plc.build_plc_model(ns["AllPredPLC"])
+    mine = plc.build_plc_model()
+    assert list(ref.state_dict()) == list(mine.state_dict())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, mine.state_dict()[k]), k
+    case = dict(B=1, T=9600, kind="uniform")
+    a, t = cases.codec_inputs(case)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        out_ref = ref.forward_step(a, t)
+    mask = out_ref["latent_mask"][:, 0]
+    assert mask.any() and not mask.all()
+    torch.manual_seed(5)
+    assert torch.equal(plc.make_token_loss_mask(1, 30, plc.PACKET_TOK, plc.PACKET_LOSS_PROB), mask)
+    out = mine.forward_step(a, t, mask_tokens=mask)
+    assert torch.equal(out["y_hat"], out_ref["y_hat"]) and torch.equal(out["tgt"], out_ref["tgt"])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_ema_step_restatement_equals_reference_class():
+    """oracle.proposed.ema_step against ResidualVQEMA.ema_step of Training/compare_dacvsproposal_3.py:264-276."""
+    ns = ref_loader.load_reference_classes(ref_loader.TRAIN_SCRIPT, ref_loader.TRAIN_WANTED)
+    torch.manual_seed(3)
+    vq = ns["ResidualVQEMA"](dim=96, n_books=3, n_embed=64, decay=0.99)
+    books = [b.detach().clone() for b in vq.books]
+    z = 0.3 * torch.randn(2, 96, 40, generator=torch.Generator().manual_seed(4))
+    vq.ema_step(z)
+    info = proposed.ema_step(books, z, 0.99)
+    for b_ref, b in zip(vq.books, books):
+        assert torch.equal(b_ref.data, b)
+    assert int(info[0]["counts"].sum()) == 80
+
+
+def test_plc_and_ema_goldens():
+    """The committed fixtures (made by the reference's classes, oracle/make_golden.py) against the restatements."""
+    from oracle import plc
+    model = plc.build_plc_model()
+    for name, case in plc.PLC_CASES.items():
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"plc_{name}.npz"))
+        a, t = cases.codec_inputs(case)
+        mask = torch.from_numpy(g["mask"])
+        assert torch.equal(plc.plc_mask(case, mask.shape[1]), mask)
+        out = model.forward_step(a, t, mask_tokens=mask)
+        assert torch.equal(out["y_hat"], torch.from_numpy(g["y_hat"])), name
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ema_step.npz"))
+    books = [torch.from_numpy(g[f"book{i}_before"]).clone() for i in range(int(g["n_books"]))]
+    proposed.ema_step(books, torch.from_numpy(g["z_tokens"]), float(g["decay"]))
+    for i, b in enumerate(books):
+        assert torch.equal(b, torch.from_numpy(g[f"book{i}_after"])), i
