@@ -175,9 +175,16 @@ int b2c_prog_ema_update(b2c_prog* p, b2c_ref x, b2c_ref idx, b2c_ref emb, b2c_re
 int b2c_prog_attention(b2c_prog* p, b2c_ref q, int q_mode, b2c_ref kv, b2c_ref out, int B, int Tl, int chunk,
                        int heads, int dh);
 /* ResidualVQEMA.forward (:421-435) on rows x [N, D]; qsum [N, D]; idx int32 laid out [B, books_use, Tl]
- * (row_mode DENSE: n = b*Tl + t; HEAD: n = (b, j) -> t = chunk*(j+1)). */
-int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N, int row_mode,
-                 int B, int Tl, int chunk);
+ * (row_mode DENSE: n = b*Tl + t; HEAD: n = (b, j) -> t = chunk*(j+1)).
+ *   precision B2C_PREC_F32: FP32 CUDA-core kernels (FFMA scores, first maximum).  BF16X3 / BF16: ONE tcgen05 launch
+ *   for all books (rvq_tc_kernel: bf16x3 score GEMM per book with the scores in TMEM, arg-max + codeword gather +
+ *   q_sum / residual update in the epilogue, candidates within the contraction's error bound re-scored with the FP32
+ *   kernels' arithmetic) for D in {32, 64, 96, 128}, K a multiple of 64 up to 512; other shapes run the FP32
+ *   kernels -- the indices and q_sum are the same bits either way.
+ *   scratch: b2c_rvq_scratch_bytes(N, D) bytes of workspace (used by the small-batch FP32 kernels). */
+size_t b2c_rvq_scratch_bytes(int N, int D);
+int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, b2c_ref scratch, int N,
+                 int row_mode, int B, int Tl, int chunk, int precision);
 /* Receiver side of ResidualVQEMA.forward (:421-435): the code indices are an INPUT (int32, the layout b2c_prog_rvq
  * writes), qsum[n] = sum over the first books_use books of book[idx] (plain fp32 adds in book order).  Not in the
  * reference, which never decodes from indices; it is what "indices out, reconstruction in" needs. */

@@ -84,7 +84,8 @@ SIGNATURES = {
     "b2c_codebooks_refresh": (_i, [C.c_void_p, _i, _i, C.c_void_p, C.c_void_p]),
     "b2c_prog_convert": (_i, [C.c_void_p, _ref, _i, _ref, _i, C.c_size_t]),
     "b2c_prog_attention": (_i, [C.c_void_p, _ref, _i, _ref, _ref, _i, _i, _i, _i, _i]),
-    "b2c_prog_rvq": (_i, [C.c_void_p, _i, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i]),
+    "b2c_rvq_scratch_bytes": (C.c_size_t, [_i, _i]),
+    "b2c_prog_rvq": (_i, [C.c_void_p, _i, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i]),
     "b2c_prog_rvq_lookup": (_i, [C.c_void_p, _i, _i, _ref, _ref, _i, _i, _i, _i, _i]),
     "b2c_nearest_scratch_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "b2c_nearest_tc_eligible": (_i, [_i, _i, _i]),

@@ -14,6 +14,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_ru.cuh"
 #include "kernels_ext.cuh"
+#include "kernels_rvq.cuh"
 
 using namespace b2c;
 
@@ -79,6 +80,8 @@ struct Weight {
   float* bias = nullptr;      // conv bias or null
   float* aux = nullptr;       // codebooks: half norms
   TcWeight tc;                // bf16 hi/lo operand planes for the tcgen05 path (lazily absent)
+  TcBooks tcb;                // codebooks: bf16 hi/lo planes of every book + max |e|^2 per book (tcgen05 residual VQ)
+  float* emax2 = nullptr;     // device copy of tcb.emax2 [n_books]
   size_t n = 0;
   int cout = 0, cin = 0, k = 0, transposed = 0, stride = 1, padding = 0;
   int n_phase = 1, kt = 0;
@@ -138,6 +141,9 @@ extern "C" int b2c_ctx_destroy(b2c_ctx* ctx) {
     if (w.dev) cudaFree(w.dev);
     if (w.bias) cudaFree(w.bias);
     if (w.aux) cudaFree(w.aux);
+    if (w.tcb.hi) cudaFree(w.tcb.hi);
+    if (w.tcb.lo) cudaFree(w.tcb.lo);
+    if (w.emax2) cudaFree(w.emax2);
     tc_weight_free(w.tc);
   }
   delete ctx;
@@ -248,8 +254,38 @@ extern "C" int b2c_pack_codebooks(b2c_ctx* ctx, const float* const* books, int n
   if (rc) return rc;
   rc = upload(ctx, hn.data(), hn.size(), &w.aux);
   if (rc) return rc;
+  {  // bf16 hi / lo planes (K-major) and max |e|^2 per book for the tcgen05 residual VQ
+    std::vector<__nv_bfloat16> hi(all.size()), lo(all.size());
+    std::vector<float> emax((size_t)n_books, 0.f);
+    for (size_t i = 0; i < all.size(); ++i) {
+      hi[i] = __float2bfloat16_rn(all[i]);
+      lo[i] = __float2bfloat16_rn(all[i] - __bfloat162float(hi[i]));
+    }
+    for (int b = 0; b < n_books; ++b)
+      for (int k = 0; k < K; ++k) emax[b] = fmaxf(emax[b], 2.0f * hn[(size_t)b * K + k] * 1.0001f);
+    CUDA_TRY(cudaMalloc((void**)&w.tcb.hi, all.size() * 2));
+    CUDA_TRY(cudaMalloc((void**)&w.tcb.lo, all.size() * 2));
+    CUDA_TRY(cudaMemcpy(w.tcb.hi, hi.data(), all.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w.tcb.lo, lo.data(), all.size() * 2, cudaMemcpyHostToDevice));
+    rc = upload(ctx, emax.data(), emax.size(), &w.emax2);
+    if (rc) return rc;
+    ctx->bytes += all.size() * 4;
+    w.tcb.n_books = n_books; w.tcb.K = K; w.tcb.D = D;
+  }
   ctx->w.push_back(w);
   return (int)ctx->w.size() - 1;
+}
+
+// after an in-place codebook change: bf16 planes of one book and max |e|^2 (ordered-int atomicMax; values >= 0)
+static __global__ void book_planes_f32(const float* __restrict__ emb, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                       const float* __restrict__ half_n, float* __restrict__ emax2, int K, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * D) {
+    __nv_bfloat16 h, l;
+    split_bf16(emb[i], h, l);
+    hi[i] = h; lo[i] = l;
+  }
+  if (i < K) atomicMax(reinterpret_cast<int*>(emax2), __float_as_int(2.0f * half_n[i] * 1.0001f));
 }
 
 // 0.5 * |e_k|^2 with the arithmetic of b2c_pack_codebooks (separate multiply and add, ascending d)
@@ -271,6 +307,12 @@ extern "C" int b2c_codebooks_refresh(b2c_ctx* ctx, int wid, int book, const floa
   float* dst = w.dev + (size_t)book * w.K * w.D;
   CUDA_TRY(cudaMemcpyAsync(dst, dev_book, (size_t)w.K * w.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   half_sqnorm_seq_f32<<<(w.K + 127) / 128, 128, 0, st>>>(dst, w.aux + (size_t)book * w.K, w.K, w.D);
+  if (w.tcb.hi) {
+    CUDA_TRY(cudaMemsetAsync(w.emax2 + book, 0, sizeof(float), st));
+    const size_t off = (size_t)book * w.K * w.D;
+    book_planes_f32<<<(w.K * w.D + 255) / 256, 256, 0, st>>>(dst, w.tcb.hi + off, w.tcb.lo + off, w.aux + (size_t)book * w.K,
+                                                             w.emax2 + book, w.K, w.D);
+  }
   CUDA_TRY(cudaPeekAtLastError());
   return B2C_OK;
 }
@@ -342,7 +384,8 @@ struct Op {
   DacRvqArgs dac;
   TcConvPlan tc;
   TcRuPlan ru;
-  void* scratch = nullptr;   // device memory owned by the op (split residual VQ: residual rows + arg-max keys)
+  RvqTcPlan rvq_tc;
+  bool use_rvq_tc = false;
   int i[8] = {0};
   float f[2] = {0.f, 0.f};
   size_t n = 0;
@@ -369,11 +412,6 @@ extern "C" int b2c_prog_create(b2c_ctx* ctx, b2c_prog** out) {
   return B2C_OK;
 }
 extern "C" int b2c_prog_destroy(b2c_prog* p) {
-  if (p) {
-    DeviceGuard guard__(p->ctx->device);
-    for (auto& op : p->ops)
-      if (op.scratch) cudaFree(op.scratch);
-  }
   delete p;
   return B2C_OK;
 }
@@ -393,8 +431,9 @@ extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   if (!p) return 0;
   int n = 0;
   for (const auto& op : p->ops) {
-    if (rvq_one_launch(p->ctx, op)) n += 1;
-    else if (op.type == OP_RVQ && op.scratch && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
+    if (op.type == OP_RVQ && op.use_rvq_tc) n += 1;
+    else if (rvq_one_launch(p->ctx, op)) n += 1;
+    else if (op.type == OP_RVQ && op.r[3] != B2C_NULL_REF && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
     else if (op.type == OP_NEAREST) {
       if (op.precision == B2C_PREC_F32) n += 2;                       // half norms, scores
       else {
@@ -682,32 +721,37 @@ extern "C" int b2c_prog_ema_update(b2c_prog* p, b2c_ref x, b2c_ref idx, b2c_ref 
   return B2C_OK;
 }
 
-extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, int N,
-                            int row_mode, int B, int Tl, int chunk) {
+extern "C" size_t b2c_rvq_scratch_bytes(int N, int D) {
+  if (N <= 0 || D <= 0) return 0;
+  // split residual VQ (FP32 kernels, small batches): residual [N, D] fp32 + one 64-bit arg-max key per row
+  return ((size_t)N * D * 4 + 255) / 256 * 256 + (size_t)N * 8;
+}
+
+extern "C" int b2c_prog_rvq(b2c_prog* p, int books_wid, int books_use, b2c_ref x, b2c_ref qsum, b2c_ref idx, b2c_ref scratch,
+                            int N, int row_mode, int B, int Tl, int chunk, int precision) {
   if (!p) return fail(B2C_ERR_ARG, "b2c_prog_rvq: NULL program");
   const Weight* w = get_w(p, books_wid, W_BOOKS, "b2c_prog_rvq");
   if (!w) return B2C_ERR_ARG;
   if (books_use < 0 || books_use > w->n_books) return fail(B2C_ERR_ARG, "b2c_prog_rvq: books_use %d of %d", books_use, w->n_books);
   if (N <= 0) return fail(B2C_ERR_ARG, "b2c_prog_rvq: empty");
   if (w->D > 256) return fail(B2C_ERR_UNSUPPORTED, "b2c_prog_rvq: code dim %d > 256", w->D);
+  if (precision < 0 || precision > B2C_PREC_BF16) return fail(B2C_ERR_ARG, "b2c_prog_rvq: bad precision %d", precision);
   Op op;
   op.type = OP_RVQ;
   blank_refs(op);
-  op.r[0] = x; op.r[1] = qsum; op.r[2] = idx;
+  op.r[0] = x; op.r[1] = qsum; op.r[2] = idx; op.r[3] = scratch;
   op.wid = books_wid;
+  op.precision = precision;
   RvqArgs& r = op.rvq;
   memset(&r, 0, sizeof(r));
   r.N = N; r.D = w->D; r.K = w->K; r.books_use = books_use; r.row_mode = row_mode; r.B = B; r.Tl = Tl > 0 ? Tl : 1;
   r.chunk = chunk > 0 ? chunk : 1;
   r.nfix = nfix_of(r.Tl, r.chunk) > 0 ? nfix_of(r.Tl, r.chunk) : 1;
   r.idx_flat = 0;
-  if (books_use > 0) {
-    // split residual VQ: residual [N, D] fp32 + one 64-bit arg-max key per row
-    DEVICE_GUARD(p->ctx->device);
-    const size_t bytes = ((size_t)N * w->D * 4 + 255) / 256 * 256 + (size_t)N * 8;
-    CUDA_TRY(cudaMalloc(&op.scratch, bytes));
-    CUDA_TRY(cudaMemset(op.scratch, 0, bytes));
-  }
+  // tensor-core precisions: the one-launch tcgen05 kernel when the shape is in its range; its indices are the FP32
+  // kernels' bit for bit (exact re-score of every candidate), so falling back to them changes time, not results
+  if (precision != B2C_PREC_F32 && books_use > 0 && qsum != B2C_NULL_REF && w->tcb.hi)
+    op.use_rvq_tc = rvq_tc_plan(N, w->D, w->K, w->n_books, books_use, &op.rvq_tc) == 0;
   p->ops.push_back(op);
   return B2C_OK;
 }
@@ -1054,18 +1098,30 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
           const char* e = getenv("B2C_RVQ_SPLIT");
           rvq_split = (e && e[0] == '0') ? 0 : 1;
         }
-        if (r.qsum && rvq_one_launch(ctx, op)) {
+        if (op.type == OP_RVQ && op.use_rvq_tc) {
+          const Weight& w = ctx->w[op.wid];
+          RvqTcParams ra;
+          memset(&ra, 0, sizeof(ra));
+          ra.x = r.x; ra.books = r.books; ra.half_n = r.half_n; ra.qsum = r.qsum; ra.idx = r.idx;
+          ra.row_mode = r.row_mode; ra.B = r.B; ra.Tl = r.Tl; ra.chunk = r.chunk; ra.nfix = r.nfix; ra.idx_flat = r.idx_flat;
+          ra.emax2 = w.emax2;
+          int rc = rvq_tc_launch(op.rvq_tc, ra, w.tcb, st);
+          if (rc) return fail(B2C_ERR_CUDA, "op %zu (residual VQ, tcgen05): launch failed (%d)", oi, rc);
+        } else if (r.qsum && rvq_one_launch(ctx, op)) {
           // enough 32-token blocks to occupy the GPU: one launch for all books.  (16-token CTAs, two per SM, measured
           // slower: 0.37 vs 0.28 ms at 4800 tokens -- the code tiles are then streamed twice as often.)
           const size_t sm = ((size_t)32 * r.D + (size_t)2 * 128 * (r.D + 4)) * sizeof(float);
           cudaError_t e = cudaFuncSetAttribute(rvq_books_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
           if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
           rvq_books_f32<4><<<(r.N + 31) / 32, 256, sm, st>>>(r);
-        } else if (r.books_use > 0 && op.type == OP_RVQ && op.scratch && rvq_split && r.qsum) {
+        } else if (r.books_use > 0 && op.type == OP_RVQ && op.r[3] != B2C_NULL_REF && rvq_split && r.qsum) {
           // per book: scores over (token block x code slice) CTAs with an atomic arg-max, then apply
-          float* resid = reinterpret_cast<float*>(op.scratch);
-          unsigned long long* keys = reinterpret_cast<unsigned long long*>(
-              reinterpret_cast<char*>(op.scratch) + ((size_t)r.N * r.D * 4 + 255) / 256 * 256);
+          char* scratch = R.get<char>(op.r[3]);
+          if (R.bad || !scratch) return fail(B2C_ERR_WORKSPACE, "op %zu (rvq): unresolved scratch", oi);
+          float* resid = reinterpret_cast<float*>(scratch);
+          unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch + ((size_t)r.N * r.D * 4 + 255) / 256 * 256);
+          cudaError_t me = cudaMemsetAsync(keys, 0, (size_t)r.N * 8, st);      // the scratch is arena memory: keys start empty
+          if (me != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq keys: %s", cudaGetErrorString(me));
           // 128-code slices (4 codes per lane) once the token blocks alone fill the GPU, else 64-code slices (more CTAs)
           const bool wide_codes = (long)((r.N + 31) / 32) * ((r.K + 127) / 128) >= 2L * ctx->sm_count;
           const int ch = wide_codes ? 128 : 64;

@@ -31,7 +31,7 @@ struct RvqTcParams {
   int row_mode, B, Tl, chunk, nfix, idx_flat;
   int BK, n_kblk, BN, n_ntiles, stages, tmem_cols;
   uint32_t a_blk_bytes, a_plane_bytes, b_blk_bytes, b_plane_bytes, b_stage_bytes, sbo, layout_type;
-  float emax2[RVQ_TC_MAX_BOOKS];   // max_k |e_k|^2 per book (error bound of the tensor-core scores)
+  const float* emax2;     // [n_books] device: max_k |e_k|^2 per book (error bound of the tensor-core scores)
 };
 
 // row `r`, elements [c0, c0 + 8) of a [128 x D] operand tile -> its 16-byte unit in the swizzled K-major layout
@@ -183,7 +183,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       }
       // error bound of a bf16x3 score: 3 * 2^-16 |x||e| (hi.lo, lo.hi rounding, dropped lo.lo) -- doubled and rounded
       // up to 2^-13 |x| max|e|, the tolerance nearest_finalize_rows uses
-      const float tol = 1.220703125e-4f * sqrtf(xn2 * 1.0001f * p.emax2[bk]) + 1e-30f;
+      const float tol = 1.220703125e-4f * sqrtf(xn2 * 1.0001f * __ldg(p.emax2 + bk)) + 1e-30f;
       const bool amb = live && (best - second < tol);
       if (__any_sync(0xffffffffu, amb)) {
         // ---- pass 2 (rare): every candidate within tol of the maximum, re-scored exactly, first maximum wins
@@ -281,7 +281,6 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
 struct TcBooks {
   __nv_bfloat16* hi = nullptr;   // [n_books * K][D], K-major
   __nv_bfloat16* lo = nullptr;
-  float emax2[RVQ_TC_MAX_BOOKS] = {0};
   int n_books = 0, K = 0, D = 0;
 };
 
@@ -345,7 +344,7 @@ inline int rvq_tc_launch(RvqTcPlan& plan, const RvqTcParams& args, const TcBooks
   RvqTcParams q = plan.q;
   q.x = args.x; q.books = args.books; q.half_n = args.half_n; q.qsum = args.qsum; q.idx = args.idx;
   q.row_mode = args.row_mode; q.B = args.B; q.Tl = args.Tl; q.chunk = args.chunk; q.nfix = args.nfix; q.idx_flat = args.idx_flat;
-  for (int i = 0; i < RVQ_TC_MAX_BOOKS; ++i) q.emax2[i] = tb.emax2[i];
+  q.emax2 = args.emax2;
   if (!plan.ready) {
     cuuint64_t dims[2] = {(cuuint64_t)q.D, (cuuint64_t)tb.n_books * tb.K};
     cuuint64_t str[1] = {(cuuint64_t)q.D * 2};

@@ -431,9 +431,11 @@ class Emitter:
         L.check(self.lib.b2c_prog_attention(self.h, self._r(q), q_mode, self._r(kv), self._r(out), B, Tl, chunk,
                                             heads, dh), "b2c_prog_attention")
 
-    def rvq(self, books_wid, books_use, x, qsum, idx, N, row_mode, B, Tl, chunk):
-        L.check(self.lib.b2c_prog_rvq(self.h, books_wid, books_use, self._r(x), self._r(qsum), self._r(idx), N,
-                                      row_mode, B, Tl, chunk), "b2c_prog_rvq")
+    def rvq(self, books_wid, books_use, x, qsum, idx, N, row_mode, B, Tl, chunk, D, prec=L.PREC_F32):
+        scratch = self.arena.alloc(int(self.lib.b2c_rvq_scratch_bytes(N, D)))
+        L.check(self.lib.b2c_prog_rvq(self.h, books_wid, books_use, self._r(x), self._r(qsum), self._r(idx),
+                                      self._r(scratch), N, row_mode, B, Tl, chunk, prec), "b2c_prog_rvq")
+        self.arena.free(scratch)
 
     def rvq_lookup(self, books_wid, books_use, idx, qsum, N, row_mode, B, Tl, chunk):
         L.check(self.lib.b2c_prog_rvq_lookup(self.h, books_wid, books_use, self._r(idx), self._r(qsum), N, row_mode, B,
@@ -702,7 +704,7 @@ def emit_residual_code(em: Emitter, pp: PackedPredictor, zt, zt_mode, z_pred, N,
     em.conv(pp.down, rn, 1, N, out_raw=rd, prec=prec, x_fmt=f)
     em.drop(rn)
     qd = em.new(N * pp.code_dim)
-    em.rvq(pp.books, books_use, rd, qd, idx, N, row_mode, B, Tl, chunk)
+    em.rvq(pp.books, books_use, rd, qd, idx, N, row_mode, B, Tl, chunk, pp.code_dim, prec)
     em.drop(rd)
     em.conv(pp.up, qd, 1, N, res=z_pred, out_raw=z_hat, prec=prec)
     em.drop(qd)

@@ -527,7 +527,8 @@ class ResidualVQEMA(_Top):
         zin = _as_f32(z)
         out = torch.empty(B, D, T, device=z.device, dtype=torch.float32)
         idx = torch.empty(B, use, T, device=z.device, dtype=torch.int64)
-        key = ("vq", wid, B, T, use)
+        prec = self._prec("pred")
+        key = ("vq", wid, B, T, use, prec)
         prog = eng.programs.get(key)
         if prog is None:
             em = Emitter(eng)
@@ -535,7 +536,7 @@ class ResidualVQEMA(_Top):
             x, q = em.new(N * D), em.new(N * D)
             ii = em.new(max(B * use * T, 1))
             em.transpose(em.ext(1), x, B, D, T)
-            em.rvq(wid, use, x, q, ii, N, L.ROWS_DENSE, B, T, T)
+            em.rvq(wid, use, x, q, ii, N, L.ROWS_DENSE, B, T, T, D, prec)
             em.transpose(q, em.ext(2), B, T, D)
             if use > 0:
                 em.widen(ii, em.ext(3), B * use * T)

@@ -169,3 +169,37 @@ def test_receiver_against_oracle_receiver(plan, dev, oracle_models):
         assert psnr(y, y_ref) > PSNR_MIN[plan]
     # and the receiver's reconstruction is the sender's up to the rounding of q_sum + (q - r) + r  vs  q_sum + q
     assert psnr(y_ref, tr["y"]) > 80.0
+
+
+@pytest.mark.parametrize("D,K,books", [(96, 512, 8), (96, 128, 10), (96, 256, 4), (64, 64, 3), (128, 512, 2), (32, 192, 5)])
+def test_tcgen05_residual_vq_equals_fp32_kernels(D, K, books, dev):
+    """rvq_tc_kernel (all books in one launch, scores in TMEM, arg-max + gather + residual update in the epilogue)
+    against the FP32 CUDA-core kernels: same indices and the same q_sum bits, including rows whose top codes are
+    closer than the tensor-core error bound (duplicated / nearly duplicated codewords force the exact re-score)."""
+    g = torch.Generator().manual_seed(D * 1000 + K + books)
+    vq = pkg.ResidualVQEMA(dim=D, n_books=books, n_embed=K).to(dev)
+    with torch.no_grad():
+        for i, b in enumerate(vq.books):
+            e = torch.randn(K, D, generator=g) / D ** 0.5 * (0.7 ** i)
+            e[K // 2:K // 2 + 8] = e[:8]                                   # exact duplicates: the FIRST must win
+            e[K // 2 + 8:K // 2 + 16] = e[8:16] * (1 + 1e-6)               # near-duplicates: inside the error bound
+            b.copy_(e.to(dev))
+    for B, T in ((1, 1), (1, 75), (3, 100), (64, 75)):
+        z = (torch.randn(B, D, T, generator=g) / D ** 0.5).to(dev)
+        z[:, :, 0] = vq.books[0][3].detach()[None, :]                      # a token sitting exactly on a codeword
+        out = {}
+        for plan in ("f32", "tc"):
+            vq.precision = plan
+            q, idx = vq(z, return_indices=True)
+            out[plan] = (q.clone(), idx.clone())
+        assert torch.equal(out["f32"][1], out["tc"][1]), (D, K, B, T, int((out["f32"][1] != out["tc"][1]).sum()))
+        assert torch.equal(out["f32"][0], out["tc"][0])
+        assert int(out["tc"][1].min()) >= 0 and int(out["tc"][1].max()) < K
+        # prefix property with fewer books
+        vq.precision = "tc"
+        q2, idx2 = vq(z, n_books_use=1, return_indices=True)
+        assert torch.equal(idx2[:, 0], out["tc"][1][:, 0])
+    # the launch count is what the B = 1 latency path cares about: one launch for all books
+    eng, wid = vq._engine(dev)
+    progs = [p for k, p in eng.programs._d.items() if k[0] == "vq" and k[-1] != 0]
+    assert progs and all(p.info["launches"] <= 4 for p in progs), [p.info["launches"] for p in progs]
