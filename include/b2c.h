@@ -251,6 +251,29 @@ int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* workspace, size
                                 int n_ext, const b2c_hostcopy* h2d, int n_h2d, const b2c_hostcopy* d2h, int n_d2h,
                                 int n_micro);
 
+/* ---------------- evaluation metrics of the callers (Evaluation/compare_dacvsproposal_5_eval.py) ----------------
+ * Plain entry points on caller tensors (device fp32 pointers, rows of L samples), enqueued on `stream`, no sync. */
+/* align_pair_24k (:188-211) for B frames: corr [B, 2*max_shift+1] = sum_j ref[j]*est[j+s], s = -max_shift..max_shift,
+ * best_shift int32 [B] = the first s with the strictly largest correlation (the reference's Python loop order). */
+int b2c_metric_xcorr_align(int device, void* stream, const float* ref, const float* est, int B, int L, int max_shift,
+                           float* corr, int* best_shift);
+/* resample_f32 (:91-97) = torchaudio sinc_interp_hann: kern [nw, 2*width+orig] is the polyphase filter bank
+ * (orig, nw = the two rates divided by their gcd), y [B, Lout], Lout = ceil(nw*L/orig). */
+int b2c_metric_resample(int device, void* stream, const float* x, float* y, const float* kern, int B, int L, int Lout,
+                        int orig, int nw, int width);
+/* psnr_batch (:180-185): out[b] = 10 log10(1 / max(mean((ref-est)^2), eps)) over n samples per row. */
+int b2c_metric_psnr(int device, void* stream, const float* ref, const float* est, float* out, int B, int n, float eps);
+/* psnr_3k_aligned_batch (:213-223) in one launch: rows aligned by shifts[b] (NULL: none) as align_pair_24k does,
+ * both resampled on the fly, only the PSNR leaves the kernel. */
+int b2c_metric_psnr_resampled(int device, void* stream, const float* ref, const float* est, const int* shifts, float* out,
+                              const float* kern, int B, int L, int orig, int nw, int width, float eps);
+/* stsim_batch (:166-177) with _mel_mag (:142-163): STFT n_fft 512 / hop 128 / periodic hann / centre + reflect,
+ * |.| clamped at 1e-8, mel_fb [257, n_mels], normalised by the per-signal maximum, per-frame cosine, 0.5*(mean+1).
+ * scratch: b2c_metric_stsim_scratch_bytes(B, L, n_mels) bytes. */
+size_t b2c_metric_stsim_scratch_bytes(int B, int L, int n_mels);
+int b2c_metric_stsim(int device, void* stream, const float* ref, const float* est, const float* mel_fb, float* scratch,
+                     float* out, int B, int L, int n_mels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,13 @@ SIGNATURES = {
                              _i]),
     "b2c_prog_run_host_pipelined": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                                          C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i, _i]),
+    "b2c_metric_xcorr_align": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i, _i, C.c_void_p, C.c_void_p]),
+    "b2c_metric_resample": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i, _i, _i, _i, _i]),
+    "b2c_metric_psnr": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i, C.c_float]),
+    "b2c_metric_psnr_resampled": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i,
+                                       _i, _i, _i, C.c_float]),
+    "b2c_metric_stsim_scratch_bytes": (C.c_size_t, [_i, _i, _i]),
+    "b2c_metric_stsim": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i, _i]),
     "b2c_prog_run_host": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                                C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i]),
 }

@@ -15,6 +15,7 @@
 #include "kernels_ru.cuh"
 #include "kernels_ext.cuh"
 #include "kernels_rvq.cuh"
+#include "kernels_metrics.cuh"
 
 using namespace b2c;
 
@@ -1444,5 +1445,85 @@ extern "C" int b2c_prog_run_host_pipelined(b2c_prog* p, void* stream, void* work
   CUDA_TRY(cudaStreamSynchronize(os));
   CUDA_TRY(cudaStreamSynchronize(xs));
   CUDA_TRY(cudaStreamSynchronize(cs));
+  return B2C_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation metrics of the callers: plain entry points on caller tensors, no program needed
+// ------------------------------------------------------------------------------------------
+extern "C" int b2c_metric_xcorr_align(int device, void* stream, const float* ref, const float* est, int B, int L,
+                                      int max_shift, float* corr, int* best_shift) {
+  if (!ref || !est || !corr || !best_shift || B <= 0 || L <= 0 || max_shift < 0 || B > 65535)
+    return fail(B2C_ERR_ARG, "b2c_metric_xcorr_align: bad argument");
+  DEVICE_GUARD(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_shift = 2 * max_shift + 1;
+  xcorr_shifts_f32<<<dim3((n_shift + XC_SPB - 1) / XC_SPB, B), 256, 0, st>>>(ref, est, corr, L, max_shift);
+  xcorr_pick_first_max<<<(B + 127) / 128, 128, 0, st>>>(corr, best_shift, B, max_shift);
+  CUDA_TRY(cudaPeekAtLastError());
+  return B2C_OK;
+}
+
+static int resample_args_ok(const char* who, int orig, int nw, int width) {
+  if (orig < 1 || nw < 1 || width < 1) return fail(B2C_ERR_ARG, "%s: bad resampling ratio %d -> %d, width %d", who, orig, nw, width);
+  if ((size_t)nw * (2 * width + orig) * sizeof(float) > 96 * 1024)
+    return fail(B2C_ERR_UNSUPPORTED, "%s: filter bank of %d x %d taps exceeds 96 KB of shared memory", who, nw, 2 * width + orig);
+  return B2C_OK;
+}
+
+extern "C" int b2c_metric_resample(int device, void* stream, const float* x, float* y, const float* kern, int B, int L,
+                                   int Lout, int orig, int nw, int width) {
+  if (!x || !y || !kern || B <= 0 || L <= 0 || Lout <= 0 || B > 65535) return fail(B2C_ERR_ARG, "b2c_metric_resample: bad argument");
+  int rc = resample_args_ok("b2c_metric_resample", orig, nw, width);
+  if (rc) return rc;
+  DEVICE_GUARD(device);
+  const size_t sm = (size_t)nw * (2 * width + orig) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(resample_sinc_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  resample_sinc_f32<<<dim3((Lout + 255) / 256, B), 256, sm, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, kern, L, Lout, orig, nw, width);
+  CUDA_TRY(cudaPeekAtLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_metric_psnr(int device, void* stream, const float* ref, const float* est, float* out, int B, int n, float eps) {
+  if (!ref || !est || !out || B <= 0 || n <= 0) return fail(B2C_ERR_ARG, "b2c_metric_psnr: bad argument");
+  DEVICE_GUARD(device);
+  psnr_rows_f32<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ref, est, out, n, eps);
+  CUDA_TRY(cudaPeekAtLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_metric_psnr_resampled(int device, void* stream, const float* ref, const float* est, const int* shifts,
+                                         float* out, const float* kern, int B, int L, int orig, int nw, int width, float eps) {
+  if (!ref || !est || !out || !kern || B <= 0 || L <= 0) return fail(B2C_ERR_ARG, "b2c_metric_psnr_resampled: bad argument");
+  int rc = resample_args_ok("b2c_metric_psnr_resampled", orig, nw, width);
+  if (rc) return rc;
+  DEVICE_GUARD(device);
+  const size_t sm = (size_t)nw * (2 * width + orig) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(psnr_resampled_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  psnr_resampled_f32<<<B, 256, sm, reinterpret_cast<cudaStream_t>(stream)>>>(ref, est, shifts, out, kern, L, orig, nw, width, eps);
+  CUDA_TRY(cudaPeekAtLastError());
+  return B2C_OK;
+}
+
+extern "C" size_t b2c_metric_stsim_scratch_bytes(int B, int L, int n_mels) {
+  if (B <= 0 || L <= 0 || n_mels <= 0) return 0;
+  const size_t frames = (size_t)L / ST_HOP + 1;
+  return ((size_t)B * 2 * frames * n_mels + (size_t)B * 2) * sizeof(float);
+}
+
+extern "C" int b2c_metric_stsim(int device, void* stream, const float* ref, const float* est, const float* mel_fb,
+                                float* scratch, float* out, int B, int L, int n_mels) {
+  if (!ref || !est || !mel_fb || !scratch || !out || B <= 0 || n_mels <= 0 || n_mels > 128 || B > 65535)
+    return fail(B2C_ERR_ARG, "b2c_metric_stsim: bad argument (n_mels <= 128)");
+  if (L <= ST_NFFT / 2) return fail(B2C_ERR_ARG, "b2c_metric_stsim: reflect padding needs more than %d samples (got %d)", ST_NFFT / 2, L);
+  DEVICE_GUARD(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int frames = L / ST_HOP + 1;
+  float* mel = scratch;
+  float* amax = scratch + (size_t)B * 2 * frames * n_mels;
+  CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)B * 2 * sizeof(float), st));
+  stft_mel_pair_f32<<<dim3(frames, B), 256, 0, st>>>(ref, est, mel_fb, mel, amax, L, frames, n_mels);
+  stsim_from_mel_f32<<<B, 256, 0, st>>>(mel, amax, out, frames, n_mels);
+  CUDA_TRY(cudaPeekAtLastError());
   return B2C_OK;
 }

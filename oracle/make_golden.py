@@ -78,8 +78,24 @@ def main():
         )
         print("wrote", name, "y", tuple(y.shape), "idx", tuple(idx.shape))
 
-    if only and "plc" not in only and "ema" not in only:
+    if only and "plc" not in only and "ema" not in only and "metrics" not in only:
         return
+    # ---- evaluation metrics: the reference's own functions (Evaluation/compare_dacvsproposal_5_eval.py) ----
+    if not only or "metrics" in only:
+        from oracle import metrics as om
+        mns = ref_loader.load_reference_metrics()
+        blobs = {}
+        for kind, B in (("shifted", 8), ("plain", 3)):
+            ref, est, lags = om.metric_inputs(B=B, kind=kind)
+            blobs[f"{kind}_lags"] = np.array(lags)
+            blobs[f"{kind}_stsim"] = np.array(mns["stsim_batch"](ref, est))
+            blobs[f"{kind}_psnr"] = np.array(mns["psnr_batch"](ref, est))
+            blobs[f"{kind}_psnr3k"] = np.array(mns["psnr_3k_aligned_batch"](ref, est))
+            blobs[f"{kind}_shift"] = np.array([mns["align_pair_24k"](ref[b:b + 1], est[b:b + 1])[2] for b in range(B)])
+            blobs[f"{kind}_ref3k"] = mns["resample_f32"](ref, 24000, 3000).numpy()
+            blobs[f"{kind}_ref16k_head"] = mns["resample_f32"](ref[:1], 24000, 16000).numpy()[..., :512]
+        np.savez_compressed(os.path.join(OUT, "metrics.npz"), **blobs)
+        print("wrote metrics", {k: v.shape for k, v in blobs.items()})
     # ---- packet-loss concealment: the reference's AllPredPLC (PLC/PLC1_eval.py) with a seeded token mask ----
     if not only or "plc" in only:
         from oracle import plc

@@ -29,7 +29,19 @@ TRAIN_SCRIPT = os.path.join(REF_ROOT, "Training", "compare_dacvsproposal_3.py")
 TRAIN_WANTED = ("CODE_DIM", "RVQ_N_BOOKS", "RVQ_EMBED", "EMA_DECAY", "AR_CHUNK_TOK", "ResidualVQEMA")
 
 
-def load_reference_classes(path: str = REF_SCRIPT, wanted=None) -> dict:
+METRIC_SCRIPT = os.path.join(REF_ROOT, "Evaluation", "compare_dacvsproposal_5_eval.py")
+METRIC_WANTED = ("EVAL_SR", "ORIG_3K", "ALIGN_MAX_SHIFT_SAMPLES", "_MEL_CACHE", "resample_f32", "_mel_mag", "stsim_batch",
+                 "psnr_batch", "align_pair_24k", "psnr_3k_aligned_batch")
+
+
+def load_reference_metrics() -> dict:
+    """The reference's own metric functions (Evaluation/compare_dacvsproposal_5_eval.py:91-97, :139-223); they call
+    torchaudio (Resample, MelScale), which this container has."""
+    import torchaudio
+    return load_reference_classes(METRIC_SCRIPT, METRIC_WANTED, extra_ns={"torchaudio": torchaudio})
+
+
+def load_reference_classes(path: str = REF_SCRIPT, wanted=None, extra_ns=None) -> dict:
     import torch
     import torch.nn as nn
     import torch.nn.functional as F
@@ -38,6 +50,7 @@ def load_reference_classes(path: str = REF_SCRIPT, wanted=None) -> dict:
     with open(path, "r") as fh:
         tree = ast.parse(fh.read(), filename=path)
     ns = {"math": math, "torch": torch, "nn": nn, "F": F}
+    ns.update(extra_ns or {})
     for node in tree.body:
         name = None
         if isinstance(node, (ast.ClassDef, ast.FunctionDef)):

@@ -36,7 +36,8 @@ def test_no_cpu_fallback(lib):
     x = torch.zeros(1, 1, 4800)
     for call in (lambda: net.forward_eval(x, x), lambda: net.A_ENC(x), lambda: net.T_DEC(torch.zeros(1, 1024, 4)),
                  lambda: pkg.nearest_code(torch.zeros(4, 8), torch.zeros(16, 8)),
-                 lambda: net.vq(torch.zeros(1, 96, 4))):
+                 lambda: net.vq(torch.zeros(1, 96, 4)), lambda: pkg.metrics.psnr_batch(x, x),
+                 lambda: pkg.metrics.stsim_batch(x, x), lambda: pkg.metrics.psnr_3k_aligned_batch(x, x)):
         with pytest.raises(pkg.B2CError):
             call()
 

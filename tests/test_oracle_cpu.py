@@ -215,3 +215,55 @@ def test_plc_and_ema_goldens():
     proposed.ema_step(books, torch.from_numpy(g["z_tokens"]), float(g["decay"]))
     for i, b in enumerate(books):
         assert torch.equal(b, torch.from_numpy(g[f"book{i}_after"])), i
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation metrics: oracle/metrics.py against the reference's own functions and their goldens
+# ---------------------------------------------------------------------------------------------
+def _have_torchaudio():
+    try:
+        import torchaudio  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not (ref_loader.available() and _have_torchaudio()), reason="reference tree / torchaudio not here")
+def test_metric_restatement_equals_reference_functions():
+    """Bit-equal: stsim, psnr, aligned 3 kHz PSNR, best shift, both resamplers (torchaudio's tables restated)."""
+    import warnings
+    from oracle import metrics as om
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mns = ref_loader.load_reference_metrics()
+        ref, est, _ = om.metric_inputs(B=3, T=12000, seed=5)
+        assert mns["stsim_batch"](ref, est) == om.stsim_batch(ref, est)
+        assert mns["psnr_batch"](ref, est) == om.psnr_batch(ref, est)
+        assert mns["psnr_3k_aligned_batch"](ref, est) == om.psnr_3k_aligned_batch(ref, est)
+        for b in range(3):
+            ra, ea, s = mns["align_pair_24k"](ref[b:b + 1], est[b:b + 1])
+            rb, eb, s2 = om.align_pair_24k(ref[b:b + 1], est[b:b + 1])
+            assert s == s2 and torch.equal(ra, rb) and torch.equal(ea, eb)
+        for sr in (3000, 16000, 44100):
+            assert torch.equal(mns["resample_f32"](ref, 24000, sr), om.resample_f32(ref, 24000, sr))
+
+
+def test_metric_goldens_and_product_tables(golden_dir):
+    """tests/golden/metrics.npz was written by the reference's functions; the restatement reproduces it, and the
+    constant tables the CUDA path uploads (filter bank of the resampler, mel filters) are the oracle's bit for bit."""
+    from oracle import metrics as om
+    from multimodal_vqvae_compression_audio_tactile_b200 import metrics as pm
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for kind, B in (("shifted", 8), ("plain", 3)):
+        ref, est, lags = om.metric_inputs(B=B, kind=kind)
+        assert list(g[f"{kind}_lags"]) == lags
+        np.testing.assert_array_equal(np.array(om.stsim_batch(ref, est)), g[f"{kind}_stsim"])
+        np.testing.assert_array_equal(np.array(om.psnr_batch(ref, est)), g[f"{kind}_psnr"])
+        np.testing.assert_array_equal(np.array(om.psnr_3k_aligned_batch(ref, est)), g[f"{kind}_psnr3k"])
+        assert list(g[f"{kind}_shift"]) == lags          # the synthetic lag is what the search finds
+        np.testing.assert_array_equal(om.resample_f32(ref, 24000, 3000).numpy(), g[f"{kind}_ref3k"])
+    for a, b in ((24000, 3000), (24000, 16000), (3000, 24000), (24000, 44100)):
+        ko, wo, oo, no = om.sinc_resample_kernel(a, b)
+        kp, wp, op_, np_ = pm.sinc_resample_kernel(a, b)
+        assert (wo, oo, no) == (wp, op_, np_) and torch.equal(ko[:, 0], kp)
+    assert torch.equal(om.mel_filterbank(257, 0.0, 12000.0, 64, 24000), pm.mel_filterbank())
