@@ -38,7 +38,7 @@ typedef struct b2c_ctx b2c_ctx;
 typedef struct b2c_prog b2c_prog;
 typedef uint64_t b2c_ref;
 
-#define B2C_ABI_VERSION 3
+#define B2C_ABI_VERSION 4
 #define B2C_NULL_REF ((b2c_ref)0xFFFFFFFFFFFFFFFFull)
 #define B2C_REF(slot, off) ((((b2c_ref)(slot)) << 56) | (b2c_ref)(off))
 
@@ -147,6 +147,21 @@ int b2c_prog_ru(b2c_prog* p, int wid7, int alpha2_wid, int wid1, b2c_ref x_act, 
                 b2c_ref out_act, int alpha_next_wid, int B, int L, int dilation, int precision, int act_fmt);
 /* dac Decoder head: Conv1d(cin, 1, k=7, p=3) + tanh on x [B, L, cin] -> y [B, L]. */
 int b2c_prog_head(b2c_prog* p, int wid, b2c_ref x, b2c_ref y, int B, int L, int x_fmt);
+/* Backward-data pass of the decoder (Training/compare_dacvsproposal_3.py:386-409 back-propagates the
+ * loss through the frozen T_DEC into predict / proj_*).  One op covers "snake -> conv" of the forward:
+ *   out = conv(x; w) * snake'(pre; alpha) + res,   snake'(v) = 1 + sin(2 alpha v) alpha / (alpha + 1e-9)
+ * x = gradient w.r.t. the forward conv's output (activation format x_fmt), w = that conv's backward-data form packed as
+ * a bias-free Conv1d (Conv1d: channels transposed and taps flipped, padding dil*(k-1) - p; ConvTranspose1d: the same
+ * tensor read as Conv1d [cin, cout, k] with the forward stride and padding), pre = the forward input of the snake
+ * (fp32, shape of the output), res = gradient arriving over the skip connection (optional).  out_raw fp32 and / or
+ * out_act (act_fmt: what the next backward contraction reads). */
+int b2c_prog_conv_dsnake(b2c_prog* p, int wid, b2c_ref x, b2c_ref pre, int alpha_wid, b2c_ref res, b2c_ref out_raw,
+                         b2c_ref out_act, int B, int Lin, int stride, int dilation, int padding, int precision, int x_fmt,
+                         int act_fmt);
+/* Backward-data of the decoder tail snake -> Conv1d(C, 1, 7, p=3) -> tanh: g_y, y [B, L]; x_raw [B, L, C] = the
+ * forward input of the last snake; g_raw fp32 / g_act (act_fmt) [B, L, C] = gradient w.r.t. x_raw. */
+int b2c_prog_head_bwd(b2c_prog* p, int wid, int alpha_wid, b2c_ref g_y, b2c_ref y, b2c_ref x_raw, b2c_ref g_raw,
+                      b2c_ref g_act, int B, int L, int act_fmt);
 /* LayerNorm over C of rows gathered by a_mode from a (minus sub, plus pe row), optional scale*tanh.
  * nn.LayerNorm eps = 1e-5.  (CrossPredictor.ln_q/ln_kv/ffn[0] :394-395,:377; TokenNorm :357-360 with
  * tanh and the clamped scalar, :472-474) */
@@ -211,6 +226,14 @@ int b2c_prog_convert(b2c_prog* p, b2c_ref src, int src_fmt, b2c_ref dst, int dst
 /* widen int32 -> int64 (PyTorch index dtype at the module boundary) */
 int b2c_prog_i32_to_i64(b2c_prog* p, b2c_ref in, b2c_ref out, size_t n);
 
+/* Two launch queues inside one program (batch-1 streaming: the two encoders are independent until the predictor and
+ * neither fills the GPU alone).  Ops added after b2c_prog_set_lane(p, 1) are enqueued on a second stream owned by the
+ * context, forked from the caller's stream at the first of them; after b2c_prog_set_lane(p, 0) on the caller's stream
+ * again; b2c_prog_join makes the caller's stream wait for the second queue (b2c_prog_run joins at the end in any case).
+ * Buffers written on one lane and read on the other must not be touched in between; arithmetic is unaffected. */
+int b2c_prog_set_lane(b2c_prog* p, int lane);
+int b2c_prog_join(b2c_prog* p);
+
 /* Enqueue the program on `stream` (a cudaStream_t).  ext[i] is the device pointer of slot i+1. */
 int b2c_prog_run(b2c_prog* p, void* stream, void* workspace, size_t workspace_bytes, void* const* ext, int n_ext);
 
@@ -269,10 +292,11 @@ int b2c_metric_psnr_resampled(int device, void* stream, const float* ref, const 
                               const float* kern, int B, int L, int orig, int nw, int width, float eps);
 /* stsim_batch (:166-177) with _mel_mag (:142-163): STFT n_fft 512 / hop 128 / periodic hann / centre + reflect,
  * |.| clamped at 1e-8, mel_fb [257, n_mels], normalised by the per-signal maximum, per-frame cosine, 0.5*(mean+1).
+ * mel_range (optional, int32 [n_mels][2]): bins [lo, hi) outside which a band's filter is zero.
  * scratch: b2c_metric_stsim_scratch_bytes(B, L, n_mels) bytes. */
 size_t b2c_metric_stsim_scratch_bytes(int B, int L, int n_mels);
-int b2c_metric_stsim(int device, void* stream, const float* ref, const float* est, const float* mel_fb, float* scratch,
-                     float* out, int B, int L, int n_mels);
+int b2c_metric_stsim(int device, void* stream, const float* ref, const float* est, const float* mel_fb,
+                     const int* mel_range, float* scratch, float* out, int B, int L, int n_mels);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ NULL_REF = 0xFFFFFFFFFFFFFFFF
 ACT_NONE, ACT_SNAKE, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 PREC_F32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 FMT_F32, FMT_BF16X2, FMT_BF16 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 ROWS_DENSE, ROWS_HEAD, ROWS_HEAD_PREV, ROWS_ZERO = 0, 1, 2, 3
 PE_NONE, PE_CHUNK_POS, PE_ROW0, PE_ROW_N = 0, 1, 2, 3
 
@@ -75,6 +75,8 @@ SIGNATURES = {
     "b2c_prog_convT": (_i, [C.c_void_p, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i]),
     "b2c_ru_tc_eligible": (_i, [C.c_void_p, _i, _i, _i]),
     "b2c_prog_ru": (_i, [C.c_void_p, _i, _i, _i, _ref, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i]),
+    "b2c_prog_conv_dsnake": (_i, [C.c_void_p, _i, _ref, _ref, _i, _ref, _ref, _ref, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "b2c_prog_head_bwd": (_i, [C.c_void_p, _i, _i, _ref, _ref, _ref, _ref, _ref, _i, _i, _i]),
     "b2c_prog_head": (_i, [C.c_void_p, _i, _ref, _ref, _i, _i, _i]),
     "b2c_prog_layernorm": (_i, [C.c_void_p, _i, _i, _ref, _i, _ref, _i, _i, _i, C.c_float, _ref, _i, _i, _i, _i, _i]),
     "b2c_prog_layernorm_masked": (_i, [C.c_void_p, _i, _i, _ref, _ref, _i, _i, _ref, _i, _i, _i, _i, _i]),
@@ -94,6 +96,8 @@ SIGNATURES = {
     "b2c_prog_scatter_heads": (_i, [C.c_void_p, _ref, _ref, _i, _i, _i, _i]),
     "b2c_prog_transpose": (_i, [C.c_void_p, _ref, _ref, _i, _i, _i]),
     "b2c_prog_i32_to_i64": (_i, [C.c_void_p, _ref, _ref, C.c_size_t]),
+    "b2c_prog_set_lane": (_i, [C.c_void_p, _i]),
+    "b2c_prog_join": (_i, [C.c_void_p]),
     "b2c_prog_run": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i]),
     "b2c_prog_profile": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                              C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -106,7 +110,8 @@ SIGNATURES = {
     "b2c_metric_psnr_resampled": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i,
                                        _i, _i, _i, C.c_float]),
     "b2c_metric_stsim_scratch_bytes": (C.c_size_t, [_i, _i, _i]),
-    "b2c_metric_stsim": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i, _i]),
+    "b2c_metric_stsim": (_i, [_i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i, _i,
+                              _i]),
     "b2c_prog_run_host": (_i, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), _i,
                                C.POINTER(HostCopy), _i, C.POINTER(HostCopy), _i]),
 }

@@ -101,6 +101,9 @@ struct b2c_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D
   cudaStream_t out_stream = nullptr;    // D2H
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  // second launch queue of two-lane programs (b2c_prog_set_lane): created on first use
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static int upload(b2c_ctx* ctx, const float* host, size_t n, float** dev) {
@@ -133,6 +136,9 @@ extern "C" int b2c_ctx_destroy(b2c_ctx* ctx) {
   DeviceGuard guard__(ctx->device);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+  if (ctx->lane_stream) cudaStreamDestroy(ctx->lane_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -372,7 +378,7 @@ extern "C" int b2c_pack_dac_rvq(b2c_ctx* ctx, int n_q, int c, int d, int K, cons
 // programs
 // ------------------------------------------------------------------------------------------
 enum OpType { OP_STEM, OP_CONV, OP_HEAD, OP_LN, OP_ATTN, OP_RVQ, OP_NEAREST, OP_DACRVQ, OP_SCATTER, OP_TRANSPOSE,
-              OP_WIDEN, OP_CONV_TC, OP_CONVERT, OP_RU_TC, OP_ATTN_FULL, OP_SELECT, OP_EMA };
+              OP_WIDEN, OP_CONV_TC, OP_CONVERT, OP_RU_TC, OP_ATTN_FULL, OP_SELECT, OP_EMA, OP_HEAD_BWD, OP_LANE, OP_JOIN };
 
 struct Op {
   OpType type;
@@ -432,6 +438,7 @@ extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   if (!p) return 0;
   int n = 0;
   for (const auto& op : p->ops) {
+    if (op.type == OP_LANE || op.type == OP_JOIN) continue;   // launch-queue markers
     if (op.type == OP_RVQ && op.use_rvq_tc) n += 1;
     else if (rvq_one_launch(p->ctx, op)) n += 1;
     else if (op.type == OP_RVQ && op.r[3] != B2C_NULL_REF && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
@@ -450,6 +457,28 @@ extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   return n;
 }
 extern "C" int b2c_prog_num_ops(const b2c_prog* p) { return p ? (int)p->ops.size() : 0; }
+
+// Two launch queues inside one program: ops emitted after b2c_prog_set_lane(p, 1) are enqueued on a second stream
+// owned by the context (forked from the caller's stream at the first of them), ops after b2c_prog_set_lane(p, 0) on the
+// caller's stream again; b2c_prog_join makes the caller's stream wait for the second queue.  Used by the batch-1
+// codec program: the two encoders are independent until the predictor and neither fills the GPU alone.
+extern "C" int b2c_prog_set_lane(b2c_prog* p, int lane) {
+  if (!p || lane < 0 || lane > 1) return fail(B2C_ERR_ARG, "b2c_prog_set_lane: lane 0 or 1");
+  Op op;
+  op.type = OP_LANE;
+  for (auto& r : op.r) r = B2C_NULL_REF;
+  op.i[0] = lane;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
+extern "C" int b2c_prog_join(b2c_prog* p) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_join: NULL program");
+  Op op;
+  op.type = OP_JOIN;
+  for (auto& r : op.r) r = B2C_NULL_REF;
+  p->ops.push_back(op);
+  return B2C_OK;
+}
 
 static void blank_refs(Op& op) {
   for (auto& r : op.r) r = B2C_NULL_REF;
@@ -486,11 +515,11 @@ extern "C" int b2c_prog_stem(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, b
 
 static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref res, b2c_ref out_raw, b2c_ref out_act,
                     int act, int alpha_wid, int B, int Lin, int stride, int dilation, int padding, int res_mode,
-                    int Tl, int chunk, int precision, int x_fmt, int act_fmt) {
+                    int Tl, int chunk, int precision, int x_fmt, int act_fmt, b2c_ref dmul = B2C_NULL_REF) {
   if (!p) return fail(B2C_ERR_ARG, "%s: NULL program", who);
   const Weight* w = get_w(p, wid, W_CONV, who);
   if (!w) return B2C_ERR_ARG;
-  if (act == B2C_ACT_SNAKE && !get_w(p, alpha_wid, W_VEC, who)) return B2C_ERR_ARG;
+  if ((act == B2C_ACT_SNAKE || dmul != B2C_NULL_REF) && !get_w(p, alpha_wid, W_VEC, who)) return B2C_ERR_ARG;
   if (B <= 0 || Lin <= 0) return fail(B2C_ERR_ARG, "%s: empty batch or length", who);
   if (w->cin % 16 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cin=%d must be a multiple of 16", who, w->cin);
   if (w->cout % 2 != 0) return fail(B2C_ERR_UNSUPPORTED, "%s: Cout=%d must be even", who, w->cout);
@@ -507,11 +536,12 @@ static int add_conv(b2c_prog* p, const char* who, int wid, b2c_ref x, b2c_ref re
   op.type = OP_CONV;
   op.x_fmt = x_fmt; op.act_fmt = act_fmt;
   blank_refs(op);
-  op.r[0] = x; op.r[1] = res; op.r[2] = out_raw; op.r[3] = out_act;
+  op.r[0] = x; op.r[1] = res; op.r[2] = out_raw; op.r[3] = out_act; op.r[4] = dmul;
   op.wid = wid; op.wid2 = alpha_wid;
   op.precision = precision;
   ConvArgs& a = op.conv;
   memset(&a, 0, sizeof(a));
+  if (dmul != B2C_NULL_REF) a.dmul = reinterpret_cast<const float*>(1);   // "present" for the planner; resolved at run time
   a.B = B; a.Lin = Lin; a.Cin = w->cin; a.Cout = w->cout; a.KT = w->kt;
   a.n_phase = w->n_phase;
   a.act = act; a.res_mode = res_mode; a.Tl = Tl > 0 ? Tl : 1; a.chunk = chunk > 0 ? chunk : 1;
@@ -560,6 +590,41 @@ extern "C" int b2c_prog_convT(b2c_prog* p, int wid, b2c_ref x, b2c_ref out_raw, 
   }
   return add_conv(p, "b2c_prog_convT", wid, x, B2C_NULL_REF, out_raw, out_act, act, alpha_wid, B, Lin, 1, 1, 0, 0, 0,
                   0, precision, x_fmt, act_fmt);
+}
+
+extern "C" int b2c_prog_conv_dsnake(b2c_prog* p, int wid, b2c_ref x, b2c_ref pre, int alpha_wid, b2c_ref res, b2c_ref out_raw,
+                                    b2c_ref out_act, int B, int Lin, int stride, int dilation, int padding, int precision,
+                                    int x_fmt, int act_fmt) {
+  if (p) {
+    const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_conv_dsnake");
+    if (!w) return B2C_ERR_ARG;
+    if (w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_conv_dsnake: weight %d is a ConvTranspose1d (pack its backward form as a Conv1d)", wid);
+    if (w->bias) return fail(B2C_ERR_ARG, "b2c_prog_conv_dsnake: backward-data weights carry no bias");
+  }
+  if (pre == B2C_NULL_REF) return fail(B2C_ERR_ARG, "b2c_prog_conv_dsnake: the pre-activation tensor is required");
+  return add_conv(p, "b2c_prog_conv_dsnake", wid, x, res, out_raw, out_act, B2C_ACT_NONE, alpha_wid, B, Lin, stride, dilation,
+                  padding, 0, 0, 0, precision, x_fmt, act_fmt, pre);
+}
+
+extern "C" int b2c_prog_head_bwd(b2c_prog* p, int wid, int alpha_wid, b2c_ref g_y, b2c_ref y, b2c_ref x_raw, b2c_ref g_raw,
+                                 b2c_ref g_act, int B, int L, int act_fmt) {
+  if (!p) return fail(B2C_ERR_ARG, "b2c_prog_head_bwd: NULL program");
+  const Weight* w = get_w(p, wid, W_CONV, "b2c_prog_head_bwd");
+  if (!w || !get_w(p, alpha_wid, W_VEC, "b2c_prog_head_bwd(alpha)")) return B2C_ERR_ARG;
+  if (w->cout != 1 || w->k != 7 || w->transposed) return fail(B2C_ERR_ARG, "b2c_prog_head_bwd: expects Conv1d(C, 1, 7)");
+  if (B <= 0 || L <= 0 || B > 65535) return fail(B2C_ERR_ARG, "b2c_prog_head_bwd: empty batch or length");
+  if (!fmt_ok(act_fmt)) return fail(B2C_ERR_ARG, "b2c_prog_head_bwd: bad activation format %d", act_fmt);
+  if (g_y == B2C_NULL_REF || y == B2C_NULL_REF || x_raw == B2C_NULL_REF || (g_raw == B2C_NULL_REF && g_act == B2C_NULL_REF))
+    return fail(B2C_ERR_ARG, "b2c_prog_head_bwd: missing buffer");
+  Op op;
+  op.type = OP_HEAD_BWD;
+  blank_refs(op);
+  op.r[0] = g_y; op.r[1] = y; op.r[2] = x_raw; op.r[3] = g_raw; op.r[4] = g_act;
+  op.wid = wid; op.wid2 = alpha_wid;
+  op.i[0] = B; op.i[1] = L;
+  op.act_fmt = act_fmt;
+  p->ops.push_back(op);
+  return B2C_OK;
 }
 
 static int ru_weights_ok(const b2c_ctx* ctx, int wid7, int wid1, int precision) {
@@ -918,10 +983,46 @@ static int launch_conv_f32(const ConvArgs& a, cudaStream_t st, int sm_count) {
   return B2C_OK;
 }
 
-static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = nullptr) {
+static int run_ops(b2c_prog* p, cudaStream_t main_st, Resolver& R, cudaEvent_t* ev = nullptr) {
   b2c_ctx* ctx = p->ctx;
+  cudaStream_t st = main_st;
+  bool forked = false;
+  auto join = [&]() -> int {
+    if (!forked) return B2C_OK;
+    CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->lane_stream));
+    CUDA_TRY(cudaStreamWaitEvent(main_st, ctx->ev_join, 0));
+    forked = false;
+    return B2C_OK;
+  };
   for (size_t oi = 0; oi < p->ops.size(); ++oi) {
     Op& op = p->ops[oi];
+    if (op.type == OP_LANE || op.type == OP_JOIN) {
+      if (ev) {   // per-op profile: one queue, the markers cost nothing
+        cudaEventRecord(ev[2 * oi], st);
+        cudaEventRecord(ev[2 * oi + 1], st);
+        continue;
+      }
+      if (op.type == OP_JOIN) {
+        int rc = join();
+        if (rc) return rc;
+        st = main_st;
+      } else if (op.i[0] == 1) {
+        if (!ctx->lane_stream) {
+          CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
+          CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+          CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        if (!forked) {
+          CUDA_TRY(cudaEventRecord(ctx->ev_fork, main_st));
+          CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_fork, 0));
+          forked = true;
+        }
+        st = ctx->lane_stream;
+      } else {
+        st = main_st;
+      }
+      continue;
+    }
     if (ev) cudaEventRecord(ev[2 * oi], st);
     switch (op.type) {
       case OP_STEM: {
@@ -957,10 +1058,11 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         a.out_act = reinterpret_cast<float*>(act_any);
         a.w = w.dev;
         a.bias = w.bias;
-        a.alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].dev : nullptr;
+        a.dmul = R.get<const float>(op.r[4]);
+        a.alpha = (a.act == ACT_SNAKE || a.dmul) ? ctx->w[op.wid2].dev : nullptr;
         if (R.bad || !a.x || (!a.out_raw && !a.out_act)) return fail(B2C_ERR_WORKSPACE, "op %zu (conv): unresolved buffer", oi);
         if (op.type == OP_CONV_TC) {
-          const float* inv_alpha = a.act == ACT_SNAKE ? ctx->w[op.wid2].aux : nullptr;
+          const float* inv_alpha = (a.act == ACT_SNAKE || a.dmul) ? ctx->w[op.wid2].aux : nullptr;
           int rc = tc_conv_launch(op.tc, a, inv_alpha, x_any, act_any, w.tc, st);
           if (rc) return fail(B2C_ERR_CUDA, "op %zu (conv, tcgen05): launch failed (%d)", oi, rc);
         } else {
@@ -1259,6 +1361,20 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         ema_update_f32<<<op.i[2], 128, 0, st>>>(x, idx, emb, counts, op.i[0], op.i[1], op.f[0], op.f[1]);
         break;
       }
+      case OP_HEAD_BWD: {
+        const Weight& w = ctx->w[op.wid];
+        const float* gy = R.get<const float>(op.r[0]);
+        const float* yy = R.get<const float>(op.r[1]);
+        const float* xr = R.get<const float>(op.r[2]);
+        float* graw = R.get<float>(op.r[3]);
+        void* gact = R.get<char>(op.r[4]);
+        if (R.bad || !gy || !yy || !xr) return fail(B2C_ERR_WORKSPACE, "op %zu (head backward): unresolved buffer", oi);
+        const int B = op.i[0], L = op.i[1];
+        const size_t sm = (size_t)(64 + 8 + 7 * w.cin) * sizeof(float);
+        head_k7_bwd_f32<<<dim3((L + 63) / 64, B), 256, sm, st>>>(gy, yy, xr, w.dev, ctx->w[op.wid2].dev, graw, gact, op.act_fmt,
+                                                                  (size_t)B * L * w.cin, L, w.cin);
+        break;
+      }
       case OP_WIDEN: {
         const int* in = R.get<const int>(op.r[0]);
         long long* out = R.get<long long>(op.r[1]);
@@ -1266,12 +1382,17 @@ static int run_ops(b2c_prog* p, cudaStream_t st, Resolver& R, cudaEvent_t* ev = 
         widen_i32_i64<<<(unsigned)((op.n + 255) / 256), 256, 0, st>>>(in, out, op.n);
         break;
       }
+      case OP_LANE:
+      case OP_JOIN: break;   // handled above
     }
     if (ev) cudaEventRecord(ev[2 * oi + 1], st);
     cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "op %zu (type %d): %s", oi, (int)op.type, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      join();
+      return fail(B2C_ERR_CUDA, "op %zu (type %d): %s", oi, (int)op.type, cudaGetErrorString(e));
+    }
   }
-  return B2C_OK;
+  return join();   // a program never returns with work on the second queue the caller's stream does not wait for
 }
 
 // algorithmic work of one launch: flops of the contraction, minimal global bytes
@@ -1301,6 +1422,12 @@ static void op_work(const b2c_ctx* ctx, const Op& op, int* kind, double* flops, 
       double n = (double)op.i[0] * op.i[1];
       *kind = B2C_KIND_STEM; *flops = 2.0 * n * 7 * w.cout;
       *bytes = 4.0 * (n + n * w.cout * ((op.r[1] != B2C_NULL_REF) + (op.r[2] != B2C_NULL_REF)));
+      break;
+    }
+    case OP_HEAD_BWD: {
+      const Weight& w = ctx->w[op.wid];
+      double n = (double)op.i[0] * op.i[1];
+      *kind = B2C_KIND_HEAD; *flops = 2.0 * n * 7 * w.cin; *bytes = 4.0 * (2.0 * n * w.cin + 2.0 * n) + 2.0 * n * w.cin;
       break;
     }
     case OP_HEAD: {
@@ -1512,7 +1639,7 @@ extern "C" size_t b2c_metric_stsim_scratch_bytes(int B, int L, int n_mels) {
 }
 
 extern "C" int b2c_metric_stsim(int device, void* stream, const float* ref, const float* est, const float* mel_fb,
-                                float* scratch, float* out, int B, int L, int n_mels) {
+                                const int* mel_range, float* scratch, float* out, int B, int L, int n_mels) {
   if (!ref || !est || !mel_fb || !scratch || !out || B <= 0 || n_mels <= 0 || n_mels > 128 || B > 65535)
     return fail(B2C_ERR_ARG, "b2c_metric_stsim: bad argument (n_mels <= 128)");
   if (L <= ST_NFFT / 2) return fail(B2C_ERR_ARG, "b2c_metric_stsim: reflect padding needs more than %d samples (got %d)", ST_NFFT / 2, L);
@@ -1522,7 +1649,7 @@ extern "C" int b2c_metric_stsim(int device, void* stream, const float* ref, cons
   float* mel = scratch;
   float* amax = scratch + (size_t)B * 2 * frames * n_mels;
   CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)B * 2 * sizeof(float), st));
-  stft_mel_pair_f32<<<dim3(frames, B), 256, 0, st>>>(ref, est, mel_fb, mel, amax, L, frames, n_mels);
+  stft_mel_pair_f32<<<dim3(frames, B), 256, 0, st>>>(ref, est, mel_fb, mel_range, mel, amax, L, frames, n_mels);
   stsim_from_mel_f32<<<B, 256, 0, st>>>(mel, amax, out, frames, n_mels);
   CUDA_TRY(cudaPeekAtLastError());
   return B2C_OK;

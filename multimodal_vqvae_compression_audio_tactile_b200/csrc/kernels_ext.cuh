@@ -205,4 +205,45 @@ __global__ void __launch_bounds__(128) ema_update_f32(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward-data of the decoder's tail (the forward is Snake1d -> Conv1d(C, 1, 7, p=3) -> tanh,
+// SURVEY App. A): with v the conv output and y = tanh(v),
+//   g_v[l] = g_y[l] (1 - y[l]^2);   g_s[q][c] = sum_t w[t][c] g_v[q + 3 - t];   g_x[q][c] = g_s[q][c] snake'(x[q][c]; alpha[c])
+// x is the pre-activation input of the last snake.  g_x is written as fp32 (the residual stream of the gradient)
+// and in the activation format the next backward contraction reads.  HBM-bound: x read once, g_x written once.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_k7_bwd_f32(const float* __restrict__ g_y, const float* __restrict__ y,
+                                                       const float* __restrict__ x_raw, const float* __restrict__ w,
+                                                       const float* __restrict__ alpha, float* __restrict__ g_raw,
+                                                       void* __restrict__ g_act, int act_fmt, size_t act_n, int L, int C) {
+  constexpr int TP = 64;
+  extern __shared__ float hb_sm[];
+  float* gv = hb_sm;            // TP + 6: g_v[l0 - 3 .. l0 + TP + 3)
+  float* ws = hb_sm + TP + 8;   // 7 * C
+  const int b = blockIdx.y, l0 = blockIdx.x * TP;
+  for (int i = threadIdx.x; i < TP + 6; i += blockDim.x) {
+    const int l = l0 + i - 3;
+    float g = 0.f;
+    if (l >= 0 && l < L) {
+      const float yy = __ldg(y + (size_t)b * L + l);
+      g = __ldg(g_y + (size_t)b * L + l) * (1.0f - yy * yy);
+    }
+    gv[i] = g;
+  }
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) ws[i] = __ldg(w + i);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TP * C; idx += blockDim.x) {
+    const int pp = idx / C, c = idx - pp * C;
+    const int l = l0 + pp;
+    if (l >= L) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) acc = fmaf(ws[t * C + c], gv[pp + 6 - t], acc);
+    const size_t o = ((size_t)b * L + l) * C + c;
+    const float g = acc * dsnake_f(__ldg(x_raw + o), __ldg(alpha + c));
+    if (g_raw) g_raw[o] = g;
+    if (g_act) store_fmt(g_act, act_fmt, act_n, o, g);
+  }
+}
+
 }  // namespace b2c

@@ -80,6 +80,11 @@ __device__ __forceinline__ float snake_sel(float v, float alpha, float inv) {
   return SFU ? snake_sfu(v, alpha, inv) : snake_fast(v, alpha, inv);
 }
 
+// d/dx snake(x) = 1 + sin(2 alpha x) * alpha / (alpha + 1e-9): the factor of the decoder's backward-data pass
+__device__ __forceinline__ float dsnake_f(float v, float alpha) {
+  return fmaf(sinf(2.0f * alpha * v), alpha * __frcp_rn(__fadd_rn(alpha, 1e-9f)), 1.0f);
+}
+
 __device__ __forceinline__ float gelu_f(float v) {
   // nn.GELU() (erf form): 0.5 x (1 + erf(x / sqrt 2))
   return __fmul_rn(__fmul_rn(v, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(v, 0.70710678118654752440f))));
@@ -112,6 +117,8 @@ struct ConvArgs {
   int in_off[8];
   int out_off[8];
   int act, res_mode, Tl, chunk;
+  // backward-data pass: the contraction (+ bias) is multiplied by snake'(dmul[out position]; alpha) BEFORE res is added
+  const float* dmul;
 };
 
 template <int TN>
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(256, 2) conv_gemm_f32(const ConvArgs a) {
       for (int e = 0; e < VW; ++e) {
         float t = acc[i][g * VW + e];
         if (a.bias) t = __fadd_rn(t, __ldg(a.bias + co + e));
+        if (a.dmul) t = __fmul_rn(t, dsnake_f(__ldg(a.dmul + orow + co + e), __ldg(a.alpha + co + e)));
         if (a.res) t = __fadd_rn(t, __ldg(a.res + rrow + co + e));
         v[e] = t;
       }

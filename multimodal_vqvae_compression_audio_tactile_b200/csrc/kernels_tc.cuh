@@ -253,6 +253,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 struct TcConvParams {
   const float* bias;
   const float* res;
+  const float* dmul;    // backward-data pass: (acc + bias) * snake'(dmul[out position]; alpha), then + res
   float* out_raw;
   void* out_act;        // FMT_F32: float*; FMT_PLANES / FMT_HI: bf16 hi plane, lo plane = hi + act_plane_elems
   const float* alpha;
@@ -287,6 +288,11 @@ constexpr int TC_STG_LD = 36;                        // floats per staging row: 
 constexpr int TC_STG_BYTES = 2 * TC_BM * TC_STG_LD * 4;
 
 
+// snake'(x) with the per-channel reciprocal 1 / (alpha + 1e-9) precomputed (backward-data epilogues)
+__device__ __forceinline__ float dsnake_pre(float v, float alpha, float inv) {
+  return fmaf(sinf(2.0f * alpha * v), alpha * inv, 1.0f);
+}
+
 // L2 prefetch of the residual rows of one output tile (issued one tile ahead by the 512 epilogue threads): the
 // epilogue's residual loads are latency-bound otherwise -- only one 32-column chunk (16 KB per SM) is in flight.
 __device__ __forceinline__ void tc_prefetch_res(const TcConvParams& p, int b, int ph, int jt, int nt) {
@@ -309,7 +315,7 @@ __device__ __forceinline__ void tc_prefetch_res(const TcConvParams& p, int b, in
 // barrier the 512 threads re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the
 // bias / residual loads and the raw / activated stores are coalesced.  Two staging tiles alternate: one
 // barrier per chunk.  When tempty_bar != 0 it is arrived on once the accumulator has been drained.
-template <int SFU>
+template <int SFU, int DM = 0>
 __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* stg, uint32_t& chunk_ctr, uint32_t t_acc,
                                                  int b, int ph, int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
   const int ew = warp - 2;
@@ -341,9 +347,15 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
     if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-    if (p.out_act && p.act == ACT_SNAKE) {
+    if ((p.out_act && p.act == ACT_SNAKE) || DM) {
       al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
       ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+    }
+    float4 dm[2];
+    if (DM) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        dm[i] = valid[i] ? __ldg(reinterpret_cast<const float4*>(p.dmul + orow[i] + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     {
       float v[8];
@@ -367,6 +379,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
       if (!valid[i]) continue;
       float4 a = *reinterpret_cast<const float4*>(sb + (r0 + 64 * i) * TC_STG_LD + cq * 4);
       a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      if (DM) {
+        a.x *= dsnake_pre(dm[i].x, al.x, ia.x); a.y *= dsnake_pre(dm[i].y, al.y, ia.y);
+        a.z *= dsnake_pre(dm[i].z, al.z, ia.z); a.w *= dsnake_pre(dm[i].w, al.w, ia.w);
+      }
       if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
       if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
       if (p.out_act) {
@@ -425,7 +441,7 @@ __device__ __forceinline__ void tc_prefetch_res_g(const TcConvParams& p, int b, 
   }
 }
 
-template <int SFU>
+template <int SFU, int DM = 0>
 __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float* stg_g, int g, uint32_t t_acc, int b, int ph,
                                                    int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
   const int wg = (warp - 2) & 7;
@@ -456,9 +472,15 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), al = bb, ia = bb;
     if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-    if (p.out_act && p.act == ACT_SNAKE) {
+    if ((p.out_act && p.act == ACT_SNAKE) || DM) {
       al = __ldg(reinterpret_cast<const float4*>(p.alpha + co));
       ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + co));
+    }
+    float4 dm[4];
+    if (DM) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dm[i] = valid[i] ? __ldg(reinterpret_cast<const float4*>(p.dmul + orow[i] + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     {
       float v[16];
@@ -482,6 +504,10 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
       if (!valid[i]) continue;
       float4 a = *reinterpret_cast<const float4*>(stg_g + (r0 + 32 * i) * TC_STG_LD + cq * 4);
       a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      if (DM) {
+        a.x *= dsnake_pre(dm[i].x, al.x, ia.x); a.y *= dsnake_pre(dm[i].y, al.y, ia.y);
+        a.z *= dsnake_pre(dm[i].z, al.z, ia.z); a.w *= dsnake_pre(dm[i].w, al.w, ia.w);
+      }
       if (p.res) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
       if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + orow[i] + co) = a;
       if (p.out_act) {
@@ -708,7 +734,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // re-read the tile row-major (8 lanes x float4 = one 128-byte row segment), so the bias / residual loads
     // and the raw / activated stores are coalesced.  Two staging tiles alternate: one barrier per chunk.
     float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
-    if (EPI == 0 && p.epi_groups == 2) {
+    if (EPI != 1 && p.epi_groups == 2) {
       // two independent groups of 8 warps: group g drains TMEM buffer g (tiles g, g + 2, ... of this CTA)
       const int g = (warp - 2) >> 3;
       float* stg_g = stg + g * (TC_BM * TC_STG_LD);
@@ -737,7 +763,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           epi_group_sync(g);
           if (((threadIdx.x - 64) & 255) == 0) mbar_arrive(smem_u32(&bar_tempty[g]));
         } else {
-          tc_epilogue_tile_g<!X3>(p, stg_g, g, tmem_base + g * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[g]), warp, lane);
+          tc_epilogue_tile_g<!X3, EPI == 2>(p, stg_g, g, tmem_base + g * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[g]), warp, lane);
         }
       }
     } else {
@@ -767,8 +793,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc_fence_before();
           asm volatile("bar.sync 1, 512;" ::: "memory");
           if (threadIdx.x == 64) mbar_arrive(smem_u32(&bar_tempty[acc]));
-        } else if (EPI == 0)
-          tc_epilogue_tile<!X3>(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
+        } else if (EPI != 1)
+          tc_epilogue_tile<!X3, EPI == 2>(p, stg, chunk_ctr, tmem_base + acc * p.acc_stride, b, ph, jt, nt, smem_u32(&bar_tempty[acc]),
                            warp, lane);
         else
           tc_epilogue_argmax(p, stg, tcount, tmem_base + acc * p.acc_stride, jt, nt, smem_u32(&bar_tempty[acc]), warp, lane);
@@ -1238,7 +1264,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   // accumulates channel-block-major: a layer must use the same kernel and order at every batch size.)
   const bool slab_wide = !plan->x3 && a.KT >= 3 && largest_bn(a.Cout) >= 192;
   const bool slab_pays = slab_wide;
-  if (a.in_step == 1 && tc_slab_enabled() && (slab_pays || tc_slab_forced())) {
+  if (a.in_step == 1 && !a.dmul && tc_slab_enabled() && (slab_pays || tc_slab_forced())) {
     // slab kernel: narrower channel blocks, several m-tiles per work item
     int bn2 = a.Cout % 128 == 0 ? 128 : (a.Cout % 96 == 0 ? 96 : (a.Cout % 64 == 0 ? 64 : bn));
     {
@@ -1310,7 +1336,7 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
                           void* out_act, const TcWeight& w, cudaStream_t st) {
   TcConvParams p = plan.p;
   p.bias = a.bias; p.res = a.res; p.out_raw = a.out_raw; p.out_act = out_act; p.alpha = a.alpha;
-  p.inv_alpha = inv_alpha;
+  p.inv_alpha = inv_alpha; p.dmul = a.dmul;
   if (plan.cached_x != x_planes) {
     const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(x_planes);
     const __nv_bfloat16* xl = xh + (size_t)p.B * p.Lin * p.Cin;
@@ -1351,6 +1377,19 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
       e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
       if (e != cudaSuccess) return -2;
       tc_launch(conv_tc2_kernel<0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    }
+    return 0;
+  }
+  if (p.dmul) {
+    // backward-data epilogue (EPI = 2): a separate instantiation, so the forward kernels' code and registers are untouched
+    if (plan.x3) {
+      e = cudaFuncSetAttribute(conv_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+      if (e != cudaSuccess) return -2;
+      tc_launch(conv_tc_kernel<1, 2>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
+    } else {
+      e = cudaFuncSetAttribute(conv_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+      if (e != cudaSuccess) return -2;
+      tc_launch(conv_tc_kernel<0, 2>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB_hi, plan.mB_lo, p);
     }
     return 0;
   }

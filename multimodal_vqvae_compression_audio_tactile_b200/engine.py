@@ -237,7 +237,24 @@ class Engine:
             self._ws = torch.empty(max(nbytes, ALIGN), dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def workspace_side(self, nbytes: int) -> torch.Tensor:
+        """Second workspace of two-lane programs (the side lane's activations: nothing the main lane allocates while
+        both run can alias them)."""
+        ws = getattr(self, "_ws_side", None)
+        if ws is None or ws.numel() < nbytes:
+            self._ws_side = None
+            self._ws_side = ws = torch.empty(max(nbytes, ALIGN), dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _ext(self, prog: Program, ext_ptrs):
+        """external pointers of a run: a two-lane program takes the side workspace as its last slot"""
+        side = prog.info.get("side_bytes", 0)
+        if side:
+            return list(ext_ptrs) + [self.workspace_side(side).data_ptr()]
+        return ext_ptrs
+
     def run(self, prog: Program, ext_ptrs):
+        ext_ptrs = self._ext(prog, ext_ptrs)
         ws = self.workspace(prog.ws_bytes)
         arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -247,6 +264,7 @@ class Engine:
     def profile(self, prog: Program, ext_ptrs):
         """Per-launch device times with cudaEvent pairs (measuring aid, not the timed path).
         -> list of dicts {kind, ms, flops, bytes}."""
+        ext_ptrs = self._ext(prog, ext_ptrs)
         ws = self.workspace(prog.ws_bytes)
         arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
         cap = prog.info["ops"] + 8
@@ -261,6 +279,7 @@ class Engine:
 
     def run_host(self, prog: Program, ext_ptrs, h2d, d2h):
         """h2d / d2h: lists of (host_ptr, slot, nbytes).  Synchronises the stream."""
+        ext_ptrs = self._ext(prog, ext_ptrs)
         ws = self.workspace(prog.ws_bytes)
         arr = (C.c_void_p * max(len(ext_ptrs), 1))(*ext_ptrs)
         hin = (L.HostCopy * max(len(h2d), 1))(*[L.HostCopy(p, s, n) for p, s, n in h2d])
@@ -273,6 +292,7 @@ class Engine:
     def run_host_pipelined(self, prog: Program, ext_sets, h2d, d2h, n_micro: int):
         """n_micro equal micro-batches, copies overlapped with compute (b2c_prog_run_host_pipelined).
         ext_sets: two lists of device pointers; h2d / d2h: (host_ptr of micro-batch 0, slot, bytes per micro-batch)."""
+        ext_sets = [self._ext(prog, ext_sets[0]), self._ext(prog, ext_sets[1])]
         ws = self.workspace(prog.ws_bytes)
         n_ext = len(ext_sets[0])
         arr = (C.c_void_p * (2 * n_ext))(*(list(ext_sets[0]) + list(ext_sets[1])))
@@ -295,15 +315,37 @@ class Emitter:
         self.h = h
         self.arena = Arena()
         self.fp32_reroutes = 0
+        # second launch queue (b2c_prog_set_lane): its buffers live in a second workspace, passed as external slot
+        # `side_slot`, with its own arena -- see Engine.workspace_side
+        self.arena_side = Arena()
+        self.side_slot = None
+        self._lane = 0
+
+    def lane(self, lane: int, side_slot: int = None):
+        """Ops (and buffers) emitted from here on go to launch queue `lane` (0 = the caller's stream)."""
+        if lane == 1:
+            if side_slot is None and self.side_slot is None:
+                raise L.B2CError("the side lane needs an external slot for its workspace")
+            self.side_slot = side_slot if side_slot is not None else self.side_slot
+        L.check(self.lib.b2c_prog_set_lane(self.h, lane), "b2c_prog_set_lane")
+        self._lane = lane
+
+    def join(self):
+        L.check(self.lib.b2c_prog_join(self.h), "b2c_prog_join")
+        self._lane = 0
 
     # buffers
-    def new(self, nfloats: int) -> int:
+    def new(self, nfloats: int):
+        if self._lane == 1:
+            return ("ext", self.side_slot, self.arena_side.alloc(4 * nfloats))
         return self.arena.alloc(4 * nfloats)
 
     def drop(self, *offs):
         for o in offs:
             if isinstance(o, int):
                 self.arena.free(o)
+            elif isinstance(o, tuple) and self.side_slot is not None and o[1] == self.side_slot:
+                self.arena_side.free(o[2])
 
     @staticmethod
     def ext(slot: int, off_bytes: int = 0):
@@ -318,6 +360,8 @@ class Emitter:
         return L.ref(0, buf)
 
     def finish(self, n_ext: int, **info) -> Program:
+        if self.side_slot is not None:
+            info["side_bytes"] = self.arena_side.peak + ALIGN
         return Program(self.h, self.arena.peak + ALIGN, n_ext,
                        dict(info, launches=self.lib.b2c_prog_num_launches(self.h), ops=self.lib.b2c_prog_num_ops(self.h),
                             fp32_reroutes=self.fp32_reroutes))
@@ -339,7 +383,7 @@ class Emitter:
         return L.check(self.lib.b2c_conv_tc_eligible(self.eng.ctx, w.wid, Lin, w.stride, w.dilation),
                        "b2c_conv_tc_eligible") == 1
 
-    def _contract(self, w: ConvW, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit):
+    def _contract(self, w: ConvW, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit, quiet=False):
         """Shared by conv / convT: run the contraction at `prec` when the tensor-core kernel takes the
         layer, else on the FP32 kernel, converting activation storage on either side when the caller's
         formats differ from what that kernel reads / writes."""
@@ -349,9 +393,9 @@ class Emitter:
             # B2C_STRICT_PRECISION=1 turns it into an error.
             what = (f"conv {w.cin}->{w.cout} k={w.k} stride={w.stride} dil={w.dilation} at Lin={Lin}: not eligible for "
                     f"the tcgen05 kernel (precision {prec}); running on the FP32 CUDA-core kernel")
-            if os.environ.get("B2C_STRICT_PRECISION", "0") == "1":
+            if os.environ.get("B2C_STRICT_PRECISION", "0") == "1" and not quiet:
                 raise L.B2CError(what)
-            if what not in self.eng.fp32_reroutes:
+            if what not in self.eng.fp32_reroutes and not quiet:
                 self.eng.fp32_reroutes.append(what)
                 warnings.warn("b200 codec: " + what, RuntimeWarning, stacklevel=3)
             self.fp32_reroutes += 1
@@ -400,6 +444,25 @@ class Emitter:
                                             alpha if alpha is not None else -1, B, Lin, pr, xf, of), "b2c_prog_convT")
 
         self._contract(w, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit)
+
+    def conv_dsnake(self, w: ConvW, x, pre, alpha, B, Lin, *, res=None, out_raw=None, out_act=None, prec=L.PREC_F32,
+                    x_fmt=L.FMT_F32, act_fmt=L.FMT_F32):
+        """Backward-data of "snake -> conv": out = conv(x; w) * snake'(pre; alpha) + res (b2c_prog_conv_dsnake).
+        w is the conv's backward-data form (PackedDecoderBwd)."""
+        Lout = (Lin + 2 * w.padding - w.dilation * (w.k - 1) - 1) // w.stride + 1
+
+        def emit(xb, xf, ob, of, pr):
+            L.check(self.lib.b2c_prog_conv_dsnake(self.h, w.wid, self._r(xb), self._r(pre), alpha, self._r(res),
+                                                  self._r(out_raw), self._r(ob), B, Lin, w.stride, w.dilation, w.padding,
+                                                  pr, xf, of), "b2c_prog_conv_dsnake")
+
+        # a strided contraction whose input length is not a multiple of the stride (the 2999-sample stage of the
+        # decoder) has no TMA view: it runs on the FP32 kernel by construction, not as a surprise
+        self._contract(w, x, B, Lin, Lout, x_fmt, act_fmt, out_act, prec, emit, quiet=w.stride > 1 and Lin % w.stride != 0)
+
+    def head_bwd(self, w: ConvW, alpha, g_y, y, x_raw, g_raw, g_act, B, Lx, act_fmt=L.FMT_F32):
+        L.check(self.lib.b2c_prog_head_bwd(self.h, w.wid, alpha, self._r(g_y), self._r(y), self._r(x_raw), self._r(g_raw),
+                                           self._r(g_act), B, Lx, act_fmt), "b2c_prog_head_bwd")
 
     def head(self, w: ConvW, x, y, B, Lx, x_fmt=L.FMT_F32):
         L.check(self.lib.b2c_prog_head(self.h, w.wid, self._r(x), self._r(y), B, Lx, x_fmt), "b2c_prog_head")
@@ -603,6 +666,141 @@ def emit_decoder(em: Emitter, pd: PackedDecoder, z, y, B, Tl, prec, free_input=T
     em.head(pd.head, x_act, y, B, Lx, x_fmt=f)
     em.drop(x_act)
     return Lx
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder with gradients: forward that keeps every snake's input, and the backward-data pass
+# ---------------------------------------------------------------------------------------------
+def _folded_weight(m) -> torch.Tensor:
+    """w = g * v / ||v|| of a weight-normed conv (norm over all dims but 0, in double), fp32 CPU."""
+    v = m.weight_v.detach().to("cpu", torch.float64)
+    g = m.weight_g.detach().to("cpu", torch.float64).reshape(-1, 1, 1)
+    return (v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1))).to(torch.float32)
+
+
+def _pack_conv_bwd(eng: Engine, m) -> ConvW:
+    """Backward-data form of a conv as a bias-free Conv1d.  Conv1d [co, ci, k] (stride 1): channels transposed, taps
+    flipped, padding dil*(k-1) - p.  ConvTranspose1d [ci, co, k]: d/dx is the strided Conv1d whose weight [cout'=ci,
+    cin'=co, k] is the same tensor, with the forward stride and padding."""
+    w = _folded_weight(m)
+    if getattr(m, "transposed", False):
+        cw = eng.pack_plain(w.contiguous())
+        cw.stride, cw.padding = m.stride, m.padding
+        return cw
+    if m.stride != 1:
+        raise L.B2CError("backward-data of a strided Conv1d is not needed by the decoder and not built")
+    cw = eng.pack_plain(w.permute(1, 0, 2).flip(2).contiguous())
+    cw.dilation, cw.padding = m.dilation, m.dilation * (m.kernel_size - 1) - m.padding
+    return cw
+
+
+@dataclass
+class PackedDecoderBwd:
+    stem: ConvW
+    blocks: list   # [(up backward ConvW, [(c7 backward, c1 backward)] * 3)]
+
+    @staticmethod
+    def pack(eng: Engine, dec) -> "PackedDecoderBwd":
+        layers = list(dec.model)
+        blocks = []
+        for db in layers[1:-3]:
+            b = db.block
+            blocks.append((_pack_conv_bwd(eng, b[1]),
+                           [(_pack_conv_bwd(eng, ru.block[1]), _pack_conv_bwd(eng, ru.block[3])) for ru in (b[2], b[3], b[4])]))
+        return PackedDecoderBwd(_pack_conv_bwd(eng, layers[0]), blocks)
+
+
+class SavedLayout:
+    """Where the forward leaves the inputs of every snake (fp32, channel-last) inside the buffer the autograd node
+    owns (external slot `slot`): x0 = stem output, per block u = up-conv output, h[r] = k=7 conv output and y[r] = unit
+    output of the three residual units.  Forward and backward programs are emitted against the same layout."""
+
+    def __init__(self, pd: PackedDecoder, B: int, Tl: int, slot: int):
+        self.slot, self.top = slot, 0
+        self.lens = [Tl + 2 * pd.stem.padding - (pd.stem.k - 1)]
+        self.x0 = self._new(B * self.lens[0] * pd.stem.cout)
+        self.u, self.h, self.y = [], [], []
+        for (_, up, *_r) in pd.blocks:
+            Lo = (self.lens[-1] - 1) * up.stride - 2 * up.padding + up.k
+            self.lens.append(Lo)
+            n = B * Lo * up.cout
+            self.u.append(self._new(n))
+            self.h.append([self._new(n) for _ in range(3)])
+            self.y.append([self._new(n) for _ in range(3)])
+        self.nbytes = self.top
+
+    def _new(self, nfloats):
+        off = self.top
+        self.top += (4 * nfloats + ALIGN - 1) // ALIGN * ALIGN
+        return ("ext", self.slot, off)
+
+
+def emit_decoder_train(em: Emitter, pd: PackedDecoder, z, y, B, Tl, prec, lay: SavedLayout):
+    """emit_decoder with every residual unit as two launches whose pre-activations go to `lay` (the fused unit keeps
+    h in shared memory; the backward needs it)."""
+    f = L.FMT_OF_PREC[prec]
+    Lx = Tl
+    x_act = em.new(B * Lx * pd.stem.cout)
+    em.conv(pd.stem, z, B, Lx, out_raw=lay.x0, out_act=x_act, alpha=pd.blocks[0][0], prec=prec, x_fmt=L.FMT_F32, act_fmt=f)
+    for bi, (a_up, up, r0, r1, r2) in enumerate(pd.blocks):
+        Lo = lay.lens[bi + 1]
+        n = B * Lo * up.cout
+        n_act = em.new(n)
+        em.convT(up, x_act, B, Lx, out_raw=lay.u[bi], out_act=n_act, alpha=r0.a1, prec=prec, x_fmt=f, act_fmt=f)
+        em.drop(x_act)
+        x_raw, x_act, Lx = lay.u[bi], n_act, Lo
+        nxt = pd.blocks[bi + 1][0] if bi + 1 < len(pd.blocks) else pd.a_final
+        for ri, ru in enumerate((r0, r1, r2)):
+            h_act = em.new(n)
+            em.conv(ru.c7, x_act, B, Lx, out_raw=lay.h[bi][ri], out_act=h_act, alpha=ru.a2, prec=prec, x_fmt=f, act_fmt=f)
+            em.drop(x_act)
+            y_act = em.new(n)
+            em.conv(ru.c1, h_act, B, Lx, res=x_raw, out_raw=lay.y[bi][ri], out_act=y_act,
+                    alpha=(r1.a1, r2.a1, nxt)[ri], prec=prec, x_fmt=f, act_fmt=f)
+            em.drop(h_act)
+            x_raw, x_act = lay.y[bi][ri], y_act
+    em.head(pd.head, x_act, y, B, Lx, x_fmt=f)
+    em.drop(x_act)
+
+
+def emit_decoder_bwd(em: Emitter, pd: PackedDecoder, pb: PackedDecoderBwd, lay: SavedLayout, g_y, y, g_z, B, Tl, prec):
+    """dL/dz of the decoder: g_y, y [B, Lout] -> g_z [B, C, Tl] (the reference's layout).  Reverse walk of
+    emit_decoder_train; per forward "snake -> conv" one b2c_prog_conv_dsnake launch, the skip connection of a residual
+    unit is its `res` operand."""
+    f = L.FMT_OF_PREC[prec]
+    nb = len(pd.blocks)
+    Lx, C = lay.lens[nb], pd.head.cin
+    g_raw, g_act = em.new(B * Lx * C), em.new(B * Lx * C)
+    em.head_bwd(pd.head, pd.a_final, g_y, y, lay.y[nb - 1][2], g_raw, g_act, B, Lx, act_fmt=f)
+    for bi in reversed(range(nb)):
+        a_up, up, r0, r1, r2 = pd.blocks[bi]
+        up_b, ru_b = pb.blocks[bi]
+        Lx, C = lay.lens[bi + 1], up.cout
+        n = B * Lx * C
+        for ri in (2, 1, 0):
+            ru = (r0, r1, r2)[ri]
+            c7b, c1b = ru_b[ri]
+            x_in = lay.u[bi] if ri == 0 else lay.y[bi][ri - 1]
+            gh = em.new(n)
+            em.conv_dsnake(c1b, g_act, lay.h[bi][ri], ru.a2, B, Lx, out_act=gh, prec=prec, x_fmt=f, act_fmt=f)
+            em.drop(g_act)
+            n_raw, n_act = em.new(n), em.new(n)
+            em.conv_dsnake(c7b, gh, x_in, ru.a1, B, Lx, res=g_raw, out_raw=n_raw, out_act=n_act, prec=prec, x_fmt=f,
+                           act_fmt=f)
+            em.drop(gh, g_raw)
+            g_raw, g_act = n_raw, n_act
+        Lp, Cp = lay.lens[bi], up.cin
+        pre = lay.x0 if bi == 0 else lay.y[bi - 1][2]
+        n_raw = em.new(B * Lp * Cp) if bi > 0 else None
+        n_act = em.new(B * Lp * Cp)
+        em.conv_dsnake(up_b, g_act, pre, a_up, B, Lx, out_raw=n_raw, out_act=n_act, prec=prec, x_fmt=f, act_fmt=f)
+        em.drop(g_act, g_raw)
+        g_raw, g_act = n_raw, n_act
+    gz = em.new(B * Tl * pd.stem.cin)
+    em.conv(pb.stem, g_act, B, lay.lens[0], out_raw=gz, prec=prec, x_fmt=f)
+    em.drop(g_act)
+    em.transpose(gz, g_z, B, Tl, pd.stem.cin)
+    em.drop(gz)
 
 
 @dataclass

@@ -91,7 +91,12 @@ def _mel_table(device, n_mels=64, sr=EVAL_SR, n_fft=512):
     key = ("mel", str(device), n_mels, sr, n_fft)
     tab = _tables.get(key)
     if tab is None:
-        tab = _tables[key] = mel_filterbank(n_fft // 2 + 1, 0.0, sr * 0.5, n_mels, sr).to(device)
+        fb = mel_filterbank(n_fft // 2 + 1, 0.0, sr * 0.5, n_mels, sr)
+        nz = fb != 0                                   # bins [lo, hi) of every band's triangle
+        lo = torch.where(nz.any(0), nz.int().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        hi = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).int().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        rng = torch.stack([lo, hi], dim=1).to(torch.int32).contiguous()
+        tab = _tables[key] = (fb.to(device), rng.to(device))
     return tab
 
 
@@ -204,10 +209,11 @@ def stsim_tensor(ref_1T, est_1T, n_mels: int = 64) -> torch.Tensor:
     lib = L.load()
     out = torch.empty(B, device=r.device, dtype=torch.float32)
     if B:
-        fb = _mel_table(r.device, n_mels)
+        fb, rng = _mel_table(r.device, n_mels)
         scratch = torch.empty(int(lib.b2c_metric_stsim_scratch_bytes(B, T, n_mels)) // 4, device=r.device,
                               dtype=torch.float32)
-        L.check(lib.b2c_metric_stsim(_dev_index(r), _stream(r), _p(r), _p(e), _p(fb), _p(scratch), _p(out), B, T, n_mels),
+        L.check(lib.b2c_metric_stsim(_dev_index(r), _stream(r), _p(r), _p(e), _p(fb), _p(rng), _p(scratch), _p(out), B, T,
+                                     n_mels),
                 "b2c_metric_stsim")
     return out
 

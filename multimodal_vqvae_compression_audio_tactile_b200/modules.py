@@ -20,8 +20,9 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .engine import (Emitter, Engine, PackedDecoder, PackedEncoder, PackedPredictor, emit_decoder, emit_encoder,
-                     emit_latent_coder, emit_predict_full, emit_predict_rows)
+from .engine import (Emitter, Engine, PackedDecoder, PackedDecoderBwd, PackedEncoder, PackedPredictor, SavedLayout,
+                     emit_decoder, emit_decoder_bwd, emit_decoder_train, emit_encoder, emit_latent_coder,
+                     emit_predict_full, emit_predict_rows)
 
 CODE_DIM = 96       # Evaluation/dac_vcpwq_proposed6_latency.py:336
 AR_CHUNK_TOK = 16   # :337
@@ -168,6 +169,9 @@ class _Top(nn.Module):
         """precision of stage `key` ('enc' | 'pred' | 'dec'): `precision` is a plan name (_lib.PLANS) or a
         {stage: arithmetic} dict."""
         p = self.precision
+        owner = self.__dict__.get("_b2c_owner")
+        if owner is not None and "precision" not in self.__dict__ and owner[0]() is not None:
+            p = owner[0]().precision      # a sub-module called on its own follows its model's plan unless it was given one
         if isinstance(p, str):
             if p not in L.PLANS:
                 raise ValueError(f"unknown precision plan {p!r}; choose from {sorted(L.PLANS)}")
@@ -253,8 +257,30 @@ class Encoder(_Top):
         return out.to(x.dtype)
 
 
+class _DecoderGrad(torch.autograd.Function):
+    """T_DEC with a gradient w.r.t. its input: both directions run in libb2c.so (the frozen decoder of the training
+    scripts, Training/compare_dacvsproposal_3.py:306-307, :386-409 -- the loss reaches predict / proj_* through it)."""
+
+    @staticmethod
+    def forward(ctx, z, dec):
+        y, saved = dec._forward_saving(z)
+        ctx.dec, ctx.saved, ctx.z_shape, ctx.z_dtype = dec, saved, tuple(z.shape), z.dtype
+        ctx.save_for_backward(y)
+        return y.to(z.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_y):
+        (y,) = ctx.saved_tensors
+        g_z = ctx.dec._backward_data(ctx.saved, y, g_y, ctx.z_shape)
+        ctx.saved = None
+        return g_z.to(ctx.z_dtype), None
+
+
 class Decoder(_Top):
-    """``T_DEC``: z [B, C, Tl] -> y [B, 1, 320*Tl - 8]."""
+    """``T_DEC``: z [B, C, Tl] -> y [B, 1, 320*Tl - 8].  With autograd enabled and ``z.requires_grad`` the call is
+    differentiable w.r.t. ``z`` (backward-data pass on the GPU; the decoder's own weights are frozen in every
+    reference script and get no gradient)."""
 
     def __init__(self, input_channel=1024, channels=1536, rates=(8, 5, 4, 2), d_out=1):
         super().__init__()
@@ -269,17 +295,87 @@ class Decoder(_Top):
     def _pack(self, eng):
         return PackedDecoder.pack(eng, self)
 
-    @torch.no_grad()
     def forward(self, z):
-        _require_cuda(z)
+        if torch.is_grad_enabled() and z.requires_grad:
+            _require_cuda(z)
+            if any(p.requires_grad for p in self.parameters()) and not self.__dict__.get("_b2c_warned_wgrad"):
+                self.__dict__["_b2c_warned_wgrad"] = True
+                import warnings
+                warnings.warn("b200 codec: Decoder parameters require grad, but only dL/dz is computed (the reference "
+                              "freezes T_DEC); call requires_grad_(False) on them", RuntimeWarning, stacklevel=2)
+            return _DecoderGrad.apply(z, self)
+        return self._forward_nograd(z)
+
+    def _check(self, z, pk):
         if z.dim() != 3:
             raise ValueError(f"Decoder expects [B, C, Tl], got {tuple(z.shape)}")
-        eng, pk = self._engine(z.device)
         B, c, Tl = z.shape
         if c != pk.stem.cin:
             raise ValueError(f"Decoder expects {pk.stem.cin} channels, got {c}")
         if B == 0 or Tl == 0:
             raise ValueError("Decoder: empty input")
+
+    def _grad_prec(self):
+        """arithmetic of the differentiable path: the plan's decoder precision; the FP32 plan keeps >= 16 mantissa bits
+        on the tensor cores (bf16x3) -- the backward-data epilogue exists on the tcgen05 and FP32 kernels alike, but the
+        CUDA-core kernel is several times slower."""
+        return self._prec("dec")
+
+    @torch.no_grad()
+    def _forward_saving(self, z):
+        """forward that keeps the input of every snake: -> (y [B, 1, Lo] fp32, [(b0, nb, saved bytes tensor)])."""
+        eng, pk = self._engine(z.device)
+        self._check(z, pk)
+        B, c, Tl = z.shape
+        Lo, prec = pk.out_len(Tl), self._grad_prec()
+        zin = _as_f32(z)
+        y = torch.empty(B, 1, Lo, device=z.device, dtype=torch.float32)
+        saved = []
+        mb = min(B, self.micro_batch)
+        for b0 in range(0, B, mb):
+            nb = min(mb, B - b0)
+            lay = SavedLayout(pk, nb, Tl, 3)
+            key = ("dec-train", id(pk), nb, Tl, prec)
+            prog = eng.programs.get(key)
+            if prog is None:
+                em = Emitter(eng)
+                zc = em.new(nb * Tl * c)
+                em.transpose(em.ext(1), zc, nb, c, Tl)
+                emit_decoder_train(em, pk, zc, em.ext(2), nb, Tl, prec, lay)
+                prog = eng.programs[key] = em.finish(3)
+            buf = torch.empty(lay.nbytes, device=z.device, dtype=torch.uint8)
+            eng.run(prog, [zin[b0:].data_ptr(), y[b0:].data_ptr(), buf.data_ptr()])
+            saved.append((b0, nb, buf))
+        return y, saved
+
+    @torch.no_grad()
+    def _backward_data(self, saved, y, g_y, z_shape):
+        eng, pk = self._engine(y.device)
+        B, c, Tl = z_shape
+        prec = self._grad_prec()
+        pb = eng.aux.get(("dec-bwd-weights", id(pk)))
+        if pb is None:
+            pb = eng.aux[("dec-bwd-weights", id(pk))] = PackedDecoderBwd.pack(eng, self)
+        gy = _as_f32(g_y)
+        yy = _as_f32(y)
+        g_z = torch.empty(B, c, Tl, device=y.device, dtype=torch.float32)
+        for b0, nb, buf in saved:
+            lay = SavedLayout(pk, nb, Tl, 3)
+            key = ("dec-bwd", id(pk), nb, Tl, prec)
+            prog = eng.programs.get(key)
+            if prog is None:
+                em = Emitter(eng)
+                emit_decoder_bwd(em, pk, pb, lay, em.ext(1), em.ext(2), em.ext(4), nb, Tl, prec)
+                prog = eng.programs[key] = em.finish(4)
+            eng.run(prog, [gy[b0:].data_ptr(), yy[b0:].data_ptr(), buf.data_ptr(), g_z[b0:].data_ptr()])
+        return g_z
+
+    @torch.no_grad()
+    def _forward_nograd(self, z):
+        _require_cuda(z)
+        eng, pk = self._engine(z.device)
+        self._check(z, pk)
+        B, c, Tl = z.shape
         Lo = pk.out_len(Tl)
         zin = _as_f32(z)
         y = torch.empty(B, 1, Lo, device=z.device, dtype=torch.float32)
@@ -620,17 +716,28 @@ class ProposedEval(_Top):
         """ext slots: 1 a [nb,T], 2 t [nb,T], 3 y [nb,Lout], 4 idx i32 [nb,use,Tl], 5 audio codes i32 [nb,n_q,Tl],
         6 z_run ([nb,Tl,C] channel-last, or [nb,C,Tl] when latents_cm)."""
         pe, pd, pt = self._prec("enc"), self._prec("dec"), self._prec("pred")
-        key = ("codec", nb, T, use, decode, latents_cm, pe, pd, pt)
+        key = ("codec", nb, T, use, decode, latents_cm, pe, pd, pt, self._two_lanes(nb))
         prog = eng.programs.get(key)
         if prog is not None:
             return prog
         em = Emitter(eng)
         c = pk["pp"].c
+        two_lanes = self._two_lanes(nb)
+        if two_lanes:
+            # small batches: neither encoder fills the GPU (a 512-channel layer of one frame is 5 row tiles), and the two
+            # are independent until the predictor -- the tactile encoder runs on a second launch queue beside the audio
+            # encoder + DAC quantizer.  Same kernels, same arithmetic; only the queueing differs.
+            em.lane(1, side_slot=7)
+            zt, Tl2 = emit_encoder(em, pk["t_enc"], em.ext(2), nb, T, pe)
+            em.lane(0)
         za, Tl = emit_encoder(em, pk["a_enc"], em.ext(1), nb, T, pe)
         qa = em.new(nb * Tl * c)
         em.dac_rvq(pk["a_q"], pk["n_q"], za, qa, em.ext(5), nb, Tl)
         em.drop(za)
-        zt, Tl2 = emit_encoder(em, pk["t_enc"], em.ext(2), nb, T, pe)
+        if two_lanes:
+            em.join()
+        else:
+            zt, Tl2 = emit_encoder(em, pk["t_enc"], em.ext(2), nb, T, pe)
         assert Tl2 == Tl
         z_run = em.new(nb * Tl * c)
         emit_latent_coder(em, pk["pp"], qa, zt, z_run, em.ext(4), nb, Tl, AR_CHUNK_TOK, use, pt)
@@ -639,8 +746,18 @@ class ProposedEval(_Top):
             em.transpose(z_run, em.ext(6), nb, Tl, c)
         if decode:
             emit_decoder(em, pk["t_dec"], z_run, em.ext(3), nb, Tl, pd)
-        prog = eng.programs[key] = em.finish(6, Tl=Tl, Lout=pk["t_dec"].out_len(Tl))
+        prog = eng.programs[key] = em.finish(7 if two_lanes else 6, Tl=Tl, Lout=pk["t_dec"].out_len(Tl))
         return prog
+
+    #: frames per program up to which the two encoders run on two launch queues (B2C_LANES=0 / 1 forces it off / on)
+    two_lane_max_batch = 4
+
+    def _two_lanes(self, nb):
+        import os
+        e = os.environ.get("B2C_LANES")
+        if e is not None:
+            return e != "0"
+        return nb <= self.two_lane_max_batch
 
     def program_decode(self, eng, pk, nb, T, use):
         """Receiver program: ext slots 1 a [nb,T], 3 y [nb,Lout], 4 idx i32 [nb,use,Tl] (INPUT), 5 audio codes i32."""
@@ -754,7 +871,8 @@ class ProposedEval(_Top):
             with torch.cuda.graph(graph):
                 eng.run(prog, ext)
             prog.pinned = True
-            rec = eng.aux[key] = dict(graph=graph, st=st, prog=prog, ws=eng.workspace(prog.ws_bytes))   # keeps the workspace alive
+            rec = eng.aux[key] = dict(graph=graph, st=st, prog=prog, ws=eng.workspace(prog.ws_bytes),   # keeps the workspaces alive
+                                      ws_side=eng.workspace_side(prog.info["side_bytes"]) if prog.info.get("side_bytes") else None)
         st = rec["st"]
         st["a"].copy_(a); st["t"].copy_(t)
         rec["graph"].replay()
@@ -831,14 +949,97 @@ class ProposedEval(_Top):
         self.last_host_bytes = (h2d_b, d2h_b)
         return y_out, idx_out
 
-    @torch.no_grad()
     def forward_step(self, a_1T, tc_1T):
-        """Forward of AllPredAR.forward_step (Training/compare_dacvsproposal_3.py:300-340), no gradients."""
-        y = self.forward_eval(a_1T, tc_1T)
-        n = min(y.shape[-1], tc_1T.shape[-1])
-        return {"y_hat": y[..., :n], "tgt": tc_1T[..., :n]}
+        """AllPredAR.forward_step (Training/compare_dacvsproposal_3.py:300-340).  Without autograd: the fused CUDA
+        program of ``forward_eval``.  With autograd enabled (the training loop, :386-409): the frozen backbones
+        (A_ENC, A_QUANT, T_ENC) and the residual VQ run in libb2c.so without a graph, T_DEC runs in libb2c.so in both
+        directions (``_DecoderGrad``: backward-data pass), and the 9 M-parameter trainable layers in between
+        (predict, tokennorm, scale, proj_down / proj_up) are evaluated with PyTorch operators so that autograd
+        produces their parameter gradients; the straight-through estimator of ``vq`` (:259-260) passes the gradient
+        unchanged.  Returns the reference's dict."""
+        if not torch.is_grad_enabled():
+            with torch.no_grad():
+                y = self.forward_eval(a_1T, tc_1T)
+            n = min(y.shape[-1], tc_1T.shape[-1])
+            return {"y_hat": y[..., :n], "tgt": tc_1T[..., :n]}
+        _require_cuda(a_1T, tc_1T)
+        Tw = tc_1T.shape[-1]
+        with torch.no_grad():
+            za = self.A_ENC(a_1T)
+            qa, *_ = self.A_QUANT(za)
+            zt_teacher = self.T_ENC(tc_1T)
+        B, C_, Tlat = zt_teacher.shape
+        z_run = torch.zeros_like(zt_teacher)
+        chunks, rD_all = [], []
+        for s0 in range(0, Tlat, AR_CHUNK_TOK):
+            e0 = min(Tlat, s0 + AR_CHUNK_TOK)
+            zt_prev = torch.zeros(B, C_, e0 - s0, device=zt_teacher.device, dtype=zt_teacher.dtype)
+            prev = torch.cat(chunks, dim=-1) if chunks else None
+            if s0 == 0:
+                pass                                   # z_run[..., 0:e-1] is still zero for the first chunk (:314-315)
+            else:
+                zt_prev[..., :1] = prev[..., s0 - 1:s0]       # only the previous chunk's last token is non-zero (:316-317)
+            z_pred = _predict_autograd(self.predict, zt_prev, qa[..., s0:e0])
+            r = zt_teacher[..., s0:e0] - z_pred.detach()
+            rN = torch.tanh(_tokennorm_autograd(self.tokennorm, r))
+            rD = self.proj_down(self.scale.clamp(5e-3, 0.5) * rN)
+            qD = _VQStraightThrough.apply(rD, self.vq)
+            z_hat = z_pred + self.proj_up(qD)
+            chunks.append(z_hat)
+            rD_all.append(rD.detach())
+        z_run = torch.cat(chunks, dim=-1)
+        y_hat = self.T_DEC(z_run)
+        T = min(y_hat.shape[-1], tc_1T.shape[-1], Tw)
+        fz = lambda x: torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)          # finite_or_zero (:87-88)
+        return {"y_hat": fz(y_hat[..., :T]), "tgt": fz(tc_1T[..., :T]), "z_pred": None, "z_teacher": zt_teacher,
+                "z_run": z_run, "r_tokens": torch.cat(rD_all, dim=-1) if rD_all else None}
 
     forward = forward_eval
+
+
+# ------------------------------------------------------------------------------------------
+# autograd side of the training forward (the trainable layers only; see ProposedEval.forward_step)
+# ------------------------------------------------------------------------------------------
+class _VQStraightThrough(torch.autograd.Function):
+    """ResidualVQEMA.forward under autograd (Training/compare_dacvsproposal_3.py:253-262): the value is the CUDA
+    kernel's q_sum (same op order as ``q_sum + (q - residual).detach() + residual``), the gradient w.r.t. z is the
+    identity, the codebooks get none (they move by ema_step)."""
+
+    @staticmethod
+    def forward(ctx, z, vq):
+        with torch.no_grad():
+            return vq(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def _predict_autograd(pr: "CrossPredictor", zt_prev, za):
+    """CrossPredictor.forward (:236-243) written with differentiable PyTorch operators on the module's parameters."""
+    F = torch.nn.functional
+    T = zt_prev.shape[-1]
+    pe = pr.pos.pe[:T].t().unsqueeze(0)
+    q = (zt_prev + pe).permute(0, 2, 1)
+    kv = (za + pe).permute(0, 2, 1)
+    q = F.layer_norm(q, q.shape[-1:], pr.ln_q.weight, pr.ln_q.bias, pr.ln_q.eps)
+    kv = F.layer_norm(kv, kv.shape[-1:], pr.ln_kv.weight, pr.ln_kv.bias, pr.ln_kv.eps)
+
+    def split(x):
+        b, t, c = x.shape
+        return x.view(b, t, pr.h, pr.dh).permute(0, 2, 1, 3)
+
+    Q, K, V = split(F.linear(q, pr.q_proj.weight)), split(F.linear(kv, pr.k_proj.weight)), split(F.linear(kv, pr.v_proj.weight))
+    attn = (Q @ K.transpose(-2, -1)) / math.sqrt(pr.dh)
+    ctx = attn.softmax(dim=-1) @ V
+    b, h, t, d = ctx.shape
+    y = F.linear(pr.drop(ctx.permute(0, 2, 1, 3).contiguous().view(b, t, h * d)), pr.out.weight)
+    y = pr.ffn(y + q) + (y + q)
+    return y.permute(0, 2, 1)
+
+
+def _tokennorm_autograd(tn: "TokenNorm", z):
+    return tn.ln(z.permute(0, 2, 1)).permute(0, 2, 1)
 
 
 def build_proposed(rvq_books: int, rvq_embed: int) -> ProposedEval:

@@ -78,8 +78,29 @@ def main():
         )
         print("wrote", name, "y", tuple(y.shape), "idx", tuple(idx.shape))
 
-    if only and "plc" not in only and "ema" not in only and "metrics" not in only:
+    if only and not ({"plc", "ema", "metrics", "train"} & set(only)):
         return
+    # ---- training step with autograd: the reference's AllPredAR.forward_step + backward ----
+    if not only or "train" in only:
+        from oracle import training as otr
+        from oracle import proposed as oproposed
+        case = otr.TRAIN_CASE
+        net = build_reference_style_model(oproposed.ProposedEval, case)
+        ref = ref_loader.reference_train_model(net, case["books"], case["K"])
+        a, t = codec_inputs(case)
+        holder = {}
+        hook = ref.T_DEC.register_forward_pre_hook(lambda m, inp: (inp[0].retain_grad(), holder.__setitem__("z", inp[0]))[0] and None)
+        out = ref.forward_step(a, t)
+        hook.remove()
+        loss = otr.objective(out)
+        loss.backward()
+        named = dict(ref.named_parameters())
+        blobs = dict(loss=np.array(float(loss)), y_hat=out["y_hat"].detach().numpy(), g_z_run=holder["z"].grad.numpy(),
+                     fingerprint=weights_fingerprint(net))
+        for k in otr.GRAD_KEYS:
+            blobs["grad_" + k] = named[k].grad.numpy()[..., :32] if named[k].grad.dim() == 2 else named[k].grad.numpy()
+        np.savez_compressed(os.path.join(OUT, "train_step.npz"), **blobs)
+        print("wrote train_step", float(loss), {k: v.shape for k, v in blobs.items()})
     # ---- evaluation metrics: the reference's own functions (Evaluation/compare_dacvsproposal_5_eval.py) ----
     if not only or "metrics" in only:
         from oracle import metrics as om

@@ -27,6 +27,17 @@ PLC_WANTED = ("PACKET_TOK", "PACKET_LOSS_PROB", "finite_or_zero", "PosEnc1D", "T
               "make_token_loss_mask", "AllPredPLC")
 TRAIN_SCRIPT = os.path.join(REF_ROOT, "Training", "compare_dacvsproposal_3.py")
 TRAIN_WANTED = ("CODE_DIM", "RVQ_N_BOOKS", "RVQ_EMBED", "EMA_DECAY", "AR_CHUNK_TOK", "ResidualVQEMA")
+TRAIN_STEP_WANTED = TRAIN_WANTED + ("finite_or_zero", "PosEnc1D", "TokenNorm", "CrossPredictor", "AllPredAR")
+
+
+def reference_train_model(oracle_net, books: int, K: int):
+    """The reference's AllPredAR (Training/compare_dacvsproposal_3.py:284-340) on the oracle model's backbones and
+    parameters (AllPredAR and ProposedEval name their layers alike)."""
+    ns = load_reference_classes(TRAIN_SCRIPT, TRAIN_STEP_WANTED)
+    ns["RVQ_N_BOOKS"], ns["RVQ_EMBED"] = books, K
+    ref = ns["AllPredAR"](oracle_net.A_ENC, oracle_net.A_QUANT, oracle_net.T_ENC, oracle_net.T_DEC, 1024)
+    ref.load_state_dict(oracle_net.state_dict(), strict=True)
+    return ref.eval()
 
 
 METRIC_SCRIPT = os.path.join(REF_ROOT, "Evaluation", "compare_dacvsproposal_5_eval.py")

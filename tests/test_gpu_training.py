@@ -1,0 +1,108 @@
+"""GPU parity of the differentiable path: the decoder's backward-data pass (libb2c.so,
+b2c_prog_conv_dsnake / b2c_prog_head_bwd) against torch.autograd through the oracle decoder, and the training-mode
+forward_step (Training/compare_dacvsproposal_3.py:300-340, :386-409) against the golden the reference's own AllPredAR
+wrote (loss, dL/dz_run, parameter gradients).  Floating point: tolerances below, per precision plan."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_vqvae_compression_audio_tactile_b200 as pkg
+from oracle import cases, dac_arch, proposed
+from oracle import training as otr
+
+pytestmark = pytest.mark.gpu
+
+#: relative L2 error of a gradient tensor.  f32 plan: FP32 FFMA both ways (summation order only).  tc plan: the decoder
+#: runs single-pass bf16 (8 mantissa bits per operand, fp32 accumulate) forward and backward through ~30 layers.
+REL_L2 = {"f32": 2e-4, "tc": 4e-2, "tc_exact": 2e-3}
+COS_MIN = {"f32": 0.999999, "tc": 0.999, "tc_exact": 0.99999}
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("plan", ["f32", "tc", "tc_exact"])
+@pytest.mark.parametrize("B,Tl", [(2, 6), (1, 19)])
+def test_decoder_backward_data_against_oracle_autograd(dev, plan, B, Tl):
+    torch.manual_seed(7)
+    ref = dac_arch.Decoder().eval()
+    for p in ref.parameters():
+        p.requires_grad_(False)
+    dec = pkg.Decoder()
+    dec.load_state_dict(ref.state_dict())
+    dec = dec.to(dev).eval()
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    dec.precision = plan
+    g = torch.Generator().manual_seed(3)
+    z0 = torch.randn(B, 1024, Tl, generator=g) * 2.0
+    zr = z0.clone().requires_grad_(True)
+    yr = ref(zr)
+    w = torch.randn(yr.shape, generator=g)
+    (w * yr).sum().backward()
+    zg = z0.clone().to(dev).requires_grad_(True)
+    yg = dec(zg)
+    assert yg.requires_grad and yg.shape == yr.shape
+    (w.to(dev) * yg).sum().backward()
+    assert zg.grad is not None and zg.grad.shape == zr.grad.shape
+    e, c = rel_l2(zg.grad.cpu(), zr.grad), cosine(zg.grad.cpu(), zr.grad)
+    print(f"decoder dL/dz plan={plan} B={B} Tl={Tl}: rel L2 {e:.3e} cosine {c:.7f}")
+    assert e < REL_L2[plan] and c > COS_MIN[plan]
+    # the differentiable forward is the same function as the no-grad forward (fused units vs two launches per unit)
+    with torch.no_grad():
+        y2 = dec(z0.to(dev))
+    assert rel_l2(yg.detach().cpu(), y2.cpu()) < (1e-6 if plan == "f32" else 2e-2)
+    # no gradient requested: no graph
+    assert not dec(z0.to(dev)).requires_grad
+
+
+@pytest.mark.parametrize("plan", ["f32", "tc"])
+def test_training_forward_step_gradients_against_reference_golden(dev, golden_dir, plan):
+    g = np.load(os.path.join(golden_dir, "train_step.npz"))
+    case = otr.TRAIN_CASE
+    ref = cases.build_reference_style_model(proposed.ProposedEval, case)
+    net = pkg.build_proposed(case["books"], case["K"])
+    net.load_state_dict(ref.state_dict())
+    net = net.to(dev).eval()
+    net.precision = plan
+    a, t = cases.codec_inputs(case)
+    out = net.forward_step(a.to(dev), t.to(dev))
+    assert set(("y_hat", "tgt", "z_teacher", "r_tokens")) <= set(out)
+    out["z_run"].retain_grad()
+    loss = otr.objective(out)
+    loss.backward()
+    y_err = float((out["y_hat"].detach().cpu() - torch.from_numpy(g["y_hat"])).abs().max())
+    print(f"train step plan={plan}: loss {float(loss):.6f} vs {float(g['loss']):.6f}, max|y - y_ref| {y_err:.2e}")
+    assert abs(float(loss) - float(g["loss"])) < (1e-5 if plan == "f32" else 2e-3)
+    assert y_err < (2e-5 if plan == "f32" else 4e-3)
+    e = rel_l2(out["z_run"].grad.cpu(), torch.from_numpy(g["g_z_run"]))
+    print(f"  dL/dz_run rel L2 {e:.3e}")
+    assert e < REL_L2[plan]
+    named = dict(net.named_parameters())
+    for k in otr.GRAD_KEYS:
+        got = named[k].grad.cpu()
+        got = got[..., :32] if got.dim() == 2 else got
+        want = torch.from_numpy(g["grad_" + k])
+        e = rel_l2(got, want)
+        print(f"  grad {k}: rel L2 {e:.3e}")
+        assert e < 2 * REL_L2[plan], k
+    # the frozen backbones received nothing
+    assert all(p.grad is None for p in net.T_DEC.parameters())
+    # without autograd the same call is the fused eval program
+    with torch.no_grad():
+        o2 = net.forward_step(a.to(dev), t.to(dev))
+    assert not o2["y_hat"].requires_grad

@@ -267,3 +267,45 @@ def test_metric_goldens_and_product_tables(golden_dir):
         kp, wp, op_, np_ = pm.sinc_resample_kernel(a, b)
         assert (wo, oo, no) == (wp, op_, np_) and torch.equal(ko[:, 0], kp)
     assert torch.equal(om.mel_filterbank(257, 0.0, 12000.0, 64, 24000), pm.mel_filterbank())
+
+
+# ---------------------------------------------------------------------------------------------
+# training step with autograd
+# ---------------------------------------------------------------------------------------------
+def _train_grad(g, k):
+    return g[..., :32] if g.dim() == 2 else g
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_training_step_restatement_equals_reference_class():
+    """oracle/training.py against the reference's own AllPredAR.forward_step + backward: bit-equal output, loss and
+    parameter gradients."""
+    import warnings
+    from oracle import training as otr
+    case = otr.TRAIN_CASE
+    net = cases.build_reference_style_model(proposed.ProposedEval, case)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_loader.reference_train_model(net, case["books"], case["K"])
+        a, t = cases.codec_inputs(case)
+        out_r = ref.forward_step(a, t)
+        loss_r = otr.objective(out_r)
+        loss_r.backward()
+        g_ref = {k: dict(ref.named_parameters())[k].grad.clone() for k in otr.GRAD_KEYS}
+        loss_o, g_or, _, out_o = otr.run_case(net, case)
+    assert float(loss_r) == loss_o and torch.equal(out_r["y_hat"], out_o["y_hat"])
+    assert torch.equal(out_r["r_tokens"], out_o["r_tokens"])
+    for k in otr.GRAD_KEYS:
+        assert torch.equal(g_ref[k], g_or[k]), k
+
+
+def test_training_step_golden(golden_dir):
+    from oracle import training as otr
+    g = np.load(os.path.join(golden_dir, "train_step.npz"))
+    net = cases.build_reference_style_model(proposed.ProposedEval, otr.TRAIN_CASE)
+    loss, grads, g_z, out = otr.run_case(net, otr.TRAIN_CASE)
+    assert loss == float(g["loss"])
+    np.testing.assert_array_equal(out["y_hat"].detach().numpy(), g["y_hat"])
+    np.testing.assert_array_equal(g_z.numpy(), g["g_z_run"])
+    for k in otr.GRAD_KEYS:
+        np.testing.assert_array_equal(_train_grad(grads[k], k).numpy(), g["grad_" + k])
