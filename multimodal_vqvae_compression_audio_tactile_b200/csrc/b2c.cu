@@ -433,13 +433,24 @@ static bool rvq_one_launch(const b2c_ctx* ctx, const Op& op) {
   return fused && op.type == OP_RVQ && !r.lookup && r.books_use > 0 && op.r[1] != B2C_NULL_REF && (r.D & 3) == 0 && r.D <= 128 &&
          (long)((r.N + 31) / 32) * 2 >= ctx->sm_count;
 }
+// a handful of tokens (batch-1 streaming): one CTA per token walks all the books (rvq_token_f32)
+static bool rvq_per_token(const b2c_ctx* ctx, const Op& op) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B2C_RVQ_TOKEN");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const RvqArgs& r = op.rvq;
+  return on && op.type == OP_RVQ && !r.lookup && r.books_use > 0 && op.r[1] != B2C_NULL_REF && r.D <= 256 && r.N <= 2 * ctx->sm_count;
+}
 // kernel launches one run of the program enqueues (an op can be several launches)
 extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
   if (!p) return 0;
   int n = 0;
   for (const auto& op : p->ops) {
     if (op.type == OP_LANE || op.type == OP_JOIN) continue;   // launch-queue markers
-    if (op.type == OP_RVQ && op.use_rvq_tc) n += 1;
+    if (rvq_per_token(p->ctx, op)) n += 1;
+    else if (op.type == OP_RVQ && op.use_rvq_tc) n += 1;
     else if (rvq_one_launch(p->ctx, op)) n += 1;
     else if (op.type == OP_RVQ && op.r[3] != B2C_NULL_REF && op.rvq.books_use > 0) n += 2 * op.rvq.books_use;   // scores + apply per book
     else if (op.type == OP_NEAREST) {
@@ -1201,7 +1212,9 @@ static int run_ops(b2c_prog* p, cudaStream_t main_st, Resolver& R, cudaEvent_t* 
           const char* e = getenv("B2C_RVQ_SPLIT");
           rvq_split = (e && e[0] == '0') ? 0 : 1;
         }
-        if (op.type == OP_RVQ && op.use_rvq_tc) {
+        if (rvq_per_token(ctx, op)) {
+          rvq_token_f32<<<r.N, 256, 0, st>>>(r);
+        } else if (op.type == OP_RVQ && op.use_rvq_tc) {
           const Weight& w = ctx->w[op.wid];
           RvqTcParams ra;
           memset(&ra, 0, sizeof(ra));
@@ -1278,6 +1291,32 @@ static int run_ops(b2c_prog* p, cudaStream_t main_st, Resolver& R, cudaEvent_t* 
             const long cost = waves * (6 + w);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; warps = w; }
           }
+        }
+        // a handful of tokens (batch-1 streaming): one CTA per token, the stage's serial chain split over 8 warps
+        static int dac_token = -1;
+        if (dac_token < 0) {
+          const char* e = getenv("B2C_DACRVQ_TOKEN");
+          dac_token = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (dac_token && d.C % 256 == 0 && d.N <= 2 * ctx->sm_count) {
+          cudaError_t e = cudaSuccess;
+          switch (d.C / 32) {
+            case 32:
+              e = cudaFuncSetAttribute(dac_rvq_token_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+              if (e == cudaSuccess) dac_rvq_token_f32<32><<<d.N, 256, sm, st>>>(d);
+              break;
+            case 16:
+              e = cudaFuncSetAttribute(dac_rvq_token_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+              if (e == cudaSuccess) dac_rvq_token_f32<16><<<d.N, 256, sm, st>>>(d);
+              break;
+            case 8:
+              e = cudaFuncSetAttribute(dac_rvq_token_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+              if (e == cudaSuccess) dac_rvq_token_f32<8><<<d.N, 256, sm, st>>>(d);
+              break;
+            default: return fail(B2C_ERR_UNSUPPORTED, "dac rvq: latent dim %d not in {256,512,1024}", d.C);
+          }
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "dac rvq smem: %s", cudaGetErrorString(e));
+          break;
         }
         const int blocks = (d.N + tpw * warps - 1) / (tpw * warps);
 #define B2C_DACRVQ(CPL)                                                                                             \

@@ -1046,6 +1046,79 @@ __global__ void __launch_bounds__(256) rvq_books_f32(const RvqArgs p) {
     }
   }
 }
+// Residual VQ for a handful of tokens (batch-1 streaming: 75 tokens, then 4 chunk heads): ONE CTA PER TOKEN walks all
+// the books; thread = code (K / 256 codes each, one fmaf chain over d per code, rows read straight from L2 -- every CTA
+// reads the same 196 KB book), block arg-max (first maximum), then the D threads that own a channel apply
+// q_sum + (q - r) + r and r - q.  Same scores, tie-breaking and op order as rvq_scores_f32 + rvq_apply_f32, so the
+// indices and q_sum are the same bits; the per-book chain of two launches (or one 128-row tensor-core CTA doing
+// everything serially) becomes one launch of N CTAs: 132 -> ~25 us for 75 tokens x 8 books.
+__global__ void __launch_bounds__(256) rvq_token_f32(const RvqArgs p) {
+  __shared__ __align__(16) float r_s[256];
+  __shared__ float red_s[8];
+  __shared__ int red_i[8];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.D, K = p.K;
+  const bool vec = (D & 3) == 0;
+  float r = 0.f, qs = 0.f;
+  if (tid < D) { r = __ldg(p.x + (long)n * D + tid); r_s[tid] = r; }
+  __syncthreads();
+  int b, tt;
+  if (p.row_mode == ROWS_DENSE) { b = n / p.Tl; tt = n - b * p.Tl; }
+  else { b = n / p.nfix; tt = p.chunk * (n - b * p.nfix + 1); }
+  for (int bk = 0; bk < p.books_use; ++bk) {
+    const float* book = p.books + (size_t)bk * K * D;
+    const float* hn = p.half_n + (size_t)bk * K;
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int code = tid; code < K; code += 256) {
+      const float* e = book + (size_t)code * D;
+      float acc = 0.f;
+      if (vec) {
+#pragma unroll 4
+        for (int d = 0; d < D; d += 4) {
+          const float4 ev = __ldg(reinterpret_cast<const float4*>(e + d));
+          const float4 xv = *reinterpret_cast<const float4*>(r_s + d);
+          acc = fmaf(xv.x, ev.x, acc); acc = fmaf(xv.y, ev.y, acc);
+          acc = fmaf(xv.z, ev.z, acc); acc = fmaf(xv.w, ev.w, acc);
+        }
+      } else {
+        for (int d = 0; d < D; ++d) acc = fmaf(r_s[d], __ldg(e + d), acc);
+      }
+      const float sc = __fsub_rn(acc, __ldg(hn + code));
+      if (sc > best) { best = sc; bidx = code; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
+    }
+    if (lane == 0) { red_s[warp] = best; red_i[warp] = bidx; }
+    __syncthreads();
+    best = red_s[0]; bidx = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float os = red_s[w];
+      const int oi = red_i[w];
+      if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
+    }
+    if (bidx >= K) bidx = 0;
+    if (tid < D) {
+      const float q = __ldg(book + (size_t)bidx * D + tid);
+      qs = __fadd_rn(__fadd_rn(qs, __fsub_rn(q, r)), r);
+      r = __fsub_rn(r, q);
+    }
+    if (tid == 0) {
+      if (p.idx_flat) p.idx[n] = bidx;
+      else p.idx[((long)b * p.books_use + bk) * p.Tl + tt] = bidx;
+    }
+    __syncthreads();            // every thread has read r_s and the reduction slots of this book
+    if (tid < D) r_s[tid] = r;
+    __syncthreads();
+  }
+  if (tid < D) p.qsum[(long)n * D + tid] = qs;
+}
+
 // Receiver side of the residual VQ: the code indices are given, qsum[n] = sum_b book_b[idx[b][n]] (books in order, plain
 // fp32 adds).  One warp per token; the index layout is the one rvq_apply_f32 / rvq_books_f32 write.
 __global__ void __launch_bounds__(256) rvq_lookup_f32(const RvqArgs p) {
@@ -1274,6 +1347,128 @@ __global__ void __launch_bounds__(32 * DACRVQ_MAX_WARPS, 1) dac_rvq_f32(const Da
 #pragma unroll
       for (int i = 0; i < CPL; ++i) p.zq[(long)(n0 + u) * C + lane + 32 * i] = zq[u][i];
     }
+}
+
+// The same 32 stages for a handful of tokens (batch-1 streaming: 75): ONE CTA (8 warps) PER TOKEN, so the serial chain of
+// a stage is split eight ways -- warp = output dimension of in_proj (the same 32-term per-lane sums and shuffle tree as
+// above), thread = 4 codes of the search, thread = C/256 channels of out_proj -- instead of one warp walking ~1600
+// dependent instructions per stage.  Stage weights stream through the same double-buffered shared-memory tile.  Every
+// value is computed with the arithmetic and order of dac_rvq_f32: same codes, same z_q bits (0.19 -> ~0.05 ms at 75 tokens).
+template <int CPL>
+__global__ void __launch_bounds__(256, 1) dac_rvq_token_f32(const DacRvqArgs p) {
+  extern __shared__ __align__(16) float wsm[];
+  __shared__ float r_s[32 * CPL];
+  __shared__ float ze_s[8];
+  __shared__ float red_s[8];
+  __shared__ int red_i[8];
+  constexpr int CPT = CPL / 8;            // channels per thread of out_proj (C / 256)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x;
+  const int C = p.C, K = p.K;
+  const int staged = 17 * C + 9 * K + 8;
+  const int bb = n / p.Tl, tt = n - bb * p.Tl;
+  float r[CPT], zq[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    r[j] = __ldg(p.z + (long)n * C + tid + 256 * j);
+    zq[j] = 0.f;
+    r_s[tid + 256 * j] = r[j];
+  }
+  auto prefetch = [&](int st, int buf) {
+    const float4* src = reinterpret_cast<const float4*>(p.w + (long)st * p.stage_stride);
+    float4* dst = reinterpret_cast<float4*>(wsm + (long)buf * staged);
+    for (int i = tid; i < staged / 4; i += 256) cp_async16(dst + i, src + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
+  for (int st = 0; st < p.n_q; ++st) {
+    if (st + 1 < p.n_q) {
+      prefetch(st + 1, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                       // stage weights landed; r_s of the previous stage complete
+    const float* Win = wsm + (long)(st & 1) * staged;
+    const float* bin = Win + 8 * C;
+    const float* cbnT = bin + 8;
+    const float* c2 = cbnT + 8 * K;
+    const float* WoutT = c2 + K;
+    const float* bout = WoutT + 8 * C;
+    const float* cb = p.w + (long)st * p.stage_stride + staged;
+    {  // in_proj: warp = dimension
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) s = fmaf(Win[warp * C + lane + 32 * i], r_s[lane + 32 * i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) ze_s[warp] = __fadd_rn(s, bin[warp]);
+    }
+    __syncthreads();
+    float ze[8], en2[8], e2;
+    {
+      float nn = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { ze[d] = ze_s[d]; nn = fmaf(ze[d], ze[d], nn); }
+      const float den = fmaxf(sqrtf(nn), 1e-12f);
+      float en[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) en[d] = __fdiv_rn(ze[d], den);
+      e2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) e2 = __fadd_rn(e2, __fmul_rn(en[d], en[d]));
+#pragma unroll
+      for (int d = 0; d < 8; ++d) en2[d] = 2.f * en[d];
+    }
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = tid; k < K; k += 256) {
+      float dot = en2[0] * cbnT[k];
+#pragma unroll
+      for (int d = 1; d < 8; ++d) dot = fmaf(en2[d], cbnT[d * K + k], dot);
+      const float dist = __fadd_rn(__fsub_rn(e2, dot), c2[k]);
+      if (dist < best) { best = dist; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
+    }
+    if (lane == 0) { red_s[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    best = red_s[0]; bi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float os = red_s[w];
+      const int oi = red_i[w];
+      if (os < best || (os == best && oi < bi)) { best = os; bi = oi; }
+    }
+    if (bi >= K) bi = 0;
+    if (tid == 0) p.codes[((long)bb * p.n_q + st) * p.Tl + tt] = bi;
+    float stv[8];
+    {
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (long)bi * 8 + 4));
+      const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int d = 0; d < 8; ++d) stv[d] = __fadd_rn(ze[d], __fsub_rn(qv[d], ze[d]));
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int c = tid + 256 * j;
+      float o = WoutT[c] * stv[0];
+#pragma unroll
+      for (int d = 1; d < 8; ++d) o = fmaf(WoutT[d * C + c], stv[d], o);
+      o = __fadd_rn(o, bout[c]);
+      zq[j] = __fadd_rn(zq[j], o);
+      r[j] = __fsub_rn(r[j], o);
+      r_s[c] = r[j];
+    }
+    __syncthreads();   // r_s complete for the next stage; this weight buffer may be refilled
+  }
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) p.zq[(long)n * C + tid + 256 * j] = zq[j];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1002,17 +1002,20 @@ class ProposedEval(_Top):
 # ------------------------------------------------------------------------------------------
 class _VQStraightThrough(torch.autograd.Function):
     """ResidualVQEMA.forward under autograd (Training/compare_dacvsproposal_3.py:253-262): the value is the CUDA
-    kernel's q_sum (same op order as ``q_sum + (q - residual).detach() + residual``), the gradient w.r.t. z is the
-    identity, the codebooks get none (they move by ema_step)."""
+    kernel's q_sum (same op order as ``q_sum + (q - residual).detach() + residual``).  Gradient: every stage adds its
+    ``residual`` un-detached and ``residual - q`` keeps the identity w.r.t. z (q comes from detached codebooks), so the
+    reference's d q_sum / d z is ``n_books`` times the identity -- reproduced here as it is; the codebooks get no gradient
+    (they move by ema_step)."""
 
     @staticmethod
     def forward(ctx, z, vq):
+        ctx.n_books = len(vq.books)
         with torch.no_grad():
             return vq(z)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None
+        return g * ctx.n_books, None
 
 
 def _predict_autograd(pr: "CrossPredictor", zt_prev, za):

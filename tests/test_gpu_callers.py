@@ -203,3 +203,34 @@ def test_tcgen05_residual_vq_equals_fp32_kernels(D, K, books, dev):
     eng, wid = vq._engine(dev)
     progs = [p for k, p in eng.programs._d.items() if k[0] == "vq" and k[-1] != 0]
     assert progs and all(p.info["launches"] <= 4 for p in progs), [p.info["launches"] for p in progs]
+
+
+def test_small_batch_token_kernels_equal_large_batch_kernels(dev):
+    """The one-CTA-per-token kernels of the batch-1 streaming path (rvq_token_f32, dac_rvq_token_f32: up to 296 tokens)
+    give the bits of the kernels larger batches select, on the same rows: residual VQ (with duplicated codewords:
+    the first must win) and the 32-stage DAC quantizer."""
+    g = torch.Generator().manual_seed(5)
+    D, K, books = 96, 512, 8
+    vq = pkg.ResidualVQEMA(dim=D, n_books=books, n_embed=K).to(dev)
+    with torch.no_grad():
+        for i, b in enumerate(vq.books):
+            e = torch.randn(K, D, generator=g) / D ** 0.5 * (0.7 ** i)
+            e[K // 2:K // 2 + 8] = e[:8]
+            b.copy_(e.to(dev))
+    z = (torch.randn(64, D, 75, generator=g) / D ** 0.5).to(dev)
+    z[:, :, 0] = vq.books[0][3].detach()[None, :]
+    for plan in ("f32", "tc"):
+        vq.precision = plan
+        q_big, i_big = vq(z, return_indices=True)
+        for nb in (1, 3):
+            q_s, i_s = vq(z[:nb], return_indices=True)
+            assert torch.equal(i_s, i_big[:nb]) and torch.equal(q_s, q_big[:nb]), (plan, nb)
+        assert int(i_big[:, 0, 0].max()) == 3 and int(i_big[:, 0, 0].min()) == 3      # the first of the duplicates
+    torch.manual_seed(7)
+    aq = pkg.ResidualVectorQuantize().to(dev)
+    za = torch.randn(8, 1024, 75, generator=g).to(dev) * 2.0
+    zq_big, codes_big, *_ = aq(za)
+    for nb in (1, 3):
+        zq_s, codes_s, *_ = aq(za[:nb])
+        assert torch.equal(codes_s, codes_big[:nb]) and torch.equal(zq_s, zq_big[:nb]), nb
+    assert len(torch.unique(codes_big)) > 32
