@@ -441,7 +441,7 @@ static bool rvq_per_token(const b2c_ctx* ctx, const Op& op) {
     on = (e && e[0] == '0') ? 0 : 1;
   }
   const RvqArgs& r = op.rvq;
-  return on && op.type == OP_RVQ && !r.lookup && r.books_use > 0 && op.r[1] != B2C_NULL_REF && r.D <= 256 && r.N <= 2 * ctx->sm_count;
+  return on && op.type == OP_RVQ && !r.lookup && r.books_use > 0 && op.r[1] != B2C_NULL_REF && (r.D & 3) == 0 && r.D <= 196 && r.N <= 2 * ctx->sm_count;
 }
 // kernel launches one run of the program enqueues (an op can be several launches)
 extern "C" int b2c_prog_num_launches(const b2c_prog* p) {
@@ -1213,7 +1213,11 @@ static int run_ops(b2c_prog* p, cudaStream_t main_st, Resolver& R, cudaEvent_t* 
           rvq_split = (e && e[0] == '0') ? 0 : 1;
         }
         if (rvq_per_token(ctx, op)) {
-          rvq_token_f32<<<r.N, 256, 0, st>>>(r);
+          const size_t tile = (size_t)RVQT_TILE * (r.D + 4) * sizeof(float);
+          const int nbuf = 2 * tile <= 200 * 1024 ? 2 : 1;
+          cudaError_t e = cudaFuncSetAttribute(rvq_token_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbuf * tile));
+          if (e != cudaSuccess) return fail(B2C_ERR_CUDA, "rvq smem: %s", cudaGetErrorString(e));
+          rvq_token_f32<<<r.N, 256, nbuf * tile, st>>>(r, nbuf);
         } else if (op.type == OP_RVQ && op.use_rvq_tc) {
           const Weight& w = ctx->w[op.wid];
           RvqTcParams ra;

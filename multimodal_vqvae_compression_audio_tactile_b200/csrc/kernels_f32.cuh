@@ -1047,74 +1047,95 @@ __global__ void __launch_bounds__(256) rvq_books_f32(const RvqArgs p) {
   }
 }
 // Residual VQ for a handful of tokens (batch-1 streaming: 75 tokens, then 4 chunk heads): ONE CTA PER TOKEN walks all
-// the books; thread = code (K / 256 codes each, one fmaf chain over d per code, rows read straight from L2 -- every CTA
-// reads the same 196 KB book), block arg-max (first maximum), then the D threads that own a channel apply
-// q_sum + (q - r) + r and r - q.  Same scores, tie-breaking and op order as rvq_scores_f32 + rvq_apply_f32, so the
-// indices and q_sum are the same bits; the per-book chain of two launches (or one 128-row tensor-core CTA doing
-// everything serially) becomes one launch of N CTAs: 132 -> ~25 us for 75 tokens x 8 books.
-__global__ void __launch_bounds__(256) rvq_token_f32(const RvqArgs p) {
+// the books.  The codes stream through shared memory in tiles of 256 (coalesced cp.async, double buffered across tiles
+// and books; thread-per-row reads straight from global memory cost one L1 tag look-up per lane and load: 9 us per
+// book); thread = code: one fmaf chain over d per code from a padded, conflict-free row, block arg-max (first maximum)
+// at the end of a book, then the D threads that own a channel apply q_sum + (q - r) + r and r - q.  Same scores,
+// tie-breaking and op order as rvq_scores_f32 + rvq_apply_f32: the indices and q_sum are the same bits.
+constexpr int RVQT_TILE = 256;
+__global__ void __launch_bounds__(256) rvq_token_f32(const RvqArgs p, int nbuf) {
+  extern __shared__ __align__(16) float rvqt_sm[];
   __shared__ __align__(16) float r_s[256];
   __shared__ float red_s[8];
   __shared__ int red_i[8];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, K = p.K;
-  const bool vec = (D & 3) == 0;
+  const int DP = D + 4, D4 = D >> 2;                    // staged path: D % 4 == 0
   float r = 0.f, qs = 0.f;
   if (tid < D) { r = __ldg(p.x + (long)n * D + tid); r_s[tid] = r; }
-  __syncthreads();
   int b, tt;
   if (p.row_mode == ROWS_DENSE) { b = n / p.Tl; tt = n - b * p.Tl; }
   else { b = n / p.nfix; tt = p.chunk * (n - b * p.nfix + 1); }
-  for (int bk = 0; bk < p.books_use; ++bk) {
-    const float* book = p.books + (size_t)bk * K * D;
-    const float* hn = p.half_n + (size_t)bk * K;
-    float best = -INFINITY;
-    int bidx = 0x7fffffff;
-    for (int code = tid; code < K; code += 256) {
-      const float* e = book + (size_t)code * D;
+  const int tiles_per_book = (K + RVQT_TILE - 1) / RVQT_TILE;
+  const int n_tiles = p.books_use * tiles_per_book;
+  auto stage = [&](int t) {          // tile t of the (book, tile) sequence -> buffer t % nbuf
+    const int bk = t / tiles_per_book, c0 = (t - bk * tiles_per_book) * RVQT_TILE;
+    const int rows = min(RVQT_TILE, K - c0);
+    const float* src = p.books + ((size_t)bk * K + c0) * D;
+    float* dst = rvqt_sm + (size_t)(t % nbuf) * RVQT_TILE * DP;
+    for (int i = tid; i < rows * D4; i += 256) {
+      const int row = i / D4, u = i - row * D4;
+      cp_async16(dst + row * DP + 4 * u, src + (size_t)row * D + 4 * u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0);
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int bk = t / tiles_per_book, ti = t - bk * tiles_per_book;
+    if (nbuf == 2 && t + 1 < n_tiles) {
+      stage(t + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                 // tile t landed; r_s holds this book's residual
+    const int code = ti * RVQT_TILE + tid;
+    if (code < K) {
+      const float* e = rvqt_sm + (size_t)(t % nbuf) * RVQT_TILE * DP + (size_t)tid * DP;
       float acc = 0.f;
-      if (vec) {
 #pragma unroll 4
-        for (int d = 0; d < D; d += 4) {
-          const float4 ev = __ldg(reinterpret_cast<const float4*>(e + d));
-          const float4 xv = *reinterpret_cast<const float4*>(r_s + d);
-          acc = fmaf(xv.x, ev.x, acc); acc = fmaf(xv.y, ev.y, acc);
-          acc = fmaf(xv.z, ev.z, acc); acc = fmaf(xv.w, ev.w, acc);
-        }
-      } else {
-        for (int d = 0; d < D; ++d) acc = fmaf(r_s[d], __ldg(e + d), acc);
+      for (int d = 0; d < D; d += 4) {
+        const float4 ev = *reinterpret_cast<const float4*>(e + d);
+        const float4 xv = *reinterpret_cast<const float4*>(r_s + d);
+        acc = fmaf(xv.x, ev.x, acc); acc = fmaf(xv.y, ev.y, acc);
+        acc = fmaf(xv.z, ev.z, acc); acc = fmaf(xv.w, ev.w, acc);
       }
-      const float sc = __fsub_rn(acc, __ldg(hn + code));
+      const float sc = __fsub_rn(acc, __ldg(p.half_n + (size_t)bk * K + code));
       if (sc > best) { best = sc; bidx = code; }
     }
+    if (ti == tiles_per_book - 1) {  // end of a book: arg-max over the CTA, apply
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
-    }
-    if (lane == 0) { red_s[warp] = best; red_i[warp] = bidx; }
-    __syncthreads();
-    best = red_s[0]; bidx = red_i[0];
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
+      }
+      if (lane == 0) { red_s[warp] = best; red_i[warp] = bidx; }
+      __syncthreads();               // also: every thread is done reading r_s and this tile
+      best = red_s[0]; bidx = red_i[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) {
-      const float os = red_s[w];
-      const int oi = red_i[w];
-      if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
+      for (int w = 1; w < 8; ++w) {
+        const float os = red_s[w];
+        const int oi = red_i[w];
+        if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
+      }
+      if (bidx >= K) bidx = 0;
+      if (tid < D) {
+        const float q = __ldg(p.books + ((size_t)bk * K + bidx) * D + tid);
+        qs = __fadd_rn(__fadd_rn(qs, __fsub_rn(q, r)), r);
+        r = __fsub_rn(r, q);
+        r_s[tid] = r;
+      }
+      if (tid == 0) {
+        if (p.idx_flat) p.idx[n] = bidx;
+        else p.idx[((long)b * p.books_use + bk) * p.Tl + tt] = bidx;
+      }
+      best = -INFINITY; bidx = 0x7fffffff;
     }
-    if (bidx >= K) bidx = 0;
-    if (tid < D) {
-      const float q = __ldg(book + (size_t)bidx * D + tid);
-      qs = __fadd_rn(__fadd_rn(qs, __fsub_rn(q, r)), r);
-      r = __fsub_rn(r, q);
-    }
-    if (tid == 0) {
-      if (p.idx_flat) p.idx[n] = bidx;
-      else p.idx[((long)b * p.books_use + bk) * p.Tl + tt] = bidx;
-    }
-    __syncthreads();            // every thread has read r_s and the reduction slots of this book
-    if (tid < D) r_s[tid] = r;
-    __syncthreads();
+    __syncthreads();                 // tile t is free (the next stage() call of either scheme overwrites it); r_s updated
+    if (nbuf == 1 && t + 1 < n_tiles) stage(t + 1);
   }
   if (tid < D) p.qsum[(long)n * D + tid] = qs;
 }

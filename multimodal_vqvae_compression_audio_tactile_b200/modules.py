@@ -982,9 +982,9 @@ class ProposedEval(_Top):
             z_pred = _predict_autograd(self.predict, zt_prev, qa[..., s0:e0])
             r = zt_teacher[..., s0:e0] - z_pred.detach()
             rN = torch.tanh(_tokennorm_autograd(self.tokennorm, r))
-            rD = self.proj_down(self.scale.clamp(5e-3, 0.5) * rN)
+            rD = _conv1x1_autograd(self.proj_down, self.scale.clamp(5e-3, 0.5) * rN)
             qD = _VQStraightThrough.apply(rD, self.vq)
-            z_hat = z_pred + self.proj_up(qD)
+            z_hat = z_pred + _conv1x1_autograd(self.proj_up, qD)
             chunks.append(z_hat)
             rD_all.append(rD.detach())
         z_run = torch.cat(chunks, dim=-1)
@@ -1039,6 +1039,12 @@ def _predict_autograd(pr: "CrossPredictor", zt_prev, za):
     y = F.linear(pr.drop(ctx.permute(0, 2, 1, 3).contiguous().view(b, t, h * d)), pr.out.weight)
     y = pr.ffn(y + q) + (y + q)
     return y.permute(0, 2, 1)
+
+
+def _conv1x1_autograd(conv: nn.Conv1d, x):
+    """nn.Conv1d(k=1) as a plain fp32 matmul: cuDNN convolutions run in TF32 by default (torch.backends.cudnn.allow_tf32),
+    which would put 10-bit operands into the gradients of proj_down / proj_up."""
+    return torch.matmul(conv.weight[:, :, 0], x) + conv.bias[None, :, None]
 
 
 def _tokennorm_autograd(tn: "TokenNorm", z):
