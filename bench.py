@@ -8,7 +8,8 @@ A step = one forward_eval over one batch of synthetic 1-s frames (24 kHz) per GP
 independent, so N GPUs run N independent shards (weak scaling, no collective on the hot path; the
 code indices are gathered ONCE, after the timed steps).  One JSON line is printed by rank 0; besides the
 contract's keys it carries `latency` (config 4: batch-1 p50/p99), `search` (config 5 corners, rows sharded
-over the GPUs), `strong_scaling` (fixed global batch, N > 1) and `torch_gpu_baseline` (context).
+over the GPUs), `strong_scaling` (fixed global batch, N > 1), `torch_gpu_baseline`, `train_step` (forward_step +
+backward through the CUDA decoder) and `eval_metrics` (alignment / PSNR / ST-SIM kernels) as context.
 """
 from __future__ import annotations
 
@@ -266,6 +267,61 @@ def torch_gpu_leg(torch, ref, dev, frames=16, reps=3):
     return out
 
 
+def train_leg(torch, net, dev, frames=6, reps=5):
+    """Context leg: one training-mode forward_step + backward (Training/compare_dacvsproposal_3.py:
+    386-409, BATCH = 6, 1-s frames): frozen backbones and residual VQ in libb2c.so, T_DEC forward AND backward-data in
+    libb2c.so, the 9 M-parameter trainable layers through autograd.  ms per step, CUDA events."""
+    out = {"frames": frames, "unit": "ms per forward_step + backward"}
+    try:
+        g = torch.Generator().manual_seed(5)
+        a = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
+        t = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
+
+        def step():
+            for p_ in net.parameters():
+                p_.grad = None
+            o = net.forward_step(a, t)
+            torch.nn.functional.l1_loss(o["y_hat"], o["tgt"]).backward()
+
+        with torch.enable_grad():
+            step(); step()
+            torch.cuda.synchronize()
+            ms = sorted(_event_times(torch, step, reps))
+        out["ms"] = ms[len(ms) // 2]
+        out["signal_s_per_s"] = frames / (out["ms"] / 1e3)
+        with torch.no_grad():
+            net.forward_eval(a, t)
+            torch.cuda.synchronize()
+            out["forward_eval_ms"] = sorted(_event_times(torch, lambda: net.forward_eval(a, t), reps))[reps // 2]
+        for p_ in net.parameters():
+            p_.grad = None
+        torch.cuda.empty_cache()
+    except Exception as e:   # context only: never fails the bench
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
+
+
+def metrics_leg(torch, dev, frames=64, reps=10):
+    """Context leg: the evaluation metrics of Evaluation/compare_dacvsproposal_5_eval.py on `frames`
+    decoded frames: 401-shift alignment + 24k->3k resample + PSNR (psnr_3k_aligned_batch) and ST-SIM."""
+    from multimodal_vqvae_compression_audio_tactile_b200 import metrics as pm
+    out = {"frames": frames, "samples": 23992, "unit": "ms per batch"}
+    try:
+        g = torch.Generator().manual_seed(6)
+        r = (torch.rand(frames, 1, 23992, generator=g) - 0.5).to(dev)
+        e = (torch.roll(r, 17, dims=-1) * 0.9).contiguous()
+        for name, fn in (("psnr_3k_aligned_ms", lambda: pm.psnr_3k_aligned_tensor(r, e)),
+                         ("stsim_ms", lambda: pm.stsim_tensor(r, e)), ("psnr_ms", lambda: pm.psnr_tensor(r, e))):
+            fn(); fn()
+            torch.cuda.synchronize()
+            v = sorted(_event_times(torch, fn, reps))
+            out[name] = v[len(v) // 2]
+        out["best_shift"] = int(pm.psnr_3k_aligned_tensor(r, e)[1][0])
+    except Exception as e_:
+        out["error"] = f"{type(e_).__name__}: {e_}"[:200]
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -474,6 +530,8 @@ def main():
                                          f"fp32 torch CPU ({sum(ts):.1f} s)"}
     if not args.no_extras:
         out["torch_gpu_baseline"] = torch_gpu_leg(torch, ref, dev)
+        out["train_step"] = train_leg(torch, net, dev)
+        out["eval_metrics"] = metrics_leg(torch, dev)
     print(json.dumps(out), flush=True)
 
 

@@ -93,13 +93,19 @@ def test_training_forward_step_gradients_against_reference_golden(dev, golden_di
     print(f"  dL/dz_run rel L2 {e:.3e}")
     assert e < REL_L2[plan]
     named = dict(net.named_parameters())
+    bad = []
     for k in otr.GRAD_KEYS:
         got = named[k].grad.cpu()
         got = got[..., :32] if got.dim() == 2 else got
         want = torch.from_numpy(g["grad_" + k])
         e = rel_l2(got, want)
-        print(f"  grad {k}: rel L2 {e:.3e}")
-        assert e < 2 * REL_L2[plan], k
+        # `scale` is ONE number: the sum of ~10^5 signed terms that cancel to a few per cent of their magnitude, so the
+        # bf16 decoder's 1 % gradient noise shows up amplified in it; tensors are compared in relative L2
+        tol = 2 * REL_L2[plan] if want.numel() > 1 else (1e-4 if plan == "f32" else 0.3)
+        print(f"  grad {k}: rel L2 {e:.3e} (tol {tol:.0e})")
+        if not e < tol:
+            bad.append((k, e))
+    assert not bad, bad
     # the frozen backbones received nothing
     assert all(p.grad is None for p in net.T_DEC.parameters())
     # without autograd the same call is the fused eval program
