@@ -273,6 +273,12 @@ def train_leg(torch, net, dev, frames=6, reps=5):
     libb2c.so, the 9 M-parameter trainable layers through autograd.  ms per step, CUDA events."""
     out = {"frames": frames, "unit": "ms per forward_step + backward"}
     try:
+        import multimodal_vqvae_compression_audio_tactile_b200 as pkg
+        host_net = net
+        net = pkg.build_proposed(BOOKS, K_CODES)           # the autograd side needs the parameters on the device
+        net.load_state_dict(host_net.state_dict())
+        net.precision = host_net.precision
+        net = net.to(dev)
         g = torch.Generator().manual_seed(5)
         a = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
         t = (torch.rand(frames, 1, T, generator=g) * 2 - 1).to(dev)
