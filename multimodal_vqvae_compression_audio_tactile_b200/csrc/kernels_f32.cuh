@@ -75,9 +75,12 @@ __device__ __forceinline__ float snake_sfu(float v, float alpha, float inv) {
   return fmaf(inv, s * s, v);
 }
 // SFU = 1 only where the activation is stored as a single bf16 plane
+#ifndef B2C_SNAKE_SFU_X3
+#define B2C_SNAKE_SFU_X3 1     // 1 = MUFU.SIN snake in the bf16x3 epilogues too (0: the polynomial)
+#endif
 template <int SFU>
 __device__ __forceinline__ float snake_sel(float v, float alpha, float inv) {
-  return SFU ? snake_sfu(v, alpha, inv) : snake_fast(v, alpha, inv);
+  return (SFU || B2C_SNAKE_SFU_X3) ? snake_sfu(v, alpha, inv) : snake_fast(v, alpha, inv);
 }
 
 // d/dx snake(x) = 1 + sin(2 alpha x) * alpha / (alpha + 1e-9): the factor of the decoder's backward-data pass

@@ -30,6 +30,10 @@ struct TcRuParams {
   // bounds the 64-channel bf16x3 units (ncu: ~7 TB/s of L2 reads at 20 % tensor activity).
   int slab;
   uint32_t slab_plane_bytes; // slab_rows * BK * 2
+  // W1 resident in shared memory for the whole kernel (loaded once; C = 64 / 96: 16 / 18 KB).  GEMM 2 then needs no
+  // ring stage, so the MMA warp may issue it BETWEEN two ring stages of the next tile's GEMM 1, as soon as h is in
+  // shared memory: epilogue B of a tile no longer waits for the whole GEMM 1 of its successor to be issued first.
+  int w1_resident;
 };
 
 // Timeline trace (B2C_TC_DEBUG bit 8, timing experiments only): CTA 0 records (tag, tile, SM clock) of its pipeline
@@ -143,6 +147,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_hempty;
   __shared__ __align__(8) uint64_t bar_afull[2];
   __shared__ __align__(8) uint64_t bar_aempty[2];
+  __shared__ __align__(8) uint64_t bar_w1;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
@@ -154,7 +159,9 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t ring_bytes = stage_bytes * (uint32_t)p.stages;
   const uint32_t slab_slot = q.slab_plane_bytes * planes;
   const uint32_t slab_u32 = smem0 + ring_bytes;                       // two slab slots (slab mode), then h, then staging
-  const uint32_t pre_h = ring_bytes + (q.slab ? 2u * slab_slot : 0u);
+  const uint32_t w1_block = p.b_bytes * planes;                      // one K block of W1: hi plane, then lo plane
+  const uint32_t w1_u32 = smem0 + ring_bytes + (q.slab ? 2u * slab_slot : 0u);
+  const uint32_t pre_h = ring_bytes + (q.slab ? 2u * slab_slot : 0u) + (q.w1_resident ? w1_block * (uint32_t)q.nk : 0u);
   const uint32_t hbuf_u32 = smem0 + pre_h;                            // 1024-aligned (all pieces are multiples of 1 KB)
   uint8_t* hbuf = smem_raw + (smem0 - smem_u32(smem_raw)) + pre_h;
   const uint32_t h_total = q.h_plane_bytes * planes;
@@ -169,6 +176,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     mbar_init(smem_u32(&bar_hfull), 1); mbar_init(smem_u32(&bar_hempty), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aempty[i]), 1); }
+    mbar_init(smem_u32(&bar_w1), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -207,6 +215,14 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (X3) tma_load_3d(dst + q.slab_plane_bytes, &tmA_lo, full, cb * p.BK, jt * TC_BM + p.in_off[0], b);
         ra.next(2);
       };
+      if (q.w1_resident && my_tiles > 0) {
+        const uint32_t full = smem_u32(&bar_w1);
+        mbar_expect_tx(full, w1_block * (uint32_t)q.nk);
+        for (int kb = 0; kb < q.nk; ++kb) {
+          tma_load_2d(w1_u32 + kb * w1_block, &tmB1_hi, full, kb * p.BK, 0);
+          if (X3) tma_load_2d(w1_u32 + kb * w1_block + p.b_bytes, &tmB1_lo, full, kb * p.BK, 0);
+        }
+      }
       const int total_steps = my_tiles * q.nk;
       if (q.slab && total_steps > 0) issue_slab(0);
       auto produce_conv7_slab = [&](int i) {
@@ -254,6 +270,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       };
       auto produce_w1 = [&](int i) {
+        if (q.w1_resident) return;
         for (int k0 = 0; k0 < q.nk; k0 += p.kgroup, rg.next(p.stages)) {
           const int cnt = min(p.kgroup, q.nk - k0);
           const uint32_t s = rg.s;
@@ -296,6 +313,30 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       else if (ksteps == 2) umma_ksteps<X3, 2>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
       else umma_ksteps<X3, 1>(d, a_lo, b_lo, apl, b_plane, desc_hi, idesc, first);
     };
+    // GEMM 2 of tile i with W1 resident: no ring stage involved, so it may be issued anywhere in the MMA stream
+    int g2_next = 0;                                   // first tile whose GEMM 2 has not been issued yet
+    auto gemm2_resident = [&](int i) {
+      const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+      mbar_wait(smem_u32(&bar_t2empty[buf]), par ^ 1u, 6);
+      tc_fence_after();
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 14, i);
+      const uint32_t d = tmem_base + (q.nbuf + buf) * p.acc_stride;
+      for (int kb = 0; kb < q.nk; ++kb) {
+        const uint32_t ha = hbuf_u32 + (uint32_t)kb * q.h_block_bytes;
+        issue(d, (ha & 0x3FFFFu) >> 4, ((w1_u32 + kb * w1_block) & 0x3FFFFu) >> 4, h_plane, kb != 0);
+      }
+      umma_commit_w(smem_u32(&bar_hempty));
+      umma_commit_w(smem_u32(&bar_t2full[buf]));
+      if (lane == 0) ru_trace(p.dbg, 1, tcnt, 16, i);
+    };
+    // between two ring stages of GEMM 1 (tile i1): has the epilogue finished h of the oldest pending tile?
+    auto poll_g2 = [&](int i1) {
+      if (!q.w1_resident || g2_next >= i1) return;
+      if (!__any_sync(0xffffffffu, mbar_test_wait(smem_u32(&bar_hfull), (uint32_t)g2_next & 1u))) return;
+      tc_fence_after();
+      gemm2_resident(g2_next);
+      ++g2_next;
+    };
     auto gemm1 = [&](int i) {
       const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
       mbar_wait(smem_u32(&bar_t1empty[buf]), par ^ 1u, 3);
@@ -318,6 +359,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               issue(d, slab_lo + (uint32_t)(k0 + g) * tap_step, (sb & 0x3FFFFu) >> 4, slab_plane, (cb | (k0 + g)) != 0);
             }
             umma_commit_w(smem_u32(&bar_empty[s]));
+            poll_g2(i);
           }
           umma_commit_w(smem_u32(&bar_aempty[sa]));
         }
@@ -335,11 +377,20 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           issue(d, (sa & 0x3FFFFu) >> 4, ((sa + p.a_bytes * planes) & 0x3FFFFu) >> 4, a_plane, (k0 + g) != 0);
         }
         umma_commit_w(smem_u32(&bar_empty[s]));
+        if (k0 + p.kgroup < n7) poll_g2(i);
       }
       umma_commit_w(smem_u32(&bar_t1full[buf]));
       if (lane == 0) ru_trace(p.dbg, 1, tcnt, 12, i);
     };
     auto gemm2 = [&](int i) {
+      if (q.w1_resident) {
+        if (i < g2_next) return;                                       // already issued inside GEMM 1 of a later tile
+        mbar_wait(smem_u32(&bar_hfull), (uint32_t)i & 1u, 5);
+        tc_fence_after();
+        gemm2_resident(i);
+        g2_next = i + 1;
+        return;
+      }
       const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
       mbar_wait(smem_u32(&bar_hfull), (uint32_t)i & 1u, 5);           // h(i) is in shared memory
       if (lane == 0) ru_trace(p.dbg, 1, tcnt, 13, i);
@@ -364,6 +415,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       umma_commit_w(smem_u32(&bar_t2full[buf]));
       if (lane == 0) ru_trace(p.dbg, 1, tcnt, 16, i);
     };
+    if (q.w1_resident && my_tiles > 0) { mbar_wait(smem_u32(&bar_w1), 0u, 13); tc_fence_after(); }
     for (int i = 0; i < la && i < my_tiles; ++i) gemm1(i);
     for (int i = 0; i < my_tiles; ++i) {
       if (i + la < my_tiles) gemm1(i + la);
@@ -519,6 +571,16 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
     if (e && e[0] == '1') want_slab = true;
     if (e && e[0] == '0') want_slab = false;
   }
+  // W1 resident + early GEMM 2 (see TcRuParams::w1_resident): where W1 is small against the ring.  B2C_RU_W1RES=0/1.
+  // Measured on B200 at 64 frames: C = 64 bf16x3 0.535 -> 0.498 ms (dilation 1, 3; at dilation 9 the larger slabs leave the
+  // ring too few stages: 0.517 -> 0.582, not selected), C = 96 bf16 0.549 -> 0.511 with 3 K blocks per ring stage.
+  bool want_w1 = ((C == 64 && dil <= 3) || C == 96) && 4 * p.acc_stride <= 512;
+  {
+    const char* e = getenv("B2C_RU_W1RES");
+    if (e && e[0] == '0') want_w1 = false;
+    if (e && e[0] == '1') want_w1 = 4 * p.acc_stride <= 512;
+  }
+  q.w1_resident = want_w1 ? 1 : 0;
   bool done = false;
   int force_bk = 0, force_g = 0;                  // experiment knobs
   {
@@ -543,7 +605,7 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
       q.slab_plane_bytes = slab ? (uint32_t)slab_rows * bk * 2 : 0u;
       p.slab_rows = slab_rows; p.box_rows = slab ? slab_rows : TC_BM;
       const uint32_t sub = (slab ? 0u : p.a_bytes * planes) + p.b_bytes * planes;
-      const int fixed = h_total + (slab ? 2 * (int)q.slab_plane_bytes * planes : 0);
+      const int fixed = h_total + (slab ? 2 * (int)q.slab_plane_bytes * planes : 0) + (q.w1_resident ? C * C * 2 * planes : 0);
       const int avail2 = 232448 - 2048 - 1024 - fixed - TC_STG_BYTES;
       const int avail1 = avail2 + TC_STG_BYTES / 2;
       int subs = avail2 / (int)sub;
@@ -556,6 +618,7 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
       if (g > 8) g = 8;
       if (slab && g > 7) g = 7;
       while (g > 1 && subs / g < 2) --g;
+      if (q.w1_resident && C == 96 && !plan->x3 && g > 3) g = 3;
       if (force_g > 0 && force_g <= subs) g = force_g;
       p.kgroup = g;
       p.stages = subs / g;

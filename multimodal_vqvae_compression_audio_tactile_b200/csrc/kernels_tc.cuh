@@ -71,8 +71,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 #endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (clock64() - t0 < 3000000000LL)   // ~1.5 s at 1.9 GHz
+  while (clock64() - t0 < 3000000000LL) { // ~1.5 s at 1.9 GHz
+#ifdef B2C_WAIT_NAP
+    __nanosleep(B2C_WAIT_NAP);            // experiment: sleep between polls (power of the waiting warps vs wake-up latency)
+#endif
     if (mbar_try_wait(bar, parity)) return;
+  }
   printf("b2c conv_tc: mbarrier timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x);
   __trap();
 }
