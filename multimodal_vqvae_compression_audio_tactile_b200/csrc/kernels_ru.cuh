@@ -34,6 +34,19 @@ struct TcRuParams {
   // ring stage, so the MMA warp may issue it BETWEEN two ring stages of the next tile's GEMM 1, as soon as h is in
   // shared memory: epilogue B of a tile no longer waits for the whole GEMM 1 of its successor to be issued first.
   int w1_resident;
+  // W7 resident as well (C = 64 bf16x3: 7 taps x [W_hi ; W_lo] = 112 KB + W1 16 KB, loaded ONCE per CTA): there is no
+  // weight ring at all -- the TMA producer streams activation slabs only (BK = 32: two half-channel slabs per tile in
+  // two slots, so the next slab always loads while the current one is multiplied) and the MMA warp issues the 28 K
+  // steps of a slab back to back.  Removes the 176 KB of L2 -> shared-memory weight traffic per tile and every ring
+  // hand-off of GEMM 1.
+  int w7_resident;
+  // direct epilogue B (C = 64 bf16x3, C = 96 bf16): the residual tile x[128 x C] arrives by TMA (two buffers, requested
+  // two tiles ahead), a thread owns one output row (its TMEM lane): y = acc2 + b1 + x is written back IN PLACE into
+  // the swizzled residual tile and snake_next(y) as bf16 plane(s) into the h buffer (free once GEMM 2 has read it);
+  // one elected thread hands both to the copy engine (cp.async.bulk.tensor stores).  No staging transpose, no
+  // per-thread global address arithmetic, no row predicates (the tensor map clips the tile tail).
+  int direct;
+  uint32_t r_bytes;          // one residual tile: 128 * C * 4
 };
 
 // Timeline trace (B2C_TC_DEBUG bit 8, timing experiments only): CTA 0 records (tag, tile, SM clock) of its pipeline
@@ -129,11 +142,73 @@ __device__ __forceinline__ void ru_epilogue_h_g(const TcRuParams& q, uint32_t t_
   }
 }
 
+// direct epilogue B of one tile (see TcRuParams::direct).  16 warps: warp = (TMEM lane quadrant, quarter of the
+// channels); thread = one output row, C / 4 channels in 8-channel units.
+template <int X3>
+__device__ __forceinline__ void ru_epilogue_direct(const TcRuParams& q, uint32_t t_acc, uint8_t* rbuf, uint8_t* hbuf,
+                                                   int warp, int lane) {
+  const TcConvParams& p = q.e;
+  const int quad = warp & 3, cg = (warp - 2) >> 2;
+  const int r = quad * 32 + lane;
+  const int cpw = p.Cout >> 2;                               // channels per warp column group
+  const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16);
+  const uint32_t swr = (uint32_t)r & 7u, swh = ((uint32_t)r >> 1) & 3u;
+  for (int u = 0; u < (cpw >> 3); ++u) {
+    const int c0 = cg * cpw + 8 * u;
+    float v[8];
+    tmem_ld8(t_src + c0, v);
+    if (p.pair_off) {
+      float v2[8];
+      tmem_ld8(t_src + p.pair_off + c0, v2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += v2[e];
+    }
+    const float4 b0 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b1 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // residual: fp32 tile of 32-channel boxes, 128-byte rows, 16-byte units XOR-swizzled by (row & 7)
+    uint8_t* rrow = rbuf + (uint32_t)(c0 >> 5) * (TC_BM * 128u) + (uint32_t)r * 128u;
+    const uint32_t un = ((uint32_t)c0 & 31u) >> 2;
+    float4* x0 = reinterpret_cast<float4*>(rrow + (((un) ^ swr) << 4));
+    float4* x1 = reinterpret_cast<float4*>(rrow + (((un + 1u) ^ swr) << 4));
+    float4 y0 = *x0, y1 = *x1;
+    y0.x += v[0] + b0.x; y0.y += v[1] + b0.y; y0.z += v[2] + b0.z; y0.w += v[3] + b0.w;
+    y1.x += v[4] + b1.x; y1.y += v[5] + b1.y; y1.z += v[6] + b1.z; y1.w += v[7] + b1.w;
+    *x0 = y0; *x1 = y1;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.alpha + c0)), a1 = __ldg(reinterpret_cast<const float4*>(p.alpha + c0 + 4));
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + c0)), i1 = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + c0 + 4));
+    float w[8];
+    w[0] = snake_sel<!X3>(y0.x, a0.x, i0.x); w[1] = snake_sel<!X3>(y0.y, a0.y, i0.y);
+    w[2] = snake_sel<!X3>(y0.z, a0.z, i0.z); w[3] = snake_sel<!X3>(y0.w, a0.w, i0.w);
+    w[4] = snake_sel<!X3>(y1.x, a1.x, i1.x); w[5] = snake_sel<!X3>(y1.y, a1.y, i1.y);
+    w[6] = snake_sel<!X3>(y1.z, a1.z, i1.z); w[7] = snake_sel<!X3>(y1.w, a1.w, i1.w);
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(w[2 * e], w[2 * e + 1]);
+    // activation plane(s): bf16 tile of 32-channel boxes, 64-byte rows, 16-byte units XOR-swizzled by ((row >> 1) & 3)
+    uint8_t* hrow = hbuf + (uint32_t)(c0 >> 5) * (TC_BM * 64u) + (uint32_t)r * 64u + (((((uint32_t)c0 & 31u) >> 3) ^ swh) << 4);
+    *reinterpret_cast<uint4*>(hrow) = make_uint4(*reinterpret_cast<const uint32_t*>(&h[0]), *reinterpret_cast<const uint32_t*>(&h[1]),
+                                                 *reinterpret_cast<const uint32_t*>(&h[2]), *reinterpret_cast<const uint32_t*>(&h[3]));
+    if (X3) {
+      __nv_bfloat162 l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        l[e] = __floats2bfloat162_rn(w[2 * e] - f.x, w[2 * e + 1] - f.y);
+      }
+      *reinterpret_cast<uint4*>(hrow + q.h_plane_bytes) =
+          make_uint4(*reinterpret_cast<const uint32_t*>(&l[0]), *reinterpret_cast<const uint32_t*>(&l[1]),
+                     *reinterpret_cast<const uint32_t*>(&l[2]), *reinterpret_cast<const uint32_t*>(&l[3]));
+    }
+  }
+}
+
 template <int X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB7_hi, const __grid_constant__ CUtensorMap tmB7_lo,
                const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRaw,
+               const __grid_constant__ CUtensorMap tmOutHi, const __grid_constant__ CUtensorMap tmOutLo,
                const __grid_constant__ TcRuParams q) {
   const TcConvParams& p = q.e;
   extern __shared__ uint8_t smem_raw[];
@@ -148,6 +223,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_afull[2];
   __shared__ __align__(8) uint64_t bar_aempty[2];
   __shared__ __align__(8) uint64_t bar_w1;
+  __shared__ __align__(8) uint64_t bar_rfull[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
@@ -159,9 +235,11 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t ring_bytes = stage_bytes * (uint32_t)p.stages;
   const uint32_t slab_slot = q.slab_plane_bytes * planes;
   const uint32_t slab_u32 = smem0 + ring_bytes;                       // two slab slots (slab mode), then h, then staging
-  const uint32_t w1_block = p.b_bytes * planes;                      // one K block of W1: hi plane, then lo plane
-  const uint32_t w1_u32 = smem0 + ring_bytes + (q.slab ? 2u * slab_slot : 0u);
-  const uint32_t pre_h = ring_bytes + (q.slab ? 2u * slab_slot : 0u) + (q.w1_resident ? w1_block * (uint32_t)q.nk : 0u);
+  const uint32_t w1_block = p.b_bytes * planes;                      // one K block of W1 / W7: hi plane, then lo plane
+  const uint32_t w7_u32 = smem0 + ring_bytes + (q.slab ? 2u * slab_slot : 0u);     // resident W7: block (tap, cb) at (tap * nk + cb)
+  const uint32_t w7_bytes = q.w7_resident ? w1_block * (uint32_t)(p.KT * q.nk) : 0u;
+  const uint32_t w1_u32 = w7_u32 + w7_bytes;
+  const uint32_t pre_h = ring_bytes + (q.slab ? 2u * slab_slot : 0u) + w7_bytes + (q.w1_resident ? w1_block * (uint32_t)q.nk : 0u);
   const uint32_t hbuf_u32 = smem0 + pre_h;                            // 1024-aligned (all pieces are multiples of 1 KB)
   uint8_t* hbuf = smem_raw + (smem0 - smem_u32(smem_raw)) + pre_h;
   const uint32_t h_total = q.h_plane_bytes * planes;
@@ -177,6 +255,8 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     mbar_init(smem_u32(&bar_hfull), 1); mbar_init(smem_u32(&bar_hempty), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aempty[i]), 1); }
     mbar_init(smem_u32(&bar_w1), 1);
+    mbar_init(smem_u32(&bar_rfull[0]), 1); mbar_init(smem_u32(&bar_rfull[1]), 1);
+    if (q.direct) { tma_prefetch_desc(&tmRes); tma_prefetch_desc(&tmRaw); tma_prefetch_desc(&tmOutHi); if (X3) tma_prefetch_desc(&tmOutLo); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -217,7 +297,14 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       };
       if (q.w1_resident && my_tiles > 0) {
         const uint32_t full = smem_u32(&bar_w1);
-        mbar_expect_tx(full, w1_block * (uint32_t)q.nk);
+        mbar_expect_tx(full, w1_block * (uint32_t)q.nk + w7_bytes);
+        if (q.w7_resident)
+          for (int k = 0; k < p.KT; ++k)
+            for (int cb = 0; cb < q.nk; ++cb) {
+              const uint32_t dst = w7_u32 + (uint32_t)(k * q.nk + cb) * w1_block;
+              tma_load_2d(dst, &tmB7_hi, full, cb * p.BK, k * p.Cout);
+              if (X3) tma_load_2d(dst + p.b_bytes, &tmB7_lo, full, cb * p.BK, k * p.Cout);
+            }
         for (int kb = 0; kb < q.nk; ++kb) {
           tma_load_2d(w1_u32 + kb * w1_block, &tmB1_hi, full, kb * p.BK, 0);
           if (X3) tma_load_2d(w1_u32 + kb * w1_block + p.b_bytes, &tmB1_lo, full, kb * p.BK, 0);
@@ -229,6 +316,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int cb = 0; cb < q.nk; ++cb) {
           const int step = i * q.nk + cb;
           if (step + 1 < total_steps) issue_slab(step + 1);
+          if (q.w7_resident) continue;                 // no weight ring
           for (int k0 = 0; k0 < p.KT; k0 += p.kgroup, rg.next(p.stages)) {
             const int cnt = min(p.kgroup, p.KT - k0);
             const uint32_t s = rg.s;
@@ -349,6 +437,15 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(smem_u32(&bar_afull[sa]), ra.par, 12);
           tc_fence_after();
           const uint32_t slab_lo = ((slab_u32 + sa * slab_slot) & 0x3FFFFu) >> 4;
+          if (q.w7_resident) {
+            for (int k = 0; k < p.KT; ++k) {
+              const uint32_t wb = w7_u32 + (uint32_t)(k * q.nk + cb) * w1_block;
+              issue(d, slab_lo + (uint32_t)k * tap_step, (wb & 0x3FFFFu) >> 4, slab_plane, (cb | k) != 0);
+            }
+            umma_commit_w(smem_u32(&bar_aempty[sa]));
+            if (cb + 1 < q.nk) poll_g2(i);
+            continue;
+          }
           for (int k0 = 0; k0 < p.KT; k0 += p.kgroup, rg.next(p.stages)) {
             const int cnt = min(p.kgroup, p.KT - k0);
             const uint32_t s = rg.s;
@@ -425,7 +522,64 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== epilogue warps =====================
     float* stg = reinterpret_cast<float*>(hbuf + h_total);
     uint32_t chunk_ctr = 0;
-    if (q.nbuf == 2 && p.epi_groups == 2) {
+    if (q.direct) {
+      // lock-step epilogue, residual in / outputs out through the copy engine
+      uint8_t* rbase = hbuf + h_total;                                    // two residual tiles
+      const uint32_t rbase_u32 = hbuf_u32 + h_total;
+      const bool elected = threadIdx.x == 64;
+      const int nbox = p.Cout >> 5;
+      auto load_res = [&](int i) {                                        // elected thread only
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+        const uint32_t full = smem_u32(&bar_rfull[i & 1]);
+        mbar_expect_tx(full, q.r_bytes);
+        for (int bx = 0; bx < nbox; ++bx)
+          tma_load_3d(rbase_u32 + (uint32_t)(i & 1) * q.r_bytes + (uint32_t)bx * (TC_BM * 128u), &tmRes, full, bx * 32, jt * TC_BM, b);
+      };
+      if (elected) {
+        if (my_tiles > 0) load_res(0);
+        if (my_tiles > 1) load_res(1);
+      }
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / p.tiles_j, jt = tile - b * p.tiles_j;
+        const uint32_t buf = (uint32_t)(i % q.nbuf), par = (uint32_t)(i / q.nbuf) & 1u;
+        // ---- A: acc1 -> h   (h is free: GEMM 2 of tile i-1 has read it [t2full(i-1)], the copy engine has read the
+        //                      activation tile staged in it [bulk wait + barrier at the end of the previous iteration])
+        mbar_wait(smem_u32(&bar_t1full[buf]), par, 8);
+        tc_fence_after();
+        ru_epilogue_h<X3>(q, tmem_base + buf * p.acc_stride, hbuf, warp, lane);
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (elected) {
+          mbar_arrive(smem_u32(&bar_t1empty[buf]));
+          mbar_arrive(smem_u32(&bar_hfull));
+        }
+        // ---- B: acc2 (+ b1 + x) -> y in place, snake_next(y) -> planes in the h buffer
+        mbar_wait(smem_u32(&bar_t2full[buf]), par, 10);
+        mbar_wait(smem_u32(&bar_rfull[i & 1]), (uint32_t)(i >> 1) & 1u, 14);
+        tc_fence_after();
+        ru_epilogue_direct<X3>(q, tmem_base + (q.nbuf + buf) * p.acc_stride, rbase + (size_t)(i & 1) * q.r_bytes, hbuf, warp, lane);
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (elected) {
+          mbar_arrive(smem_u32(&bar_t2empty[buf]));
+          const uint32_t rsrc = rbase_u32 + (uint32_t)(i & 1) * q.r_bytes;
+          for (int bx = 0; bx < nbox; ++bx) {
+            if (p.out_raw) tma_store_3d(&tmRaw, rsrc + (uint32_t)bx * (TC_BM * 128u), bx * 32, jt * TC_BM, b);
+            tma_store_3d(&tmOutHi, hbuf_u32 + (uint32_t)bx * (TC_BM * 64u), bx * 32, jt * TC_BM, b);
+            if (X3) tma_store_3d(&tmOutLo, hbuf_u32 + q.h_plane_bytes + (uint32_t)bx * (TC_BM * 64u), bx * 32, jt * TC_BM, b);
+          }
+          bulk_commit();
+          bulk_wait_read0();                                              // the staged tiles have been read
+          if (i + 2 < my_tiles) load_res(i + 2);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");                    // nobody rewrites h before the copy engine has read it
+      }
+      if (elected) bulk_wait0();
+    } else if (q.nbuf == 2 && p.epi_groups == 2) {
       // two independent 8-warp groups: group g serves this CTA's tiles i = g, g + 2, ... (TMEM buffers acc1[g], acc2[g]);
       // epilogue B of tile i then overlaps epilogue A of tile i + 1.  The single h buffer is handed over by hfull / hempty.
       const int g = (warp - 2) >> 3;
@@ -516,6 +670,8 @@ struct TcRuPlan {
   size_t smem = 0;
   const void* cached_x = nullptr;
   CUtensorMap mA_hi, mA_lo, mB7_hi, mB7_lo, mB1_hi, mB1_lo;
+  CUtensorMap mRes, mRaw, mOutHi, mOutLo;     // direct epilogue: residual in, y / activation planes out
+  const void* cached_res = nullptr; const void* cached_raw = nullptr; const void* cached_act = nullptr;
   bool b_ready = false;
 };
 
@@ -582,6 +738,32 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   }
   q.w1_resident = want_w1 ? 1 : 0;
   bool done = false;
+  // All weights resident (TcRuParams::w7_resident): C = 64 bf16x3 with N-stacked planes.  B2C_RU_W7RES=0 off.
+  {
+    const char* e = getenv("B2C_RU_W7RES");
+    const bool want_w7 = C == 64 && plan->x3 && p.pair_off && want_slab && !(e && e[0] == '0');
+    if (want_w7) {
+      const int bk = 32;
+      const int slab_rows = (TC_BM + 6 * dil + 7) / 8 * 8;
+      const int w_bytes = (7 + 1) * (C / bk) * (C * bk * 2 * planes);
+      const int slab2 = 2 * slab_rows * bk * 2 * planes;
+      const int fixed = h_total + slab2 + w_bytes;
+      int stg = 0;
+      if (fixed + TC_STG_BYTES + 1024 + 1024 <= 232448) stg = 2;
+      else if (fixed + TC_STG_BYTES / 2 + 1024 + 1024 <= 232448) stg = 1;
+      if (stg && slab_rows <= 256) {
+        p.BK = bk; q.nk = C / bk; p.n_kblk = q.nk;
+        p.a_bytes = TC_BM * bk * 2; p.b_bytes = C * bk * 2; p.sbo = 8 * bk * 2; p.layout_type = 4u;
+        q.h_block_bytes = TC_BM * bk * 2;
+        q.slab = 1; q.slab_plane_bytes = (uint32_t)slab_rows * bk * 2;
+        p.slab_rows = slab_rows; p.box_rows = slab_rows;
+        p.stg_bufs = stg; p.kgroup = 1; p.stages = 0;
+        q.w1_resident = 1; q.w7_resident = 1;
+        plan->smem = (size_t)fixed + (stg == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
+        done = true;
+      }
+    }
+  }
   int force_bk = 0, force_g = 0;                  // experiment knobs
   {
     const char* e = getenv("B2C_RU_BK");
@@ -589,6 +771,21 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
     e = getenv("B2C_RU_KGROUP");
     if (e) force_g = atoi(e);
   }
+  // direct epilogue B (TcRuParams::direct): residual tiles in / output tiles out through the copy engine.  Needs the
+  // lock-step epilogue (the activation planes are staged in the h buffer) and two residual tiles instead of the staging
+  // transposes.  MEASURED SLOWER on B200 (64 frames): C = 64 bf16x3 0.584 ms against 0.453 (two-group staging epilogue),
+  // C = 96 bf16 0.632 against 0.517 -- with one epilogue group the chain epilogue A -> GEMM 2 -> epilogue B -> store
+  // read-out is serial per tile and shared memory has no room for a second group's tiles.  Kept as an experiment:
+  // B2C_RU_DIRECT=1 (and B2C_RU_W7RES=0 for C = 64) selects it.
+  bool want_direct = false;
+  {
+    const char* e = getenv("B2C_RU_DIRECT");
+    if (e && e[0] == '1') want_direct = q.nbuf == 2 && !q.w7_resident && (out_fmt == FMT_PLANES || out_fmt == FMT_HI) && C * 512 * 2 <= 100 * 1024;
+  }
+  if (out_fmt != (plan->x3 ? FMT_PLANES : FMT_HI)) want_direct = false;
+  q.direct = want_direct ? 1 : 0;
+  q.r_bytes = (uint32_t)TC_BM * C * 4;
+  const int stg2 = q.direct ? 2 * (int)q.r_bytes : TC_STG_BYTES;   // epilogue-B buffers after h
   for (int slab = want_slab ? 1 : 0; slab >= 0 && !done; --slab) {
     for (int bk = (C % 64 == 0 && force_bk != 32) ? 64 : 32; bk >= 32 && !done; bk -= 32) {
       p.BK = bk;
@@ -606,8 +803,8 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
       p.slab_rows = slab_rows; p.box_rows = slab ? slab_rows : TC_BM;
       const uint32_t sub = (slab ? 0u : p.a_bytes * planes) + p.b_bytes * planes;
       const int fixed = h_total + (slab ? 2 * (int)q.slab_plane_bytes * planes : 0) + (q.w1_resident ? C * C * 2 * planes : 0);
-      const int avail2 = 232448 - 2048 - 1024 - fixed - TC_STG_BYTES;
-      const int avail1 = avail2 + TC_STG_BYTES / 2;
+      const int avail2 = 232448 - 2048 - 1024 - fixed - stg2;
+      const int avail1 = q.direct ? -1 : avail2 + TC_STG_BYTES / 2;
       int subs = avail2 / (int)sub;
       p.stg_bufs = 2;
       if (subs < 4 && avail1 > 0 && avail1 / (int)sub > subs) { subs = avail1 / (int)sub; p.stg_bufs = 1; }
@@ -623,14 +820,14 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
       p.kgroup = g;
       p.stages = subs / g;
       if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-      plan->smem = (size_t)p.stages * g * sub + fixed + (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2) + 1024;
+      plan->smem = (size_t)p.stages * g * sub + fixed + (q.direct ? stg2 : (p.stg_bufs == 2 ? TC_STG_BYTES : TC_STG_BYTES / 2)) + 1024;
       done = true;
     }
   }
   if (!done) return 4;
   {
     const char* e = getenv("B2C_TC_EPI2");
-    p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !(e && e[0] == '0')) ? 2 : 1;
+    p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !q.direct && !(e && e[0] == '0')) ? 2 : 1;
   }
   p.tiles_j = (L + TC_BM - 1) / TC_BM;
   p.n_ntiles = 1;
@@ -681,17 +878,39 @@ inline int tc_ru_launch(TcRuPlan& plan, const TcRuArgs& a, const TcWeight& w7, c
     if (rc) return rc;
     plan.b_ready = true;
   }
+  if (q.direct) {
+    if (plan.cached_res != a.x_raw) {
+      int rc = tc_encode_rows32(&plan.mRes, a.x_raw, true, p.B, p.Lout, p.Cout);
+      if (rc) return rc;
+      plan.cached_res = a.x_raw;
+    }
+    if (a.out_raw && plan.cached_raw != a.out_raw) {
+      int rc = tc_encode_rows32(&plan.mRaw, a.out_raw, true, p.B, p.Lout, p.Cout);
+      if (rc) return rc;
+      plan.cached_raw = a.out_raw;
+    }
+    if (plan.cached_act != a.out_act) {
+      const __nv_bfloat16* oh = reinterpret_cast<const __nv_bfloat16*>(a.out_act);
+      int rc = tc_encode_rows32(&plan.mOutHi, oh, false, p.B, p.Lout, p.Cout);
+      if (!rc) rc = tc_encode_rows32(&plan.mOutLo, plan.x3 ? oh + p.act_plane_elems : oh, false, p.B, p.Lout, p.Cout);
+      if (rc) return rc;
+      plan.cached_act = a.out_act;
+    }
+    if (!a.out_raw && !plan.cached_raw) plan.mRaw = plan.mRes;   // never dereferenced (out_raw == null), but a valid map
+  } else if (!plan.cached_res) {
+    plan.mRes = plan.mRaw = plan.mOutHi = plan.mOutLo = plan.mA_hi;   // unused by the kernel in this mode
+  }
   cudaError_t e;
   if (plan.x3) {
     e = cudaFuncSetAttribute(conv_ru_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
     tc_launch(conv_ru_kernel<1>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
-              plan.mB1_hi, plan.mB1_lo, q);
+              plan.mB1_hi, plan.mB1_lo, plan.mRes, plan.mRaw, plan.mOutHi, plan.mOutLo, q);
   } else {
     e = cudaFuncSetAttribute(conv_ru_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return -2;
     tc_launch(conv_ru_kernel<0>, plan.grid, TC_THREADS, plan.smem, st, plan.mA_hi, plan.mA_lo, plan.mB7_hi, plan.mB7_lo,
-              plan.mB1_hi, plan.mB1_lo, q);
+              plan.mB1_hi, plan.mB1_lo, plan.mRes, plan.mRaw, plan.mOutHi, plan.mOutLo, q);
   }
   return 0;
 }

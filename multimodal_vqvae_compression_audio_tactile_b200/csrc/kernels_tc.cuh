@@ -136,6 +136,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// TMA store (shared -> global, bulk async-group completion): the epilogues that stage a whole output tile in shared
+// memory hand it to the copy engine instead of storing from 512 threads
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // K-major, swizzled shared-memory matrix descriptor (sm_100 UMMA): one swizzle atom along K
 // (BK * 2 bytes == swizzle span), 8-row groups SBO bytes apart.  Advancing along K inside the
 // atom = adding bytes to the start address (the swizzle is a function of the address bits).
@@ -1331,6 +1343,21 @@ inline int tc_encode(CUtensorMap* m, const void* base, int rank, const cuuint64_
   CUresult r = tc_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                               strides_b, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 100;
+}
+
+// [B, L, C] channel-last tensor (fp32 or bf16) as a 3-D map with a {32 channels, 128 rows, 1} box: 128-byte rows
+// (fp32, SWIZZLE_128B) or 64-byte rows (bf16, SWIZZLE_64B).  Rows past L are clipped on store and zero-filled on load.
+inline int tc_encode_rows32(CUtensorMap* m, const void* base, bool f32, int B, int L, int C) {
+  const cuuint64_t es_b = f32 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t str[2] = {(cuuint64_t)C * es_b, (cuuint64_t)L * C * es_b};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = tc_encode_fn()(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                              const_cast<void*>(base), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 100;
 }
