@@ -20,6 +20,7 @@ namespace b2c {
 
 constexpr int RVQ_TC_THREADS = 192;
 constexpr int RVQ_TC_MAX_BOOKS = 16;
+constexpr int RVQ_TC_MAXC = 32;          // exact re-score candidates per ambiguous row handled by the warp (one per lane)
 
 struct RvqTcParams {
   const float* x;         // [N, D] fp32 rows
@@ -58,6 +59,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   uint8_t* abuf = sm0;
   float* rs = reinterpret_cast<float*>(sm0 + a_bytes + (size_t)p.stages * p.b_stage_bytes);   // [128][D + 1] fp32 residual
   float* hn_s = rs + TC_BM * (p.D + 1);                                                       // [K] 0.5|e|^2 of the book
+  int* cand_s = reinterpret_cast<int*>(hn_s + p.K);                                            // [128][RVQ_TC_MAXC] candidate codes
   const int DP = p.D + 1;
 
   if (warp == 0 && lane == 0) {
@@ -168,47 +170,110 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       mbar_wait(smem_u32(&bar_sfull), (uint32_t)bk & 1u, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      // ---- pass 1: tensor-core arg-max with runner-up
-      float best = -INFINITY, second = -INFINITY;
-      int bidx = 0;
-      for (int c = 0; c < p.K; c += 16) {
-        float v[16];
-        tmem_ld16(t_row + c, v);
+      // ---- pass 1: tensor-core arg-max with runner-up.  32 columns per TMEM load, two independent (best, runner-up)
+      // chains (even / odd columns) so the compare-select dependences overlap; hn_s read as float4.
+      float b0 = -INFINITY, s0 = -INFINITY, b1 = -INFINITY, s1 = -INFINITY;
+      int i0 = 0, i1 = 1;
+      for (int c = 0; c < p.K; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32_issue(t_row + c, raw);
+        float hn[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float sc = __fsub_rn(v[i], hn_s[c + i]);
-          second = fmaxf(second, fminf(best, sc));
-          if (sc > best) { best = sc; bidx = c + i; }
+        for (int u = 0; u < 8; ++u) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hn_s + c + 4 * u);
+          hn[4 * u] = h4.x; hn[4 * u + 1] = h4.y; hn[4 * u + 2] = h4.z; hn[4 * u + 3] = h4.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float sa = __fsub_rn(__uint_as_float(raw[i]), hn[i]);
+          const float sb = __fsub_rn(__uint_as_float(raw[i + 1]), hn[i + 1]);
+          s0 = fmaxf(s0, fminf(b0, sa));
+          if (sa > b0) { b0 = sa; i0 = c + i; }
+          s1 = fmaxf(s1, fminf(b1, sb));
+          if (sb > b1) { b1 = sb; i1 = c + i + 1; }
         }
       }
+      const bool take1 = b1 > b0 || (b1 == b0 && i1 < i0);
+      const float best = take1 ? b1 : b0;
+      const float second = fmaxf(fmaxf(s0, s1), take1 ? b0 : b1);
+      int bidx = take1 ? i1 : i0;
       // error bound of a bf16x3 score: 3 * 2^-16 |x||e| (hi.lo, lo.hi rounding, dropped lo.lo) -- doubled and rounded
       // up to 2^-13 |x| max|e|, the tolerance nearest_finalize_rows uses
       const float tol = 1.220703125e-4f * sqrtf(xn2 * 1.0001f * __ldg(p.emax2 + bk)) + 1e-30f;
       const bool amb = live && (best - second < tol);
-      if (__any_sync(0xffffffffu, amb)) {
-        // ---- pass 2 (rare): every candidate within tol of the maximum, re-scored exactly, first maximum wins
+      unsigned amb_mask = __ballot_sync(0xffffffffu, amb);
+      if (amb_mask) {
+        // ---- pass 2 (a few rows per warp and book): every candidate within tol of the maximum is re-scored exactly.
+        // One more sweep over the warp's TMEM lanes collects each ambiguous row's candidates (ascending code order) in
+        // shared memory; then the WARP re-scores one row at a time, lane j = candidate j: the FP32 kernel's arithmetic
+        // (one fmaf chain over d from 0, minus 0.5|e|^2) with the 24 codeword loads of a chain independent of each
+        // other, and a shuffle arg-max with the smaller code winning ties (= first maximum).  A row with more than
+        // RVQ_TC_MAXC candidates falls back to re-scoring in its own lane.
         const float* book = p.books + (size_t)bk * p.K * p.D;
-        float ebest = -INFINITY;
-        int eidx = bidx;
-        for (int c = 0; c < p.K; c += 16) {
-          float v[16];
-          tmem_ld16(t_row + c, v);                        // warp-collective: all lanes load, ambiguous lanes act
+        int* my_c = cand_s + row * RVQ_TC_MAXC;
+        int nc = 0;
+        for (int c = 0; c < p.K; c += 32) {
+          uint32_t raw[32];
+          tmem_ld32_issue(t_row + c, raw);                // warp-collective: all lanes load, ambiguous lanes act
+          tmem_ld_wait();
           if (!amb) continue;
-#pragma unroll 1
-          for (int i = 0; i < 16; ++i) {
-            if (__fsub_rn(v[i], hn_s[c + i]) < best - tol) continue;
-            const float* e = book + (size_t)(c + i) * p.D;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (__fsub_rn(__uint_as_float(raw[i]), hn_s[c + i]) >= best - tol) {
+              if (nc < RVQ_TC_MAXC) my_c[nc] = c + i;
+              ++nc;
+            }
+          }
+        }
+        __syncwarp();
+        const bool overflow = amb && nc > RVQ_TC_MAXC;
+        if (overflow) {                                   // pathological: exact arg-max over the whole book in this lane
+          float ebest = -INFINITY;
+          int eidx = bidx;
+          for (int k = 0; k < p.K; ++k) {
+            const float* e = book + (size_t)k * p.D;
             float acc = 0.f;
             for (int d = 0; d < p.D; d += 4) {
               const float4 e4 = __ldg(reinterpret_cast<const float4*>(e + d));
               acc = fmaf(rr[d], e4.x, acc); acc = fmaf(rr[d + 1], e4.y, acc);
               acc = fmaf(rr[d + 2], e4.z, acc); acc = fmaf(rr[d + 3], e4.w, acc);
             }
-            const float sc = __fsub_rn(acc, hn_s[c + i]);
-            if (sc > ebest) { ebest = sc; eidx = c + i; }
+            const float sc = __fsub_rn(acc, hn_s[k]);
+            if (sc > ebest) { ebest = sc; eidx = k; }
           }
+          bidx = eidx;
         }
-        if (amb) bidx = eidx;
+        amb_mask = __ballot_sync(0xffffffffu, amb && !overflow);
+        while (amb_mask) {
+          const int src = __ffs(amb_mask) - 1;
+          amb_mask &= amb_mask - 1;
+          const int n_c = __shfl_sync(0xffffffffu, nc, src);
+          const int srow = (warp & 3) * 32 + src;
+          const float* rsrc = rs + srow * DP;
+          float sc = -INFINITY;
+          int code = 0x7fffffff;
+          if (lane < n_c) {
+            code = cand_s[srow * RVQ_TC_MAXC + lane];
+            const float4* e = reinterpret_cast<const float4*>(book + (size_t)code * p.D);
+            float acc = 0.f;
+            for (int d = 0; d < p.D; d += 16) {
+              const float4 e0 = __ldg(e + (d >> 2)), e1 = __ldg(e + (d >> 2) + 1), e2 = __ldg(e + (d >> 2) + 2), e3 = __ldg(e + (d >> 2) + 3);
+              acc = fmaf(rsrc[d], e0.x, acc); acc = fmaf(rsrc[d + 1], e0.y, acc); acc = fmaf(rsrc[d + 2], e0.z, acc); acc = fmaf(rsrc[d + 3], e0.w, acc);
+              acc = fmaf(rsrc[d + 4], e1.x, acc); acc = fmaf(rsrc[d + 5], e1.y, acc); acc = fmaf(rsrc[d + 6], e1.z, acc); acc = fmaf(rsrc[d + 7], e1.w, acc);
+              acc = fmaf(rsrc[d + 8], e2.x, acc); acc = fmaf(rsrc[d + 9], e2.y, acc); acc = fmaf(rsrc[d + 10], e2.z, acc); acc = fmaf(rsrc[d + 11], e2.w, acc);
+              acc = fmaf(rsrc[d + 12], e3.x, acc); acc = fmaf(rsrc[d + 13], e3.y, acc); acc = fmaf(rsrc[d + 14], e3.z, acc); acc = fmaf(rsrc[d + 15], e3.w, acc);
+            }
+            sc = __fsub_rn(acc, hn_s[code]);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float so = __shfl_xor_sync(0xffffffffu, sc, o);
+            const int co = __shfl_xor_sync(0xffffffffu, code, o);
+            if (so > sc || (so == sc && co < code)) { sc = so; code = co; }
+          }
+          if (lane == src) bidx = code;
+        }
       }
       tc_fence_before();
       // ---- codeword gather, q_sum = q_sum + (q - r) + r, r = r - q, planes of the new residual
@@ -217,6 +282,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
         const float* q_row = p.books + ((size_t)bk * p.K + bidx) * p.D;
         float* qs_row = p.qsum + (size_t)n * p.D;
         const bool last = bk + 1 == p.books_use;
+#pragma unroll 4                                       // D / 8 is a multiple of 4: the codeword / q_sum loads of 4 units are in flight together
         for (int c0 = 0; c0 < p.D; c0 += 8) {
           const float4 qa = __ldg(reinterpret_cast<const float4*>(q_row + c0)), qb = __ldg(reinterpret_cast<const float4*>(q_row + c0 + 4));
           const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
@@ -318,7 +384,7 @@ inline int rvq_tc_plan(int N, int D, int K, int n_books, int books_use, RvqTcPla
   p.sbo = 8 * p.BK * 2;
   p.layout_type = p.BK == 64 ? 2u : 4u;
   p.tmem_cols = K <= 64 ? 64 : (K <= 128 ? 128 : (K <= 256 ? 256 : 512));
-  const long fixed = 2L * p.a_plane_bytes + (long)TC_BM * (D + 1) * 4 + (long)K * 4 + 1024 + 256;
+  const long fixed = 2L * p.a_plane_bytes + (long)TC_BM * (D + 1) * 4 + (long)K * 4 + (long)TC_BM * RVQ_TC_MAXC * 4 + 1024 + 256;
   bool ok = false;
   for (int bn = K >= 128 ? 128 : 64; bn >= 64 && !ok; bn >>= 1) {
     if (K % bn) continue;
