@@ -401,6 +401,57 @@ def test_fused_residual_unit_matches_separate_launches(dev):
         assert float((res[True][1] - res[False][1]).abs().max()) < (2e-2 if prec == "bf16" else 1e-4), (C_, prec)
 
 
+def test_fused_unit_kernel_variants_agree(dev):
+    """The fused unit's pipeline variants -- all weights resident (C = 64 bf16x3), W1 resident + early GEMM 2, everything
+    through the ring, and the TMA-store epilogue B (B2C_RU_DIRECT=1) -- compute the same contraction with the same
+    epilogue arithmetic; only the order of the K blocks differs (slab mode sums channel blocks outermost), i.e. fp32
+    round-off for bf16x3 and one bf16 ulp of h for the single-pass decoder units.  Ragged tile tails (L % 128 != 0)."""
+    from multimodal_vqvae_compression_audio_tactile_b200 import _lib as L
+    from multimodal_vqvae_compression_audio_tactile_b200.engine import Emitter, Engine, _pack_ru
+    torch.manual_seed(4)
+    net = pkg.build_proposed(1, 128)
+    eng = Engine(dev)
+    knobs = ("B2C_RU_W7RES", "B2C_RU_W1RES", "B2C_RU_DIRECT")
+    variants = ({}, {"B2C_RU_W7RES": "0"}, {"B2C_RU_W7RES": "0", "B2C_RU_W1RES": "0"}, {"B2C_RU_W7RES": "0", "B2C_RU_DIRECT": "1"})
+    units = [(net.T_ENC.block[1].block[i], 1000 + 37 * i, "bf16x3") for i in range(3)] + \
+            [(net.T_DEC.model[4].block[2 + i], 777 + 50 * i, "bf16") for i in range(3)]
+    saved = {k: os.environ.get(k) for k in knobs}
+    try:
+        for mod, Lx, prec in units:
+            ru = _pack_ru(eng, mod)
+            C_, B = ru.c7.cout, 3
+            pr = L.PRECISIONS[prec]
+            f = L.FMT_OF_PREC[pr]
+            n = B * Lx * C_
+            x = (torch.rand(B, Lx, C_, device=dev) * 2 - 1)
+            a_next = eng.pack_vec(torch.rand(C_) + 0.5)
+            outs = []
+            for env in variants:
+                for k in knobs:
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                em = Emitter(eng)
+                xa, ya = em.new(n), em.new(n)
+                em.convert(em.ext(1), L.FMT_F32, xa, f, n)
+                L.check(eng.lib.b2c_prog_ru(em.h, ru.c7.wid, ru.a2, ru.c1.wid, em._r(xa), em._r(em.ext(1)), em._r(em.ext(2)),
+                                            em._r(ya), a_next, B, Lx, ru.c7.dilation, pr, f), "b2c_prog_ru")
+                em.convert(ya, f, em.ext(3), L.FMT_F32, n)
+                prog = em.finish(3)
+                raw, act = torch.full((B, Lx, C_), 7.0, device=dev), torch.full((B, Lx, C_), 7.0, device=dev)
+                eng.run(prog, [x.data_ptr(), raw.data_ptr(), act.data_ptr()])
+                torch.cuda.synchronize()
+                outs.append((raw.cpu(), act.cpu()))
+            for env, (raw, act) in zip(variants[1:], outs[1:]):
+                assert float((raw - outs[0][0]).abs().max()) < (2e-3 if prec == "bf16" else 1e-5), (C_, ru.c7.dilation, env)
+                assert float((act - outs[0][1]).abs().max()) < (2e-2 if prec == "bf16" else 1e-4), (C_, ru.c7.dilation, env)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def test_host_entry_pipelined_and_ragged_tail(dev, oracle_models):
     """forward_eval_host: equal micro-batches go through b2c_prog_run_host_pipelined (copy stream overlap), the
     remainder through b2c_prog_run_host; both must give the device entry's bits."""
