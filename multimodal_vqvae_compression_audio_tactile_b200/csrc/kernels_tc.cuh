@@ -307,7 +307,20 @@ struct TcConvParams {
   int pair_off;   // > 0: the accumulator is the sum of two column ranges pair_off apart (N-stacked bf16x3, fused unit)
   int stg_bufs;   // epilogue staging tiles: 2 (one barrier per chunk) or 1 (two barriers, frees 18 KB for the rings)
   uint32_t row_bytes, a_plane_bytes;
+  // frame-packed tiles (generic kernel, short sequences): an M tile is JB consecutive positions of BB consecutive frames
+  // (JB * BB = 128, both powers of two) instead of 128 positions of one frame -- 75 positions per frame fill 59 % of a
+  // 128-row tile, 4 positions x 32 frames fill 99 %.  Row m of a tile = frame (m >> jb_shift), position (m & (JB - 1)):
+  // that is the order in which the TMA box {BK, JB, BB} lands in shared memory, and per-frame zero padding is still the
+  // tensor map's out-of-bounds fill.  JB == 0: the legacy tile (JB = 128, BB = 1).  Rows are independent in an MMA, so
+  // a frame's bits do not depend on how tiles are packed.
+  int JB, jb_shift, BB;
 };
+
+// tile (frame-group index bg, position-tile index jt), row m of the tile -> frame b and position j
+__device__ __forceinline__ void tc_row_coords(const TcConvParams& p, int bg, int jt, int m, int& b, int& j) {
+  if (p.JB == 0) { b = bg; j = jt * 128 + m; }
+  else { b = bg * p.BB + (m >> p.jb_shift); j = jt * p.JB + (m & (p.JB - 1)); }
+}
 
 constexpr int TC_BM = 128;
 constexpr int TC_MAX_STAGES = 8;
@@ -330,10 +343,11 @@ __device__ __forceinline__ void tc_prefetch_res(const TcConvParams& p, int b, in
   const int lines_per_row = p.BN >> 5;                       // 128-byte lines of one tile row
   for (int idx = et; idx < TC_BM * lines_per_row; idx += 32 * TC_EPI_WARPS) {
     const int row = idx / lines_per_row, seg = idx - row * lines_per_row;
-    const int j = jt * TC_BM + row;
+    int br, j;
+    tc_row_coords(p, b, jt, row, br, j);
     const int lo = j * p.out_step + p.out_off[ph];
-    if (j < p.Lj && lo >= 0 && lo < p.Lout) {
-      const float* a = p.res + ((size_t)b * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
+    if (j < p.Lj && br < p.B && lo >= 0 && lo < p.Lout) {
+      const float* a = p.res + ((size_t)br * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
   }
@@ -358,11 +372,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcConvParams& p, float* s
   size_t orow[2], rrow[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const int j = jt * TC_BM + r0 + 64 * i;
+    int br, j;
+    tc_row_coords(p, b, jt, r0 + 64 * i, br, j);
     const int lo = j * p.out_step + p.out_off[ph];
-    valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+    valid[i] = (j < p.Lj) && (br < p.B) && (lo >= 0) && (lo < p.Lout);
     const int los = valid[i] ? lo : 0;
-    orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
+    orow[i] = ((size_t)(valid[i] ? br : 0) * p.Lout + los) * p.Cout;
     rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
   }
   const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + cg8 * 8;
@@ -461,10 +476,11 @@ __device__ __forceinline__ void tc_prefetch_res_g(const TcConvParams& p, int b, 
   const int lines_per_row = p.BN >> 5;
   for (int idx = et; idx < TC_BM * lines_per_row; idx += 256) {
     const int row = idx / lines_per_row, seg = idx - row * lines_per_row;
-    const int j = jt * TC_BM + row;
+    int br, j;
+    tc_row_coords(p, b, jt, row, br, j);
     const int lo = j * p.out_step + p.out_off[ph];
-    if (j < p.Lj && lo >= 0 && lo < p.Lout) {
-      const float* a = p.res + ((size_t)b * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
+    if (j < p.Lj && br < p.B && lo >= 0 && lo < p.Lout) {
+      const float* a = p.res + ((size_t)br * p.Lout + lo) * p.Cout + nt * p.BN + seg * 32;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
   }
@@ -484,11 +500,12 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
   size_t orow[4], rrow[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int j = jt * TC_BM + r0 + 32 * i;
+    int br, j;
+    tc_row_coords(p, b, jt, r0 + 32 * i, br, j);
     const int lo = j * p.out_step + p.out_off[ph];
-    valid[i] = (j < p.Lj) && (lo >= 0) && (lo < p.Lout);
+    valid[i] = (j < p.Lj) && (br < p.B) && (lo >= 0) && (lo < p.Lout);
     const int los = valid[i] ? lo : 0;
-    orow[i] = ((size_t)b * p.Lout + los) * p.Cout;
+    orow[i] = ((size_t)(valid[i] ? br : 0) * p.Lout + los) * p.Cout;
     rrow[i] = p.res_mode == 1 ? (size_t)((los % p.Tl) % p.chunk) * p.Cout : orow[i];
   }
   const uint32_t t_src = t_acc + ((uint32_t)(quad * 32) << 16) + half * 16;
@@ -685,8 +702,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int jt = mt % p.tiles_j;
         mt /= p.tiles_j;
         const int ph = mt % p.n_phase;
-        const int b = mt / p.n_phase;
-        const int j0 = jt * TC_BM;
+        const int b = (mt / p.n_phase) * (p.JB ? p.BB : 1);        // first frame of the tile
+        const int j0 = jt * (p.JB ? p.JB : TC_BM);
         int tap = 0, cb = 0;
         for (int k0 = 0; k0 < n_kiter; k0 += p.kgroup, rg.next(p.stages)) {
           const int cnt = min(p.kgroup, n_kiter - k0);
@@ -1187,6 +1204,21 @@ inline bool tc_conv_eligible(const TcWeight& w, int cin, int cout, int stride, i
   return true;
 }
 
+// fewest M tiles of the generic kernel for Lj positions x B frames: 128 positions of one frame per tile (jb = 0) or
+// frame-packed tiles of jb positions x 128 / jb frames (TcConvParams::JB)
+inline long tc_best_pack(int Lj, int B, int* jb_out) {
+  long best = (long)B * ((Lj + TC_BM - 1) / TC_BM);
+  *jb_out = 0;
+  const char* e = getenv("B2C_TC_PACK");
+  if (B < 2 || (e && e[0] == '0')) return best;
+  for (int sh = 6; sh >= 0; --sh) {
+    const int jb = 1 << sh, bb = TC_BM >> sh;
+    const long t = (long)((Lj + jb - 1) / jb) * ((B + bb - 1) / bb);
+    if (t < best) { best = t; *jb_out = jb; }
+  }
+  return best;
+}
+
 // returns 0 = planned; >0 = shape not eligible; <0 = error
 inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int out_fmt, int sm_count, TcConvPlan* plan) {
   if (!w.hi) return 1;
@@ -1194,10 +1226,33 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
   if (a.in_step > 1 && (a.dil != 1 || a.Lin % a.in_step != 0)) return 3;
   int bn = largest_bn(a.Cout);
   if (!bn) return 4;
-  // small problems (batch-1 streaming): narrower channel blocks so that more SMs get a tile
+  // Channel-block width against wave quantisation: a layer with few tiles (short sequences, batch-1 streaming) runs
+  // ceil(tiles / SMs) rounds of tile time, so a narrower block can win although its MMAs are less efficient
+  // (75 positions x 64 frames, 1024 channels: 152 tiles of N = 256 take 2 rounds of 128 cycles per K step, 304 tiles of
+  // N = 128 take 3 rounds of 64).  Per K step an MMA costs max(N / 2, 32 + N / 4) cycles (tools/micro/umma_rate.cu);
+  // ~1500 cycles per tile for hand-offs and the epilogue's tail.  The bits of an output do not depend on N.
   {
-    const long mtiles = (long)a.B * a.n_phase * ((a.Lj + TC_BM - 1) / TC_BM);
-    while (bn > 64 && (bn / 2) % 32 == 0 && a.Cout % (bn / 2) == 0 && mtiles * (a.Cout / bn) * 2 <= sm_count) bn /= 2;
+    int jb_unused = 0;
+    const long mtiles = tc_best_pack(a.Lj, a.B, &jb_unused) * a.n_phase;
+    const long ksteps = (long)a.KT * (a.Cin / 16) * (precision == 1 ? 3 : 1);
+    long best_cost = -1;
+    int best_bn = bn;
+    for (int c = bn; c >= 64; c /= 2) {
+      if (c % 32 != 0 || a.Cout % c != 0) break;
+      const long tiles = mtiles * (a.Cout / c);
+      const long waves = (tiles + sm_count - 1) / sm_count;
+      const long cyc = c / 2 > 32 + c / 4 ? c / 2 : 32 + c / 4;
+      const long cost = waves * (ksteps * cyc + 1500);
+      // a narrower block must pay clearly (>= 10 %): it re-reads every activation tile once more per halving
+      if (best_cost < 0 || cost * 10 < best_cost * 9) { best_cost = cost; best_bn = c; }
+    }
+    const char* e = getenv("B2C_TC_BNWAVE");
+    if (e && e[0] == '0') {                       // the round-1 rule: narrower blocks only while the GPU is not full
+      const long mt = (long)a.B * a.n_phase * ((a.Lj + TC_BM - 1) / TC_BM);
+      while (bn > 64 && (bn / 2) % 32 == 0 && a.Cout % (bn / 2) == 0 && mt * (a.Cout / bn) * 2 <= sm_count) bn /= 2;
+    } else {
+      bn = best_bn;
+    }
   }
   if (!tc_encode_fn()) return -10;
   TcConvParams& p = plan->p;
@@ -1347,6 +1402,21 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
       }
     }
   }
+  // frame-packed tiles (TcConvParams::JB): the generic kernel, more than one frame, and fewer tiles than 128 positions of
+  // one frame per tile give.  B2C_TC_PACK=0 off.
+  if (!plan->slab) {
+    int best_jb = 0;
+    const long best = tc_best_pack(a.Lj, a.B, &best_jb);
+    if (best_jb) {
+      p.JB = best_jb; p.BB = TC_BM / best_jb;
+      p.jb_shift = 0;
+      while ((1 << p.jb_shift) < best_jb) ++p.jb_shift;
+      p.tiles_j = (a.Lj + p.JB - 1) / p.JB;
+      const long tot = best * a.n_phase * p.n_ntiles;
+      p.total_tiles = (int)tot;
+      plan->grid = (int)(tot < sm_count ? tot : sm_count);
+    }
+  }
   return 0;
 }
 
@@ -1388,14 +1458,14 @@ inline int tc_conv_launch(TcConvPlan& plan, const ConvArgs& a, const float* inv_
     if (p.in_step == 1) {
       cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Lin, (cuuint64_t)p.B};
       cuuint64_t str[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
-      cuuint32_t box[3] = {(cuuint32_t)p.BK, (cuuint32_t)(plan.slab ? p.box_rows : TC_BM), 1};
+      cuuint32_t box[3] = {(cuuint32_t)p.BK, (cuuint32_t)(plan.slab ? p.box_rows : (p.JB ? p.JB : TC_BM)), (cuuint32_t)(p.JB ? p.BB : 1)};
       rc = tc_encode(&plan.mA_hi, xh, 3, dims, str, box, p.BK);
       if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 3, dims, str, box, p.BK);
     } else {
       const int S = p.in_step;
       cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)S, (cuuint64_t)(p.Lin / S), (cuuint64_t)p.B};
       cuuint64_t str[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)S * p.Cin * 2, (cuuint64_t)p.Lin * p.Cin * 2};
-      cuuint32_t box[4] = {(cuuint32_t)p.BK, 1, TC_BM, 1};
+      cuuint32_t box[4] = {(cuuint32_t)p.BK, 1, (cuuint32_t)(p.JB ? p.JB : TC_BM), (cuuint32_t)(p.JB ? p.BB : 1)};
       rc = tc_encode(&plan.mA_hi, xh, 4, dims, str, box, p.BK);
       if (!rc) rc = tc_encode(&plan.mA_lo, plan.x3 ? xl : xh, 4, dims, str, box, p.BK);
     }
