@@ -1204,6 +1204,17 @@ inline bool tc_conv_eligible(const TcWeight& w, int cin, int cout, int stride, i
   return true;
 }
 
+// a narrower channel block is taken when its modelled cost is below this percentage of the wider one's (B2C_TC_BNWAVE_PCT)
+inline long tc_bnwave_pct() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_TC_BNWAVE_PCT");
+    v = e ? atol(e) : 90;
+    if (v < 1 || v > 100) v = 90;
+  }
+  return v;
+}
+
 // fewest M tiles of the generic kernel for Lj positions x B frames: 128 positions of one frame per tile (jb = 0) or
 // frame-packed tiles of jb positions x 128 / jb frames (TcConvParams::JB)
 inline long tc_best_pack(int Lj, int B, int* jb_out) {
@@ -1244,7 +1255,7 @@ inline int tc_conv_plan(const ConvArgs& a, const TcWeight& w, int precision, int
       const long cyc = c / 2 > 32 + c / 4 ? c / 2 : 32 + c / 4;
       const long cost = waves * (ksteps * cyc + 1500);
       // a narrower block must pay clearly (>= 10 %): it re-reads every activation tile once more per halving
-      if (best_cost < 0 || cost * 10 < best_cost * 9) { best_cost = cost; best_bn = c; }
+      if (best_cost < 0 || cost * 100 < best_cost * tc_bnwave_pct()) { best_cost = cost; best_bn = c; }
     }
     const char* e = getenv("B2C_TC_BNWAVE");
     if (e && e[0] == '0') {                       // the round-1 rule: narrower blocks only while the GPU is not full
