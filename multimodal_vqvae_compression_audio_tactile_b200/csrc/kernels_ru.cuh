@@ -225,6 +225,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __shared__ __align__(8) uint64_t bar_w1;
   __shared__ __align__(8) uint64_t bar_rfull[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int stg_lock_s;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: ptxas keeps the role code on the uniform datapath
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -245,6 +246,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t h_total = q.h_plane_bytes * planes;
 
   if (warp == 0 && lane == 0) {
+    stg_lock_s = 0;
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB7_hi); tma_prefetch_desc(&tmB1_hi);
     if (X3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB7_lo); tma_prefetch_desc(&tmB1_lo); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
@@ -583,7 +585,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // two independent 8-warp groups: group g serves this CTA's tiles i = g, g + 2, ... (TMEM buffers acc1[g], acc2[g]);
       // epilogue B of tile i then overlaps epilogue A of tile i + 1.  The single h buffer is handed over by hfull / hempty.
       const int g = (warp - 2) >> 3;
-      float* stg_g = stg + g * (TC_BM * TC_STG_LD);
+      float* stg_g = p.stg_lock ? stg : stg + g * (TC_BM * TC_STG_LD);
       const bool leader = ((threadIdx.x - 64) & 255) == 0;
       for (int i = g; i < my_tiles; i += 2) {
         const int tile = blockIdx.x + i * gridDim.x;
@@ -618,7 +620,8 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           epi_group_sync(g);
           if (leader) mbar_arrive(smem_u32(&bar_t2empty[g]));
         } else {
-          tc_epilogue_tile_g<!X3>(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane);
+          tc_epilogue_tile_g<!X3>(p, stg_g, g, tmem_base + (q.nbuf + g) * p.acc_stride, b, 0, jt, 0, smem_u32(&bar_t2empty[g]), warp, lane,
+                                  p.stg_lock ? &stg_lock_s : nullptr);
         }
         if (leader) ru_trace(p.dbg, 2 + g, tcnt, 25, i);
       }
@@ -828,6 +831,9 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   {
     const char* e = getenv("B2C_TC_EPI2");
     p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !q.direct && !(e && e[0] == '0')) ? 2 : 1;
+    // resident weights leave room for ONE staging tile: the two groups then share it under a lock (B2C_RU_STGLOCK=0: lock-step)
+    const char* el = getenv("B2C_RU_STGLOCK");
+    if (q.w7_resident && q.nbuf == 2 && p.stg_bufs == 1 && !(e && e[0] == '0') && !(el && el[0] == '0')) { p.epi_groups = 2; p.stg_lock = 1; }
   }
   p.tiles_j = (L + TC_BM - 1) / TC_BM;
   p.n_ntiles = 1;

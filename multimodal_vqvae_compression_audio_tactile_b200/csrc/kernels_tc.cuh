@@ -314,6 +314,7 @@ struct TcConvParams {
   // tensor map's out-of-bounds fill.  JB == 0: the legacy tile (JB = 128, BB = 1).  Rows are independent in an MMA, so
   // a frame's bits do not depend on how tiles are packed.
   int JB, jb_shift, BB;
+  int stg_lock;   // fused unit: two epilogue groups share one staging tile under a shared-memory lock
 };
 
 // tile (frame-group index bg, position-tile index jt), row m of the tile -> frame b and position j
@@ -486,9 +487,12 @@ __device__ __forceinline__ void tc_prefetch_res_g(const TcConvParams& p, int b, 
   }
 }
 
+// `lock` != nullptr: both groups share ONE staging tile (shared memory has no room for two): a group owns it only from
+// its TMEM registers -> staging write to the row-major re-read (a few hundred cycles per chunk); the loads before and
+// the arithmetic and stores after run from registers, outside the critical section.
 template <int SFU, int DM = 0>
 __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float* stg_g, int g, uint32_t t_acc, int b, int ph,
-                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane) {
+                                                   int jt, int nt, uint32_t tempty_bar, int warp, int lane, int* lock = nullptr) {
   const int wg = (warp - 2) & 7;
   const int quad = warp & 3;
   const int half = wg >> 2;
@@ -537,6 +541,13 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
 #pragma unroll
         for (int u = 0; u < 16; ++u) v[u] += v2[u];
       }
+      if (lock) {                                         // acquire the shared staging tile
+        if (et == 0) {
+          while (atomicCAS(lock, 0, 1) != 0) {}
+          __threadfence_block();
+        }
+        epi_group_sync(g);
+      }
       float* dst = stg_g + (quad * 32 + lane) * TC_STG_LD + half * 16;
 #pragma unroll
       for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
@@ -545,10 +556,20 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
     if (last) tc_fence_before();
     epi_group_sync(g);
     if (last && et == 0) mbar_arrive(tempty_bar);
+    float4 acc4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc4[i] = *reinterpret_cast<const float4*>(stg_g + (r0 + 32 * i) * TC_STG_LD + cq * 4);
+    if (lock) {                                           // every thread has its rows in registers: release
+      epi_group_sync(g);
+      if (et == 0) {
+        __threadfence_block();
+        atomicExch(lock, 0);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (!valid[i]) continue;
-      float4 a = *reinterpret_cast<const float4*>(stg_g + (r0 + 32 * i) * TC_STG_LD + cq * 4);
+      float4 a = acc4[i];
       a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
       if (DM) {
         a.x *= dsnake_pre(dm[i].x, al.x, ia.x); a.y *= dsnake_pre(dm[i].y, al.y, ia.y);
@@ -582,7 +603,7 @@ __device__ __forceinline__ void tc_epilogue_tile_g(const TcConvParams& p, float*
         }
       }
     }
-    epi_group_sync(g);   // the group's staging tile is rewritten by the next chunk
+    if (!lock) epi_group_sync(g);   // the group's staging tile is rewritten by the next chunk (lock mode: the acquire orders it)
   }
 }
 
