@@ -833,7 +833,8 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
     p.epi_groups = (q.nbuf == 2 && p.stg_bufs == 2 && !q.direct && !(e && e[0] == '0')) ? 2 : 1;
     // resident weights leave room for ONE staging tile: the two groups then share it under a lock (B2C_RU_STGLOCK=0: lock-step)
     const char* el = getenv("B2C_RU_STGLOCK");
-    if (q.w7_resident && q.nbuf == 2 && p.stg_bufs == 1 && !(e && e[0] == '0') && !(el && el[0] == '0')) { p.epi_groups = 2; p.stg_lock = 1; }
+    const bool lock_ok = q.w7_resident || (el && el[0] == '2');      // B2C_RU_STGLOCK=2: every unit with one staging tile (experiment)
+    if (lock_ok && q.nbuf == 2 && p.stg_bufs == 1 && !q.direct && !(e && e[0] == '0') && !(el && el[0] == '0')) { p.epi_groups = 2; p.stg_lock = 1; }
   }
   p.tiles_j = (L + TC_BM - 1) / TC_BM;
   p.n_ntiles = 1;
