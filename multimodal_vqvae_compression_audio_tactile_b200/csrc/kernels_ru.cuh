@@ -11,6 +11,13 @@
 // one launch.  Warp roles as conv_tc_kernel.  With 4*S <= 512 TMEM columns (C <= 128) acc1 and acc2 are double
 // buffered and GEMM 1 of tile i+1 is issued BEFORE GEMM 2 of tile i, so the tensor pipe works while the epilogue
 // warps produce h(i).
+//
+// Pipeline variants (selected per shape by tc_ru_plan; tests/test_gpu_parity.py::test_fused_unit_kernel_variants_agree):
+//   ring            activation tiles (or one slab per channel block) and weight tiles stream through the TMA ring;
+//   w1_resident     W1 stays in shared memory, GEMM 2 is issued between two ring stages of the next tile's GEMM 1;
+//   w7_resident     W7 and W1 stay in shared memory (C = 64 bf16x3): no weight ring, half-channel activation slabs only,
+//                   the two epilogue groups share the one staging tile that still fits (TcConvParams::stg_lock);
+//   direct          epilogue B through the copy engine (TMA residual in, TMA stores out): measured slower, experiment only.
 #pragma once
 #include "kernels_tc.cuh"
 
