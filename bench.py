@@ -36,9 +36,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="frames per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=64,
-                    help="frames per program run (64: measured +7 %% over 32 -- fewer partial waves of tiles on 148 SMs)")
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=128,
+                    help="frames per program run (64: +7 %% over 32, 128: +1 %% over 64 -- fewer partial waves of tiles on 148 "
+                         "SMs; two programs per step keep the host copies of the e2e leg under the other program)")
     ap.add_argument("--precision", default=os.environ.get("B2C_PRECISION", "auto"))
     ap.add_argument("--cpu-sample", type=int, default=8, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -478,9 +479,10 @@ def main():
     # it was captured at
     traffic, traffic_src = None, None
     traffic_alg = dd["bytes"] / dd["launches"]
-    for name in ("r02_ncu_dram_traffic_conv_mb64.json", "r01_ncu_dram_traffic_conv_mb64.json"):
+    for name, mb_file in (("r02_ncu_dram_traffic_conv_mb128.json", 128), ("r02_ncu_dram_traffic_conv_mb64.json", 64),
+                          ("r01_ncu_dram_traffic_conv_mb64.json", 64)):
         tp = os.path.join(ROOT, "profiles", name)
-        if os.path.isfile(tp) and mb == 64 and dom == "conv_tc_x3":
+        if os.path.isfile(tp) and mb == mb_file and dom == "conv_tc_x3":
             try:
                 traffic = json.load(open(tp))["x3"]["dram_bytes_per_launch"]
                 traffic_src = "profiles/" + name

@@ -108,31 +108,33 @@ def test_codec_against_golden(name, plan, dev, golden_dir, oracle_models):
         compare_frames(y, idx, codes, z, tr, plan, name)
 
 
-@pytest.mark.parametrize("which", ["bench", "calibrated"])
+@pytest.mark.parametrize("which", ["bench", "bench64", "calibrated"])
 def test_benchmarked_configuration_against_oracle(which, dev, oracle_models):
-    """The configuration bench.py times (books 8, K 512, plan tc, 64 frames per program) has its own oracle check:
-    frames 0, 31 and 63 of a 64-frame program against the oracle run on those frames alone.  'bench' uses bench.py's
-    exact model and inputs (random-init codebooks, U(-1,1), generator seed 123 = rank 0); 'calibrated' the same
-    shapes with codebooks every stage of which has many live codes."""
-    if which == "bench":
+    """The configuration bench.py times (books 8, K 512, plan tc, 128 frames per program; 64 in round 1) has its own
+    oracle check: the first, a middle and the last frame of the program against the oracle run on those frames alone.
+    'bench' / 'bench64' use bench.py's exact model and inputs (random-init codebooks, U(-1,1), generator seed 123 = rank
+    0; the first 128 / 64 frames of its 256-frame step); 'calibrated' the same shapes with codebooks every stage of
+    which has many live codes (64 frames)."""
+    nf = 128 if which == "bench" else 64
+    if which in ("bench", "bench64"):
         case = dict(books=8, K=512)
         ref = cases.build_reference_style_model(proposed.ProposedEval, case)      # bench.build_oracle()
         g = torch.Generator().manual_seed(123)
-        a = (torch.rand(128, 1, 24000, generator=g) * 2 - 1)[:64]
-        t = (torch.rand(128, 1, 24000, generator=g) * 2 - 1)[:64]
+        a = (torch.rand(256, 1, 24000, generator=g) * 2 - 1)[:nf]
+        t = (torch.rand(256, 1, 24000, generator=g) * 2 - 1)[:nf]
     else:
         case = cases.CODEC_CASES["cal_b8k512"]
         ref = oracle_models("cal_b8k512")
-        a, t = cases.codec_inputs(dict(case, B=64))
+        a, t = cases.codec_inputs(dict(case, B=nf))
     net = gpu_model(ref, case, "tc")
-    net.micro_batch = 64
+    net.micro_batch = nf
     y = net.forward_eval(a.to(dev), t.to(dev)).cpu()
     idx, codes = net.last_indices.cpu().long(), net.last_audio_codes.cpu().long()
     eng, pk = net._engine(dev)
-    assert any(k[0] == "codec" and k[1] == 64 for k in eng.programs._d), "the 64-frame program must be the one that ran"
+    assert any(k[0] == "codec" and k[1] == nf for k in eng.programs._d), f"the {nf}-frame program must be the one that ran"
     assert eng.fp32_reroutes == [], eng.fp32_reroutes
     n_exact = 0
-    for f in (0, 31, 63):
+    for f in (0, nf // 2 - 1, nf - 1):
         tr = {}
         ref.forward_eval(a[f:f + 1], t[f:f + 1], None, trace=tr)
         res = compare_frames(y[f:f + 1], idx[f:f + 1], codes[f:f + 1], None, tr, "tc", f"{which} frame {f}")

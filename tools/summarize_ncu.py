@@ -87,3 +87,9 @@ def traffic(src, dst):
 
 if __name__ == "__main__":
     {"launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if len(sys.argv) > 4:      # the command / note of THIS capture instead of the round-1 defaults
+        d = json.load(open(sys.argv[3]))
+        d["command"] = sys.argv[4]
+        if len(sys.argv) > 5:
+            d["note"] = sys.argv[5]
+        json.dump(d, open(sys.argv[3], "w"), indent=1)
