@@ -731,7 +731,11 @@ inline int tc_ru_plan(int B, int L, int C, int dil, const TcWeight& w7, const Tc
   // (352 -> 176 KB of shared-memory fill per 64-channel bf16x3 tile).  Measured on B200 once the MMA issue loop was
   // off the critical path: 64-ch bf16x3 0.285 -> 0.264 ms; 128-ch bf16x3 0.330 -> 0.375 and 96-ch bf16 0.308 -> 0.351
   // (the slab slots cost those shapes ring stages).  Hence: on for C = 64 bf16x3 only; B2C_RU_SLAB=0/1 overrides.
-  bool want_slab = (C == 64 && plan->x3);
+  // ... and, measured in the power-capped steady state (tools/power_probe.py loops a launch for seconds; the burst
+  // timing of tools/tc_selftest.py says the opposite): C = 192 bf16 0.741 -> 0.710 ms at all three dilations -- the slab
+  // removes six of the seven activation fetches per tile from the L2 -> shared-memory path, the board draws less and the
+  // governor gives 45 MHz back.
+  bool want_slab = (C == 64 && plan->x3) || (C == 192 && !plan->x3);
   {
     const char* e = getenv("B2C_RU_SLAB");
     if (e && e[0] == '1') want_slab = true;

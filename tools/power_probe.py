@@ -119,7 +119,10 @@ conv_case("enc4 k7 C512", enc[4].block[0].block[1], 600, "bf16x3")
 conv_case("dec1 k7 C768", dec[1].block[2].block[1], 600, "bf16")
 conv_case("dec2 k7 C384", dec[2].block[2].block[1], 2999, "bf16")
 ru_case("ru.dec3.d1 C192", dec[3].block[2], 11996, "bf16")
+ru_case("ru.dec3.d3 C192", dec[3].block[3], 11996, "bf16")
+ru_case("ru.dec3.d9 C192", dec[3].block[4], 11996, "bf16")
 ru_case("ru.dec4.d1 C96", dec[4].block[2], 23992, "bf16")
+ru_case("ru.dec4.d9 C96", dec[4].block[4], 23992, "bf16")
 # whole codec program
 if a.no_program:
     S.p.terminate(); sys.exit(0)
