@@ -94,6 +94,26 @@ class ClockSampler:
                     samples=len(self.rows))
 
 
+TRAFFIC_CAPTURES = (("r02_ncu_dram_traffic_conv_mb128.json", 128), ("r02_ncu_dram_traffic_conv_mb64.json", 64),
+                    ("r01_ncu_dram_traffic_conv_mb64.json", 64))
+
+
+def pick_traffic(micro_batch: int, family: str, profiles_dir: str = None):
+    """DRAM bytes per launch of the dominant family from the committed ncu capture taken at THIS micro-batch (bytes per
+    launch scale with it); (None, None) when there is no capture for it or the dominant family is not the bf16x3 one."""
+    d = profiles_dir or os.path.join(ROOT, "profiles")
+    if family != "conv_tc_x3":
+        return None, None
+    for name, mb_file in TRAFFIC_CAPTURES:
+        tp = os.path.join(d, name)
+        if mb_file == micro_batch and os.path.isfile(tp):
+            try:
+                return json.load(open(tp))["x3"]["dram_bytes_per_launch"], "profiles/" + name
+            except Exception:
+                continue
+    return None, None
+
+
 def build_oracle():
     from oracle import cases, proposed
     case = dict(books=BOOKS, K=K_CODES)
@@ -477,18 +497,8 @@ def main():
     # DRAM bytes per launch of the dominant family, from the committed ncu capture of this same bench command
     # (dram__bytes_read.sum + dram__bytes_write.sum of every launch of one program); only valid for the micro-batch
     # it was captured at
-    traffic, traffic_src = None, None
     traffic_alg = dd["bytes"] / dd["launches"]
-    for name, mb_file in (("r02_ncu_dram_traffic_conv_mb128.json", 128), ("r02_ncu_dram_traffic_conv_mb64.json", 64),
-                          ("r01_ncu_dram_traffic_conv_mb64.json", 64)):
-        tp = os.path.join(ROOT, "profiles", name)
-        if os.path.isfile(tp) and mb == mb_file and dom == "conv_tc_x3":
-            try:
-                traffic = json.load(open(tp))["x3"]["dram_bytes_per_launch"]
-                traffic_src = "profiles/" + name
-                break
-            except Exception:
-                traffic = None
+    traffic, traffic_src = pick_traffic(mb, dom)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sus"], "traffic": traffic, "traffic_algorithmic": traffic_alg,
                 "traffic_source": traffic_src,

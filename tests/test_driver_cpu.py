@@ -59,3 +59,26 @@ def test_sharded_codec_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_bench_picks_the_traffic_capture_of_its_micro_batch(tmp_path):
+    """bench.py's roofline.traffic must come from an ncu capture taken at the micro-batch it runs (bytes per launch scale
+    with it), and only for the bf16x3 family the captures cover."""
+    import json
+    import bench
+    (tmp_path / "r02_ncu_dram_traffic_conv_mb128.json").write_text(json.dumps({"x3": {"dram_bytes_per_launch": 2.0}}))
+    (tmp_path / "r02_ncu_dram_traffic_conv_mb64.json").write_text(json.dumps({"x3": {"dram_bytes_per_launch": 1.0}}))
+    assert bench.pick_traffic(128, "conv_tc_x3", str(tmp_path)) == (2.0, "profiles/r02_ncu_dram_traffic_conv_mb128.json")
+    assert bench.pick_traffic(64, "conv_tc_x3", str(tmp_path)) == (1.0, "profiles/r02_ncu_dram_traffic_conv_mb64.json")
+    assert bench.pick_traffic(32, "conv_tc_x3", str(tmp_path)) == (None, None)
+    assert bench.pick_traffic(128, "conv_tc", str(tmp_path)) == (None, None)
+    # the committed captures exist for the default step (two programs of 128) and for round 1's 64
+    assert bench.pick_traffic(128, "conv_tc_x3")[0] and bench.pick_traffic(64, "conv_tc_x3")[0]
+    assert bench.parse.__defaults__ is None           # defaults live in argparse: check them there
+    import sys
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        a = bench.parse()
+    finally:
+        sys.argv = argv
+    assert a.batch == 2 * a.micro_batch and bench.pick_traffic(a.micro_batch, "conv_tc_x3")[0]
